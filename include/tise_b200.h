@@ -1,0 +1,161 @@
+/*
+ * tise_b200.h -- C ABI of libtise_b200.so: the B200 (sm_100a) implementation of TISE's
+ * image-realism hot path (Inception-v3 features -> FID / O-FID moments + Frechet distance,
+ * IS / IS* / O-IS temperature-softmax + KL partial sums).
+ *
+ * The reference (VinAIResearch/tise-toolbox) is pure Python and has no FFI; the boundary it
+ * offers is the Python call surface of image_realism/FID/fid_score.py, inception.py,
+ * img_data.py, object_fidelity/O-IS/object_centric_inception_score.py and the two IS*
+ * scripts.  Each entry point below names the reference code it replaces (file:line, relative
+ * to the reference root); tise_toolbox_b200/*.py binds them with ctypes and re-exposes the
+ * reference's Python names.  INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (TISE_OK) or a negative tise_status; nothing throws or exits;
+ *     tise_last_error(ctx) holds a human-readable message for the last failure on that ctx.
+ *   - "d_" pointers are device pointers on ctx's device, "h_" pointers are host pointers.
+ *   - the caller owns every buffer, including workspaces (sizes from *_workspace_bytes);
+ *     only the packed network weights are owned by the ctx.
+ *   - all work is enqueued on the given stream; no call synchronises the device unless its
+ *     comment says so.  One ctx per (device, host thread); there is no global mutable state.
+ *   - there is no CPU fallback: without a CUDA device every compute call returns TISE_ERR_CUDA.
+ */
+#ifndef TISE_B200_H
+#define TISE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tise_ctx tise_ctx;
+typedef void* tise_stream; /* cudaStream_t */
+
+typedef enum {
+  TISE_OK = 0,
+  TISE_ERR_INVALID = -1,   /* bad argument (shape, null pointer, unknown weight name) */
+  TISE_ERR_CUDA = -2,      /* CUDA runtime / driver error, or no device */
+  TISE_ERR_WORKSPACE = -3, /* workspace too small */
+  TISE_ERR_STATE = -4,     /* call order (e.g. forward before weights are loaded) */
+  TISE_ERR_NUMERIC = -5    /* non-finite intermediate in tise_frechet */
+} tise_status;
+
+/* Feature taps, image_realism/FID/inception.py:14-19 (BLOCK_INDEX_BY_DIM). */
+typedef enum { TISE_TAP_64 = 0, TISE_TAP_192 = 1, TISE_TAP_768 = 2, TISE_TAP_2048 = 3 } tise_tap;
+
+/* Convolution engine.  TISE_CONV_UMMA is the product path (tcgen05 implicit GEMM);
+ * TISE_CONV_SIMT is a slow same-numerics CUDA-core kernel kept for on-device cross checks. */
+typedef enum { TISE_CONV_UMMA = 0, TISE_CONV_SIMT = 1 } tise_conv_impl;
+
+int tise_version(void);
+const char* tise_status_string(int status);
+
+/* ---- context -------------------------------------------------------------------------- */
+int tise_ctx_create(int device, tise_ctx** out);
+void tise_ctx_destroy(tise_ctx* ctx);
+const char* tise_last_error(const tise_ctx* ctx);
+
+/* conv engine (default TISE_CONV_UMMA) and operand passes: 2 = fp16 activations x (hi+lo) fp16
+ * weights, fp32 TMEM accumulation (default; FID within 1e-4 of fp32), 1 = single fp16 pass. */
+int tise_set_conv_mode(tise_ctx* ctx, int impl, int passes);
+
+/* ---- weights -------------------------------------------------------------------------- */
+/* One tensor of a torchvision Inception3 state_dict (fp32, host, contiguous), e.g.
+ * "Mixed_5b.branch1x1.conv.weight", "....bn.running_var", "fc.weight", "fc.bias".
+ * Replaces models.inception_v3(pretrained=True) + load_state_dict at
+ * image_realism/FID/inception.py:57 and object_centric_inception_score.py:42-46. */
+typedef struct {
+  const char* name;
+  const float* data;
+  int64_t numel;
+} tise_weight_desc;
+
+/* Folds eval-mode BatchNorm (eps = 1e-3) into per-channel scale/shift, splits every conv weight
+ * into fp16 hi + lo planes in the K-major layout the UMMA kernels read, uploads everything to
+ * ctx-owned device memory.  num_classes = rows of fc.weight (0: no classifier head).
+ * Synchronises the device. */
+int tise_load_inception(tise_ctx* ctx, const tise_weight_desc* tensors, int n_tensors, int num_classes);
+
+/* ---- A2: Pillow-exact bilinear resize to 299x299 ---------------------------------------- */
+/* transforms.Resize((299,299)) at fid_score.py:210 / object_centric_inception_score.py:89 and
+ * scipy.misc.imresize at inception_score_star_coco.py:118, inception_score_star_bird.py:67:
+ * Pillow's two-pass fixed-point triangle filter, bit-exact.
+ * d_imgs: packed uint8 HWC RGB images; image i starts at byte h_offsets[i] and has
+ * h_hw[2i] rows x h_hw[2i+1] columns.  If uniform != 0, h_offsets may be NULL and h_hw holds
+ * one (h, w) pair for all images.  d_out: n x 299 x 299 x 3 uint8. */
+size_t tise_resize_workspace_bytes(int n, int max_h, int max_w);
+int tise_resize_u8(tise_ctx* ctx, const uint8_t* d_imgs, const int64_t* h_offsets, const int32_t* h_hw,
+                   int uniform, int n, uint8_t* d_out, void* d_ws, size_t ws_bytes, tise_stream stream);
+
+/* ---- A3/A4: uint8 level -> network input ------------------------------------------------ */
+/* lut[c*256 + v] = float fed to Conv2d_1a_3x3 for channel c and uint8 level v; covers ToTensor
+ * (fid_score.py:211) + the affine at image_realism/FID/inception.py:120-124, or
+ * Normalize(.5,.5) (object_centric_inception_score.py:91), or x/127.5-1
+ * (inception_score_star_bird.py:70), or the coco graph's (x-128)/128. */
+int tise_set_input_lut(tise_ctx* ctx, const float* h_lut768);
+
+/* ---- A5/A6: Inception-v3 trunk ----------------------------------------------------------- */
+/* InceptionV3.forward (image_realism/FID/inception.py:100-134) for n images.
+ * Exactly one of d_u8 (n x 299 x 299 x 3 uint8, goes through the LUT) and d_f32
+ * (n x 3 x 299 x 299 float, already normalised, as the reference's model(batch) receives after
+ * its pre-amble) must be non-NULL.  d_feat: n x dims(tap) float32, the (spatially averaged)
+ * output of the requested block: TISE_TAP_2048 is pool3. */
+size_t tise_inception_workspace_bytes(const tise_ctx* ctx, int n);
+int tise_inception_features(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, int tap,
+                            float* d_feat, void* d_ws, size_t ws_bytes, tise_stream stream);
+
+/* fc head: d_logits[n x num_classes] = d_feat[n x 2048] . fc.weight^T (+ fc.bias if use_bias).
+ * object_centric_inception_score.py:52 (with bias), inception_score_star_coco.py:104-105
+ * (no bias), inception_score_star_bird.py:181-186 (with bias). */
+int tise_logits(tise_ctx* ctx, const float* d_feat, int n, int use_bias, float* d_logits, tise_stream stream);
+
+/* ---- A7: activation statistics ------------------------------------------------------------ */
+/* One-pass replacement of np.mean / np.cov at fid_score.py:194-195: adds this batch's
+ * sum_i x_i into d_sum[d] and sum_i x_i x_i^T into the LOWER triangle of d_sxx[d x d]
+ * (fp64 accumulation of exact fp32 products; buffers must be zeroed by the caller first). */
+int tise_moments_update(tise_ctx* ctx, const float* d_feat, int n, int d, double* d_sum, double* d_sxx,
+                        tise_stream stream);
+/* mu = sum / count, sigma = (sxx - count mu mu^T) / (count - 1), full symmetric matrix. */
+int tise_moments_finalize(tise_ctx* ctx, const double* d_sum, const double* d_sxx, int64_t count, int d,
+                          double* d_mu, double* d_sigma, tise_stream stream);
+
+/* ---- A11-A13: inception score partial sums ------------------------------------------------- */
+/* For each image i with split s = d_split_id[i] >= 0: p = softmax(logits[i, class_offset:C] / T)
+ * (fp32, like the reference), then d_splogp[s] += sum_c p_c log p_c, d_marg[s*Cs + c] += p_c,
+ * d_cnt[s] += 1, d_zeros[0] += #(p_c == 0)   (fp64 / int64 accumulators, Cs = C - class_offset).
+ * Replaces object_centric_inception_score.py:54-57,72-79,
+ * inception_score_star_coco.py:53-58, inception_score_star_bird.py:98-105. */
+int tise_is_update(tise_ctx* ctx, const float* d_logits, int n, int C, int class_offset, float temperature,
+                   const int32_t* d_split_id, int n_splits, double* d_splogp, double* d_marg,
+                   long long* d_cnt, long long* d_zeros, tise_stream stream);
+
+/* ---- A9: Frechet distance ------------------------------------------------------------------- */
+/* calculate_frechet_distance (fid_score.py:121-171):
+ *   |mu1-mu2|^2 + tr(s1) + tr(s2) - 2 tr sqrt(s1 s2),
+ * with tr sqrt(s1 s2) evaluated in fp64 on the device as the sum of square roots of the
+ * eigenvalues of the symmetric matrix L^T s2 L (s1 + delta I = L L^T), which equal those of s1 s2.
+ * Writes the scalar to *h_fid (host) and synchronises the stream.  flags bit0: a non-finite
+ * value appeared and the eps-regularised retry of fid_score.py:156-160 was taken. */
+size_t tise_frechet_workspace_bytes(int d);
+int tise_frechet(tise_ctx* ctx, const double* d_mu1, const double* d_sigma1, const double* d_mu2,
+                 const double* d_sigma2, int d, double eps, double* h_fid, int* h_flags, void* d_ws,
+                 size_t ws_bytes, tise_stream stream);
+
+/* ---- diagnostics ------------------------------------------------------------------------------ */
+/* One Conv2d(bias=False)+scale/shift+ReLU layer through the selected engine, used by the tests to
+ * check the UMMA kernels shape by shape.  x: n x h x w x cin fp16 NHWC (device); w: cout x cin x kh x kw
+ * fp32 (host); scale/shift: cout fp32 (host); y: n x ho x wo x cout fp16 NHWC (device).
+ * Synchronises the device. */
+int tise_debug_conv(tise_ctx* ctx, int impl, int passes, const void* d_x, int n, int h, int w, int cin,
+                    const float* h_w, const float* h_scale, const float* h_shift, int cout, int kh, int kw,
+                    int stride, int pad_h, int pad_w, int relu, void* d_y);
+
+/* Number of kernels this library has launched on this ctx since creation (for bench.py's gpu_launches). */
+long long tise_launch_count(const tise_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TISE_B200_H */

@@ -1,0 +1,116 @@
+// Shared declarations of libtise_b200.so (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/tise_b200.h"
+
+namespace tise {
+
+constexpr int kOutSize = 299;       // network input side
+constexpr int kNumSMsDefault = 148; // B200
+
+struct Net;  // net.cu
+
+}  // namespace tise
+
+struct tise_ctx {
+  int device = 0;
+  int num_sms = tise::kNumSMsDefault;
+  int smem_optin = 0;
+  std::string err;
+  long long launches = 0;
+  int conv_impl = TISE_CONV_UMMA;
+  int passes = 2;
+  float* d_lut = nullptr;  // 768 floats
+  bool lut_set = false;
+  tise::Net* net = nullptr;
+};
+
+namespace tise {
+
+int fail(tise_ctx* ctx, int status, const char* fmt, ...);
+
+#define TISE_CUDA(ctx, call)                                                                       \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return tise::fail(ctx, TISE_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,   \
+                        cudaGetErrorString(e__));                                                  \
+  } while (0)
+
+#define TISE_LAUNCH_CHECK(ctx)                                                                     \
+  do {                                                                                             \
+    (ctx)->launches++;                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess)                                                                        \
+      return tise::fail(ctx, TISE_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__,         \
+                        __LINE__, cudaGetErrorString(e__));                                        \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// One convolution layer, packed for the device (net.cu / conv_*.cu).
+// Weights are K-major [cout][taps * cin_pad] fp16 with k = (r * S + s) * cin_pad + ci, split into
+// hi = fp16(w * 2^e[co]) and lo = fp16(w * 2^e[co] - hi); scale already contains 2^-e[co].
+// ---------------------------------------------------------------------------------------------
+struct ConvLayer {
+  int cin = 0, cout = 0, R = 1, S = 1, stride = 1, pad_h = 0, pad_w = 0;
+  int cin_pad = 0;          // cin rounded up to 64
+  int ktot = 0;             // R * S * cin_pad
+  __half* d_whi = nullptr;  // [cout][ktot]
+  __half* d_wlo = nullptr;
+  float* d_scale = nullptr;  // [cout]  gamma / sqrt(var + eps) * 2^-e
+  float* d_shift = nullptr;  // [cout]  beta - mean * gamma / sqrt(var + eps)
+};
+
+// A conv launch: NHWC fp16 input view -> NHWC output view (fp16, or fp32 if out_f32).
+struct ConvArgs {
+  const __half* in = nullptr;  // base of the input tensor (channel 0 of the view)
+  int n = 0, h = 0, w = 0;     // input spatial dims
+  int in_stride = 0;           // elements per input pixel (>= cin)
+  void* out = nullptr;         // base of the output tensor + channel offset already applied
+  int out_stride = 0;          // elements per output pixel
+  int out_f32 = 0;
+  int relu = 1;
+  int ho = 0, wo = 0;
+};
+
+int conv_out_dim(int in, int k, int stride, int pad);
+
+// conv_simt.cu
+int launch_conv_simt(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, cudaStream_t st);
+// conv_umma.cu
+struct UmmaPlan {  // tensor maps are tied to pointers, so a plan is built once per (layer, buffers)
+  alignas(64) CUtensorMap tm_a;
+  alignas(64) CUtensorMap tm_bhi;
+  alignas(64) CUtensorMap tm_blo;
+  bool valid = false;
+};
+int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPlan* plan);
+int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const UmmaPlan& plan, int passes,
+                     cudaStream_t st);
+
+// stem.cu : Conv2d_1a_3x3 (3->32, 3x3, stride 2) fused with the uint8 LUT / float input
+int launch_stem(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, const float* d_w /*[27][32]*/,
+                const float* d_scale, const float* d_shift, __half* d_out, cudaStream_t st);
+
+// pool.cu
+int launch_maxpool3s2(tise_ctx* ctx, const __half* in, int n, int h, int w, int c, int in_stride, __half* out,
+                      int out_stride, cudaStream_t st);
+int launch_avgpool3s1p1(tise_ctx* ctx, const __half* in, int n, int h, int w, int c, int in_stride, __half* out,
+                        int out_stride, cudaStream_t st);
+int launch_global_avgpool(tise_ctx* ctx, const void* in, int in_f32, int n, int hw, int c, int in_stride,
+                          float* out, cudaStream_t st);
+
+// resize.cu / stats.cu / frechet.cu entry points are the C ABI functions themselves.
+
+}  // namespace tise

@@ -1,0 +1,469 @@
+// Inception-v3 trunk: weight packing, workspace plan and forward (host side).
+// Topology = torchvision.models.Inception3 as wired by image_realism/FID/inception.py:59-95
+// (block0: Conv2d_1a/2a/2b + maxpool, block1: Conv2d_3b/4a + maxpool, block2: Mixed_5b..6e,
+//  block3: Mixed_7a..7c + adaptive avg pool).  Branch outputs are written straight into channel
+// slices of the block output, in torch.cat order.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "net.cuh"
+
+namespace tise {
+
+int fail(tise_ctx* ctx, int status, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return status;
+}
+
+int conv_out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
+
+static int dev_alloc(tise_ctx* ctx, std::vector<void*>* allocs, void** p, size_t bytes) {
+  TISE_CUDA(ctx, cudaMalloc(p, bytes));
+  allocs->push_back(*p);
+  return TISE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packing: w [cout][cin][R][S] fp32 -> hi/lo fp16 planes [cout][(r*S+s)*cin_pad + ci], each output
+// channel scaled by 2^e so that its largest |w| lands in [2^11, 2^12): the lo plane then stays in
+// fp16's normal range, and 2^-e is folded into the epilogue scale (exact).
+// ---------------------------------------------------------------------------------------------
+int pack_conv_layer(tise_ctx* ctx, ConvLayer* L, const float* w, const float* scale, const float* shift,
+                    std::vector<void*>* allocs) {
+  L->cin_pad = (L->cin + 63) / 64 * 64;
+  L->ktot = L->R * L->S * L->cin_pad;
+  const size_t n = (size_t)L->cout * L->ktot;
+  std::vector<__half> hi(n, __float2half_rn(0.f)), lo(n, __float2half_rn(0.f));
+  std::vector<float> sc(L->cout), sh(L->cout);
+  const int taps = L->R * L->S;
+  for (int co = 0; co < L->cout; ++co) {
+    const float* wc = w + (size_t)co * L->cin * taps;
+    float maxabs = 0.f;
+    for (int i = 0; i < L->cin * taps; ++i) maxabs = fmaxf(maxabs, fabsf(wc[i]));
+    int e = 0;
+    if (maxabs > 0.f && isfinite(maxabs)) e = 11 - ilogbf(maxabs);
+    for (int ci = 0; ci < L->cin; ++ci)
+      for (int t = 0; t < taps; ++t) {
+        const float v = ldexpf(wc[(size_t)ci * taps + t], e);
+        const __half h = __float2half_rn(v);
+        const __half l = __float2half_rn(v - __half2float(h));
+        const size_t k = (size_t)co * L->ktot + (size_t)t * L->cin_pad + ci;
+        hi[k] = h;
+        lo[k] = l;
+      }
+    sc[co] = ldexpf(scale[co], -e);
+    sh[co] = shift[co];
+  }
+  int rc;
+  if ((rc = dev_alloc(ctx, allocs, (void**)&L->d_whi, n * sizeof(__half)))) return rc;
+  if ((rc = dev_alloc(ctx, allocs, (void**)&L->d_wlo, n * sizeof(__half)))) return rc;
+  if ((rc = dev_alloc(ctx, allocs, (void**)&L->d_scale, L->cout * sizeof(float)))) return rc;
+  if ((rc = dev_alloc(ctx, allocs, (void**)&L->d_shift, L->cout * sizeof(float)))) return rc;
+  TISE_CUDA(ctx, cudaMemcpy(L->d_whi, hi.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+  TISE_CUDA(ctx, cudaMemcpy(L->d_wlo, lo.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+  TISE_CUDA(ctx, cudaMemcpy(L->d_scale, sc.data(), L->cout * sizeof(float), cudaMemcpyHostToDevice));
+  TISE_CUDA(ctx, cudaMemcpy(L->d_shift, sh.data(), L->cout * sizeof(float), cudaMemcpyHostToDevice));
+  return TISE_OK;
+}
+
+// eval-mode BatchNorm2d(eps=1e-3) of torchvision BasicConv2d -> per-channel scale / shift
+static int fold_bn(tise_ctx* ctx, Net* net, const std::string& prefix, int cout, std::vector<float>* scale,
+                   std::vector<float>* shift) {
+  const char* names[4] = {".bn.weight", ".bn.bias", ".bn.running_mean", ".bn.running_var"};
+  const std::vector<float>* t[4];
+  for (int i = 0; i < 4; ++i) {
+    auto it = net->raw.find(prefix + names[i]);
+    if (it == net->raw.end() || (int)it->second.size() != cout)
+      return fail(ctx, TISE_ERR_INVALID, "state_dict: missing or mis-sized %s%s", prefix.c_str(), names[i]);
+    t[i] = &it->second;
+  }
+  scale->resize(cout);
+  shift->resize(cout);
+  for (int c = 0; c < cout; ++c) {
+    const double g = (*t[0])[c], b = (*t[1])[c], m = (*t[2])[c], v = (*t[3])[c];
+    const double s = g / sqrt(v + 1e-3);
+    (*scale)[c] = (float)s;
+    (*shift)[c] = (float)(b - m * s);
+  }
+  return TISE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Builder: walks the topology once; creates layers on first sight (net_load) and emits steps.
+// ---------------------------------------------------------------------------------------------
+struct Buf {
+  size_t off;  // per-image byte offset; the buffer of a batch of n starts at ws + off * n
+  int h, w, c, f32;
+};
+struct View {
+  int buf, choff, c;
+};
+
+struct Builder {
+  tise_ctx* ctx;
+  Net* net;
+  Plan* plan;  // may be null (declare-only walk)
+  int n;
+  char* ws;
+  std::vector<Buf> bufs;
+  size_t per_image = 0;
+  int rc = TISE_OK;
+
+  int buf(int h, int w, int c, int f32 = 0) {
+    Buf b{per_image, h, w, c, f32};
+    per_image += align_up((size_t)h * w * c * (f32 ? 4 : 2), 256);
+    bufs.push_back(b);
+    return (int)bufs.size() - 1;
+  }
+  View all(int b) { return View{b, 0, bufs[b].c}; }
+  char* ptr(const View& v) {
+    const Buf& b = bufs[v.buf];
+    return ws + b.off * (size_t)n + (size_t)v.choff * (b.f32 ? 4 : 2);
+  }
+
+  const ConvLayer* layer(const std::string& name, int cin, int cout, int R, int S, int stride, int ph, int pw) {
+    auto it = net->convs.find(name);
+    if (it != net->convs.end()) return &it->second;
+    auto wt = net->raw.find(name + ".conv.weight");
+    if (wt == net->raw.end() || wt->second.size() != (size_t)cout * cin * R * S) {
+      rc = fail(ctx, TISE_ERR_INVALID, "state_dict: missing or mis-sized %s.conv.weight (want %dx%dx%dx%d)",
+                name.c_str(), cout, cin, R, S);
+      return nullptr;
+    }
+    std::vector<float> scale, shift;
+    if ((rc = fold_bn(ctx, net, name, cout, &scale, &shift))) return nullptr;
+    ConvLayer L;
+    L.cin = cin;
+    L.cout = cout;
+    L.R = R;
+    L.S = S;
+    L.stride = stride;
+    L.pad_h = ph;
+    L.pad_w = pw;
+    if ((rc = pack_conv_layer(ctx, &L, wt->second.data(), scale.data(), shift.data(), &net->device_allocs)))
+      return nullptr;
+    return &(net->convs[name] = L);
+  }
+
+  void conv(const std::string& name, View in, View out, int R = 1, int S = 1, int stride = 1, int ph = 0, int pw = 0) {
+    if (rc) return;
+    const Buf& bi = bufs[in.buf];
+    const Buf& bo = bufs[out.buf];
+    const ConvLayer* L = layer(name, in.c, out.c, R, S, stride, ph, pw);
+    if (!L) return;
+    const int ho = conv_out_dim(bi.h, R, stride, ph), wo = conv_out_dim(bi.w, S, stride, pw);
+    if (ho != bo.h || wo != bo.w) {
+      rc = fail(ctx, TISE_ERR_INVALID, "internal: %s output %dx%d does not match buffer %dx%d", name.c_str(), ho, wo,
+                bo.h, bo.w);
+      return;
+    }
+    if (!plan) return;
+    Step s;
+    s.kind = STEP_CONV;
+    s.layer = L;
+    s.conv.in = (const __half*)ptr(in);
+    s.conv.n = n;
+    s.conv.h = bi.h;
+    s.conv.w = bi.w;
+    s.conv.in_stride = bi.c;
+    s.conv.out = ptr(out);
+    s.conv.out_stride = bo.c;
+    s.conv.out_f32 = bo.f32;
+    s.conv.relu = 1;
+    s.conv.ho = ho;
+    s.conv.wo = wo;
+    plan->steps.push_back(s);
+  }
+  void pool(StepKind kind, View in, View out) {
+    if (rc || !plan) return;
+    const Buf& bi = bufs[in.buf];
+    const Buf& bo = bufs[out.buf];
+    Step s;
+    s.kind = kind;
+    s.in = ptr(in);
+    s.out = ptr(out);
+    s.n = n;
+    s.h = bi.h;
+    s.w = bi.w;
+    s.c = in.c;
+    s.in_stride = bi.c;
+    s.out_stride = bo.c;
+    plan->steps.push_back(s);
+  }
+  void gap(View in) {
+    if (rc || !plan) return;
+    const Buf& bi = bufs[in.buf];
+    Step s;
+    s.kind = STEP_GAP;
+    s.in = ptr(in);
+    s.n = n;
+    s.h = bi.h;
+    s.w = bi.w;
+    s.c = in.c;
+    s.in_stride = bi.c;
+    s.in_f32 = bi.f32;
+    plan->steps.push_back(s);
+  }
+
+  // torchvision InceptionA (models/inception.py): cat[branch1x1 64, branch5x5 64, branch3x3dbl 96, branch_pool pf]
+  int inceptionA(const std::string& p, int in, int pf) {
+    const int hw = bufs[in].h, cin = bufs[in].c;
+    const int out = buf(hw, hw, 224 + pf);
+    conv(p + ".branch1x1", all(in), View{out, 0, 64});
+    const int t5 = buf(hw, hw, 48);
+    conv(p + ".branch5x5_1", all(in), all(t5));
+    conv(p + ".branch5x5_2", all(t5), View{out, 64, 64}, 5, 5, 1, 2, 2);
+    const int d1 = buf(hw, hw, 64), d2 = buf(hw, hw, 96);
+    conv(p + ".branch3x3dbl_1", all(in), all(d1));
+    conv(p + ".branch3x3dbl_2", all(d1), all(d2), 3, 3, 1, 1, 1);
+    conv(p + ".branch3x3dbl_3", all(d2), View{out, 128, 96}, 3, 3, 1, 1, 1);
+    const int tp = buf(hw, hw, cin);
+    pool(STEP_AVGPOOL, all(in), all(tp));
+    conv(p + ".branch_pool", all(tp), View{out, 224, pf});
+    return out;
+  }
+  // InceptionB: cat[branch3x3 384 (s2), branch3x3dbl 96 (s2), maxpool cin]
+  int inceptionB(const std::string& p, int in) {
+    const int hw = bufs[in].h, cin = bufs[in].c;
+    const int ho = (hw - 3) / 2 + 1;
+    const int out = buf(ho, ho, 384 + 96 + cin);
+    conv(p + ".branch3x3", all(in), View{out, 0, 384}, 3, 3, 2, 0, 0);
+    const int d1 = buf(hw, hw, 64), d2 = buf(hw, hw, 96);
+    conv(p + ".branch3x3dbl_1", all(in), all(d1));
+    conv(p + ".branch3x3dbl_2", all(d1), all(d2), 3, 3, 1, 1, 1);
+    conv(p + ".branch3x3dbl_3", all(d2), View{out, 384, 96}, 3, 3, 2, 0, 0);
+    pool(STEP_MAXPOOL, all(in), View{out, 480, cin});
+    return out;
+  }
+  // InceptionC: cat[branch1x1 192, branch7x7 192, branch7x7dbl 192, branch_pool 192]
+  int inceptionC(const std::string& p, int in, int c7) {
+    const int hw = bufs[in].h, cin = bufs[in].c;
+    const int out = buf(hw, hw, 768);
+    conv(p + ".branch1x1", all(in), View{out, 0, 192});
+    const int a1 = buf(hw, hw, c7), a2 = buf(hw, hw, c7);
+    conv(p + ".branch7x7_1", all(in), all(a1));
+    conv(p + ".branch7x7_2", all(a1), all(a2), 1, 7, 1, 0, 3);
+    conv(p + ".branch7x7_3", all(a2), View{out, 192, 192}, 7, 1, 1, 3, 0);
+    const int b1 = buf(hw, hw, c7), b2 = buf(hw, hw, c7), b3 = buf(hw, hw, c7), b4 = buf(hw, hw, c7);
+    conv(p + ".branch7x7dbl_1", all(in), all(b1));
+    conv(p + ".branch7x7dbl_2", all(b1), all(b2), 7, 1, 1, 3, 0);
+    conv(p + ".branch7x7dbl_3", all(b2), all(b3), 1, 7, 1, 0, 3);
+    conv(p + ".branch7x7dbl_4", all(b3), all(b4), 7, 1, 1, 3, 0);
+    conv(p + ".branch7x7dbl_5", all(b4), View{out, 384, 192}, 1, 7, 1, 0, 3);
+    const int tp = buf(hw, hw, cin);
+    pool(STEP_AVGPOOL, all(in), all(tp));
+    conv(p + ".branch_pool", all(tp), View{out, 576, 192});
+    return out;
+  }
+  // InceptionD: cat[branch3x3 320 (s2), branch7x7x3 192 (s2), maxpool cin]
+  int inceptionD(const std::string& p, int in) {
+    const int hw = bufs[in].h, cin = bufs[in].c;
+    const int ho = (hw - 3) / 2 + 1;
+    const int out = buf(ho, ho, 320 + 192 + cin);
+    const int a1 = buf(hw, hw, 192);
+    conv(p + ".branch3x3_1", all(in), all(a1));
+    conv(p + ".branch3x3_2", all(a1), View{out, 0, 320}, 3, 3, 2, 0, 0);
+    const int b1 = buf(hw, hw, 192), b2 = buf(hw, hw, 192), b3 = buf(hw, hw, 192);
+    conv(p + ".branch7x7x3_1", all(in), all(b1));
+    conv(p + ".branch7x7x3_2", all(b1), all(b2), 1, 7, 1, 0, 3);
+    conv(p + ".branch7x7x3_3", all(b2), all(b3), 7, 1, 1, 3, 0);
+    conv(p + ".branch7x7x3_4", all(b3), View{out, 320, 192}, 3, 3, 2, 0, 0);
+    pool(STEP_MAXPOOL, all(in), View{out, 512, cin});
+    return out;
+  }
+  // InceptionE: cat[branch1x1 320, branch3x3 (2a|2b) 768, branch3x3dbl (3a|3b) 768, branch_pool 192]
+  int inceptionE(const std::string& p, int in, int out_f32) {
+    const int hw = bufs[in].h, cin = bufs[in].c;
+    const int out = buf(hw, hw, 2048, out_f32);
+    conv(p + ".branch1x1", all(in), View{out, 0, 320});
+    const int a1 = buf(hw, hw, 384);
+    conv(p + ".branch3x3_1", all(in), all(a1));
+    conv(p + ".branch3x3_2a", all(a1), View{out, 320, 384}, 1, 3, 1, 0, 1);
+    conv(p + ".branch3x3_2b", all(a1), View{out, 704, 384}, 3, 1, 1, 1, 0);
+    const int b1 = buf(hw, hw, 448), b2 = buf(hw, hw, 384);
+    conv(p + ".branch3x3dbl_1", all(in), all(b1));
+    conv(p + ".branch3x3dbl_2", all(b1), all(b2), 3, 3, 1, 1, 1);
+    conv(p + ".branch3x3dbl_3a", all(b2), View{out, 1088, 384}, 1, 3, 1, 0, 1);
+    conv(p + ".branch3x3dbl_3b", all(b2), View{out, 1472, 384}, 3, 1, 1, 1, 0);
+    const int tp = buf(hw, hw, cin);
+    pool(STEP_AVGPOOL, all(in), all(tp));
+    conv(p + ".branch_pool", all(tp), View{out, 1856, 192});
+    return out;
+  }
+
+  void walk(int tap) {
+    // block 0
+    const int c1 = buf(149, 149, 32);
+    if (plan) {
+      Step s;
+      s.kind = STEP_STEM;
+      s.out = ptr(all(c1));
+      s.n = n;
+      plan->steps.push_back(s);
+    }
+    const int c2 = buf(147, 147, 32), c3 = buf(147, 147, 64), p1 = buf(73, 73, 64);
+    conv("Conv2d_2a_3x3", all(c1), all(c2), 3, 3, 1, 0, 0);
+    conv("Conv2d_2b_3x3", all(c2), all(c3), 3, 3, 1, 1, 1);
+    pool(STEP_MAXPOOL, all(c3), all(p1));
+    if (tap == TISE_TAP_64) return gap(all(p1));
+    // block 1
+    const int c4 = buf(73, 73, 80), c5 = buf(71, 71, 192), p2 = buf(35, 35, 192);
+    conv("Conv2d_3b_1x1", all(p1), all(c4));
+    conv("Conv2d_4a_3x3", all(c4), all(c5), 3, 3, 1, 0, 0);
+    pool(STEP_MAXPOOL, all(c5), all(p2));
+    if (tap == TISE_TAP_192) return gap(all(p2));
+    // block 2
+    int x = inceptionA("Mixed_5b", p2, 32);
+    x = inceptionA("Mixed_5c", x, 64);
+    x = inceptionA("Mixed_5d", x, 64);
+    x = inceptionB("Mixed_6a", x);
+    x = inceptionC("Mixed_6b", x, 128);
+    x = inceptionC("Mixed_6c", x, 160);
+    x = inceptionC("Mixed_6d", x, 160);
+    x = inceptionC("Mixed_6e", x, 192);
+    if (tap == TISE_TAP_768) return gap(all(x));
+    // block 3
+    x = inceptionD("Mixed_7a", x);
+    x = inceptionE("Mixed_7b", x, 0);
+    x = inceptionE("Mixed_7c", x, 1);  // fp32 output feeding the global average pool (pool3)
+    gap(all(x));
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+int net_load(tise_ctx* ctx, const tise_weight_desc* tensors, int n_tensors, int num_classes) {
+  net_free(ctx);
+  Net* net = new Net();
+  ctx->net = net;
+  for (int i = 0; i < n_tensors; ++i) {
+    if (!tensors[i].name || !tensors[i].data || tensors[i].numel < 0)
+      return fail(ctx, TISE_ERR_INVALID, "tise_load_inception: tensor %d is null", i);
+    net->raw[tensors[i].name].assign(tensors[i].data, tensors[i].data + tensors[i].numel);
+  }
+  // stem: Conv2d_1a_3x3 kept in fp32, layout [k = (r*3+s)*3+c][co]
+  {
+    auto wt = net->raw.find("Conv2d_1a_3x3.conv.weight");
+    if (wt == net->raw.end() || wt->second.size() != 32 * 27)
+      return fail(ctx, TISE_ERR_INVALID, "state_dict: missing or mis-sized Conv2d_1a_3x3.conv.weight");
+    std::vector<float> scale, shift, w(27 * 32);
+    int rc = fold_bn(ctx, net, "Conv2d_1a_3x3", 32, &scale, &shift);
+    if (rc) return rc;
+    for (int co = 0; co < 32; ++co)
+      for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r)
+          for (int s = 0; s < 3; ++s) w[((r * 3 + s) * 3 + c) * 32 + co] = wt->second[((co * 3 + c) * 3 + r) * 3 + s];
+    if ((rc = dev_alloc(ctx, &net->device_allocs, (void**)&net->d_stem_w, w.size() * 4))) return rc;
+    if ((rc = dev_alloc(ctx, &net->device_allocs, (void**)&net->d_stem_scale, 32 * 4))) return rc;
+    if ((rc = dev_alloc(ctx, &net->device_allocs, (void**)&net->d_stem_shift, 32 * 4))) return rc;
+    TISE_CUDA(ctx, cudaMemcpy(net->d_stem_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    TISE_CUDA(ctx, cudaMemcpy(net->d_stem_scale, scale.data(), 32 * 4, cudaMemcpyHostToDevice));
+    TISE_CUDA(ctx, cudaMemcpy(net->d_stem_shift, shift.data(), 32 * 4, cudaMemcpyHostToDevice));
+  }
+  // declare-only walks: create every layer, size the workspace per tap
+  for (int tap = 0; tap < 4; ++tap) {
+    Builder b{ctx, net, nullptr, 0, nullptr};
+    b.walk(tap);
+    if (b.rc) return b.rc;
+    net->bytes_per_image[tap] = b.per_image;
+  }
+  // classifier head
+  net->num_classes = num_classes;
+  if (num_classes > 0) {
+    auto fw = net->raw.find("fc.weight");
+    auto fb = net->raw.find("fc.bias");
+    if (fw == net->raw.end() || fw->second.size() != (size_t)num_classes * 2048)
+      return fail(ctx, TISE_ERR_INVALID, "state_dict: missing or mis-sized fc.weight (want %dx2048)", num_classes);
+    int rc;
+    if ((rc = dev_alloc(ctx, &net->device_allocs, (void**)&net->d_fc_w, fw->second.size() * 4))) return rc;
+    if ((rc = dev_alloc(ctx, &net->device_allocs, (void**)&net->d_fc_b, (size_t)num_classes * 4))) return rc;
+    TISE_CUDA(ctx, cudaMemcpy(net->d_fc_w, fw->second.data(), fw->second.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<float> bias(num_classes, 0.f);
+    if (fb != net->raw.end() && (int)fb->second.size() == num_classes) bias = fb->second;
+    TISE_CUDA(ctx, cudaMemcpy(net->d_fc_b, bias.data(), (size_t)num_classes * 4, cudaMemcpyHostToDevice));
+  }
+  net->raw.clear();
+  TISE_CUDA(ctx, cudaDeviceSynchronize());
+  return TISE_OK;
+}
+
+void net_free(tise_ctx* ctx) {
+  if (!ctx->net) return;
+  for (void* p : ctx->net->device_allocs) cudaFree(p);
+  delete ctx->net;
+  ctx->net = nullptr;
+}
+
+static int get_plan(tise_ctx* ctx, void* ws, int n, int tap, Plan** out) {
+  Net* net = ctx->net;
+  for (auto& p : net->plans)
+    if (p->ws == ws && p->n == n && p->tap == tap) {
+      *out = p.get();
+      return TISE_OK;
+    }
+  std::unique_ptr<Plan> plan(new Plan());
+  plan->ws = ws;
+  plan->n = n;
+  plan->tap = tap;
+  Builder b{ctx, net, plan.get(), n, (char*)ws};
+  b.walk(tap);
+  if (b.rc) return b.rc;
+  if (net->plans.size() >= 16) net->plans.erase(net->plans.begin());
+  net->plans.push_back(std::move(plan));
+  *out = net->plans.back().get();
+  return TISE_OK;
+}
+
+int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, int tap, float* d_feat, void* d_ws,
+                size_t ws_bytes, cudaStream_t st) {
+  Net* net = ctx->net;
+  if (!net) return fail(ctx, TISE_ERR_STATE, "tise_inception_features: weights not loaded");
+  if (tap < 0 || tap > 3) return fail(ctx, TISE_ERR_INVALID, "tise_inception_features: bad tap %d", tap);
+  if (n == 0) return TISE_OK;
+  if (n < 0 || (!d_u8 == !d_f32) || !d_feat || !d_ws)
+    return fail(ctx, TISE_ERR_INVALID, "tise_inception_features: need exactly one input, an output and a workspace");
+  if (d_u8 && !ctx->lut_set) return fail(ctx, TISE_ERR_STATE, "tise_inception_features: input LUT not set");
+  const size_t need = net->bytes_per_image[tap] * (size_t)n;
+  if (ws_bytes < need)
+    return fail(ctx, TISE_ERR_WORKSPACE, "tise_inception_features: workspace %zu < %zu bytes", ws_bytes, need);
+  if ((uintptr_t)d_ws & 255) return fail(ctx, TISE_ERR_INVALID, "tise_inception_features: workspace must be 256-byte aligned");
+  Plan* plan = nullptr;
+  int rc = get_plan(ctx, d_ws, n, tap, &plan);
+  if (rc) return rc;
+  for (Step& s : plan->steps) {
+    switch (s.kind) {
+      case STEP_STEM:
+        rc = launch_stem(ctx, d_u8, d_f32, n, net->d_stem_w, net->d_stem_scale, net->d_stem_shift, (__half*)s.out, st);
+        break;
+      case STEP_CONV:
+        if (ctx->conv_impl == TISE_CONV_UMMA) {
+          if (!s.umma.valid && (rc = build_umma_plan(ctx, *s.layer, s.conv, &s.umma))) break;
+          rc = launch_conv_umma(ctx, *s.layer, s.conv, s.umma, ctx->passes, st);
+        } else {
+          rc = launch_conv_simt(ctx, *s.layer, s.conv, st);
+        }
+        break;
+      case STEP_MAXPOOL:
+        rc = launch_maxpool3s2(ctx, (const __half*)s.in, s.n, s.h, s.w, s.c, s.in_stride, (__half*)s.out, s.out_stride,
+                               st);
+        break;
+      case STEP_AVGPOOL:
+        rc = launch_avgpool3s1p1(ctx, (const __half*)s.in, s.n, s.h, s.w, s.c, s.in_stride, (__half*)s.out,
+                                 s.out_stride, st);
+        break;
+      case STEP_GAP:
+        rc = launch_global_avgpool(ctx, s.in, s.in_f32, s.n, s.h * s.w, s.c, s.in_stride, d_feat, st);
+        break;
+    }
+    if (rc) return rc;
+  }
+  return TISE_OK;
+}
+
+}  // namespace tise

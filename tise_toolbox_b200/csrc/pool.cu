@@ -1,0 +1,128 @@
+// Pooling layers of Inception-v3 on NHWC fp16 tensors (torchvision Inception3: max_pool2d(3, 2),
+// avg_pool2d(3, 1, 1) with count_include_pad=True, adaptive_avg_pool2d(1)).  HBM/L2-bound
+// elementwise work: one thread per (pixel, 8-channel group), 16-byte loads and stores.
+#include "common.cuh"
+
+namespace tise {
+
+__global__ void maxpool3s2_kernel(const __half* __restrict__ in, int n, int h, int w, int c8, int in_stride,
+                                  __half* __restrict__ out, int out_stride, int ho, int wo) {
+  const long long total = (long long)n * ho * wo * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % c8);
+    long long p = i / c8;
+    const int ox = (int)(p % wo);
+    p /= wo;
+    const int oy = (int)(p % ho);
+    const int img = (int)(p / ho);
+    const __half* base = in + (((size_t)img * h + 2 * oy) * w + 2 * ox) * in_stride + g * 8;
+    __half2 m[4];
+    {
+      const uint4 v = *reinterpret_cast<const uint4*>(base);
+      const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[j] = hv[j];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        if (r == 0 && s == 0) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(base + ((size_t)r * w + s) * in_stride);
+        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], hv[j]);
+      }
+    *reinterpret_cast<uint4*>(out + (((size_t)img * ho + oy) * wo + ox) * out_stride + g * 8) =
+        *reinterpret_cast<uint4*>(m);
+  }
+}
+
+__global__ void avgpool3s1p1_kernel(const __half* __restrict__ in, int n, int h, int w, int c8, int in_stride,
+                                    __half* __restrict__ out, int out_stride) {
+  const long long total = (long long)n * h * w * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % c8);
+    long long p = i / c8;
+    const int ox = (int)(p % w);
+    p /= w;
+    const int oy = (int)(p % h);
+    const int img = (int)(p / h);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int r = -1; r <= 1; ++r)
+#pragma unroll
+      for (int s = -1; s <= 1; ++s) {
+        const int y = oy + r, x = ox + s;
+        if (y < 0 || y >= h || x < 0 || x >= w) continue;  // zero padding, still divided by 9
+        const uint4 v = *reinterpret_cast<const uint4*>(in + (((size_t)img * h + y) * w + x) * in_stride + g * 8);
+        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(hv[j]);
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
+        }
+      }
+    __half2 o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = __floats2half2_rn(acc[2 * j] / 9.0f, acc[2 * j + 1] / 9.0f);
+    *reinterpret_cast<uint4*>(out + (((size_t)img * h + oy) * w + ox) * out_stride + g * 8) =
+        *reinterpret_cast<uint4*>(o);
+  }
+}
+
+// out[img][ch] = mean over hw positions.  Consecutive threads -> consecutive channels (coalesced).
+template <typename T>
+__global__ void global_avgpool_kernel(const T* __restrict__ in, int n, int hw, int c, int in_stride,
+                                      float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * c) return;
+  const int img = i / c, ch = i - img * c;
+  const T* p = in + (size_t)img * hw * in_stride + ch;
+  float acc = 0.f;
+  for (int k = 0; k < hw; ++k) acc += (float)p[(size_t)k * in_stride];
+  out[i] = acc / (float)hw;
+}
+
+static int grid_for(long long total, int threads, int num_sms) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = (long long)num_sms * 32;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+int launch_maxpool3s2(tise_ctx* ctx, const __half* in, int n, int h, int w, int c, int in_stride, __half* out,
+                      int out_stride, cudaStream_t st) {
+  const int ho = (h - 3) / 2 + 1, wo = (w - 3) / 2 + 1;
+  const long long total = (long long)n * ho * wo * (c / 8);
+  maxpool3s2_kernel<<<grid_for(total, 256, ctx->num_sms), 256, 0, st>>>(in, n, h, w, c / 8, in_stride, out,
+                                                                       out_stride, ho, wo);
+  TISE_LAUNCH_CHECK(ctx);
+  return TISE_OK;
+}
+
+int launch_avgpool3s1p1(tise_ctx* ctx, const __half* in, int n, int h, int w, int c, int in_stride, __half* out,
+                        int out_stride, cudaStream_t st) {
+  const long long total = (long long)n * h * w * (c / 8);
+  avgpool3s1p1_kernel<<<grid_for(total, 256, ctx->num_sms), 256, 0, st>>>(in, n, h, w, c / 8, in_stride, out,
+                                                                         out_stride);
+  TISE_LAUNCH_CHECK(ctx);
+  return TISE_OK;
+}
+
+int launch_global_avgpool(tise_ctx* ctx, const void* in, int in_f32, int n, int hw, int c, int in_stride,
+                          float* out, cudaStream_t st) {
+  const int total = n * c;
+  if (in_f32)
+    global_avgpool_kernel<float><<<(total + 255) / 256, 256, 0, st>>>((const float*)in, n, hw, c, in_stride, out);
+  else
+    global_avgpool_kernel<__half><<<(total + 255) / 256, 256, 0, st>>>((const __half*)in, n, hw, c, in_stride, out);
+  TISE_LAUNCH_CHECK(ctx);
+  return TISE_OK;
+}
+
+}  // namespace tise

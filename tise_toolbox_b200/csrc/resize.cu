@@ -1,0 +1,222 @@
+// A2: Pillow-exact bilinear resize of packed uint8 HWC images to 299x299 (see include/tise_b200.h).
+//
+// Pillow's ImagingResample (src/libImaging/Resample.c) is a separable triangle filter whose
+// weights are computed in double, normalised, quantised to 22-bit fixed point, and applied with
+// int32 accumulation -- horizontal pass first into a uint8 temporary, then vertical.  The
+// coefficient kernel below repeats the double arithmetic operation by operation with explicit
+// round-to-nearest intrinsics (no FMA contraction), so the integer tables -- and therefore every
+// output byte -- are identical to Pillow's.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace tise {
+
+constexpr int kPrecisionBits = 32 - 8 - 2;
+
+__host__ __device__ inline int resize_ksize(int in_size) {
+  // ksize = ceil(support) * 2 + 1, support = max(in/out, 1)
+  int c = (in_size + kOutSize - 1) / kOutSize;  // ceil(in/out) for in > out
+  if (c < 1) c = 1;
+  return c * 2 + 1;
+}
+
+// One block per distinct input size; thread xx computes bounds/weights of output index xx.
+// Table layout per size: int bounds[299][2] (xmin, count) followed by int kk[299][kmax].
+__global__ void resize_coeffs_kernel(const int* __restrict__ sizes, int kmax, int* __restrict__ tabs) {
+  const int in_size = sizes[blockIdx.x];
+  int* bounds = tabs + (size_t)blockIdx.x * kOutSize * (2 + kmax);
+  int* kk = bounds + kOutSize * 2;
+  const int xx = threadIdx.x;
+  if (xx >= kOutSize) return;
+
+  const double scale = __ddiv_rn((double)in_size, (double)kOutSize);
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = filterscale;  // 1.0 * filterscale
+  const double ss = __ddiv_rn(1.0, filterscale);
+  const double center = __dmul_rn(__dadd_rn((double)xx, 0.5), scale);
+  int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+  if (xmax > in_size) xmax = in_size;
+  xmax -= xmin;
+
+  double ww = 0.0;
+  for (int x = 0; x < xmax; ++x) {
+    double a = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+    if (a < 0.0) a = -a;
+    const double w = a < 1.0 ? __dsub_rn(1.0, a) : 0.0;
+    ww = __dadd_rn(ww, w);
+  }
+  for (int x = 0; x < kmax; ++x) {
+    int q = 0;
+    if (x < xmax) {
+      double a = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+      if (a < 0.0) a = -a;
+      double w = a < 1.0 ? __dsub_rn(1.0, a) : 0.0;
+      if (ww != 0.0) w = __ddiv_rn(w, ww);
+      const double t = __dmul_rn(w, (double)(1 << kPrecisionBits));
+      q = w < 0.0 ? (int)__dadd_rn(-0.5, t) : (int)__dadd_rn(0.5, t);
+    }
+    kk[xx * kmax + x] = q;
+  }
+  bounds[xx * 2 + 0] = xmin;
+  bounds[xx * 2 + 1] = xmax;
+}
+
+struct ImgDesc {
+  long long src_off;  // byte offset of the image in d_imgs
+  long long tmp_off;  // byte offset of its [h][299][3] horizontal-pass temporary
+  int h, w;
+  int tab_x, tab_y;  // table indices (by input width / height)
+};
+
+__device__ __forceinline__ uint8_t clip8(int acc) {
+  int v = acc >> kPrecisionBits;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// Horizontal pass: tmp[i][y][xx][c] for y < h.  One thread per output byte, consecutive threads
+// walk (xx, c) inside a row so both the gather and the store are contiguous per warp.
+// grid = (ceil(897 / 256), max_h, n)
+__global__ void resize_h_kernel(const uint8_t* __restrict__ imgs, const ImgDesc* __restrict__ descs,
+                                const int* __restrict__ tabs, int kmax, uint8_t* __restrict__ tmp) {
+  const ImgDesc d = descs[blockIdx.z];
+  const int y = blockIdx.y;
+  if (y >= d.h) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;  // xx * 3 + c
+  if (j >= kOutSize * 3) return;
+  const int xx = j / 3, c = j - xx * 3;
+  const uint8_t* row = imgs + d.src_off + (size_t)y * d.w * 3;
+  uint8_t* out = tmp + d.tmp_off + (size_t)y * kOutSize * 3;
+  if (d.w == kOutSize) {  // Pillow skips a pass that does not change the size
+    out[j] = row[j];
+    return;
+  }
+  const int* bounds = tabs + (size_t)d.tab_x * kOutSize * (2 + kmax);
+  const int* kk = bounds + kOutSize * 2 + xx * kmax;
+  const int xmin = bounds[xx * 2], cnt = bounds[xx * 2 + 1];
+  int acc = 1 << (kPrecisionBits - 1);
+  for (int x = 0; x < cnt; ++x) acc += (int)row[(xmin + x) * 3 + c] * kk[x];
+  out[j] = clip8(acc);
+}
+
+// Vertical pass: out[i][yy][xx][c].  grid = (ceil(897 / 256), 299, n)
+__global__ void resize_v_kernel(const uint8_t* __restrict__ tmp, const ImgDesc* __restrict__ descs,
+                                const int* __restrict__ tabs, int kmax, uint8_t* __restrict__ out) {
+  const ImgDesc d = descs[blockIdx.z];
+  const int yy = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= kOutSize * 3) return;
+  const uint8_t* src = tmp + d.tmp_off;
+  uint8_t* dst = out + ((size_t)blockIdx.z * kOutSize + yy) * kOutSize * 3;
+  if (d.h == kOutSize) {
+    dst[j] = src[(size_t)yy * kOutSize * 3 + j];
+    return;
+  }
+  const int* bounds = tabs + (size_t)d.tab_y * kOutSize * (2 + kmax);
+  const int* kk = bounds + kOutSize * 2 + yy * kmax;
+  const int ymin = bounds[yy * 2], cnt = bounds[yy * 2 + 1];
+  int acc = 1 << (kPrecisionBits - 1);
+  for (int y = 0; y < cnt; ++y) acc += (int)src[(size_t)(ymin + y) * kOutSize * 3 + j] * kk[y];
+  dst[j] = clip8(acc);
+}
+
+// Workspace layout: [descs n][sizes 2n ints][tables (2n) * 299 * (2 + kmax) ints][tmp n * max_h * 897]
+struct ResizeWs {
+  size_t off_desc, off_sizes, off_tabs, off_tmp, total;
+};
+static ResizeWs resize_ws_layout(int n, int max_h, int max_w) {
+  ResizeWs L;
+  const int kmax = resize_ksize(max_h > max_w ? max_h : max_w);
+  size_t o = 0;
+  L.off_desc = o;
+  o = align_up(o + sizeof(ImgDesc) * (size_t)n, 256);
+  L.off_sizes = o;
+  o = align_up(o + sizeof(int) * 2 * (size_t)n, 256);
+  L.off_tabs = o;
+  o = align_up(o + sizeof(int) * 2 * (size_t)n * kOutSize * (2 + kmax), 256);
+  L.off_tmp = o;
+  o = align_up(o + (size_t)n * max_h * kOutSize * 3, 256);
+  L.total = o;
+  return L;
+}
+
+}  // namespace tise
+
+using namespace tise;
+
+extern "C" size_t tise_resize_workspace_bytes(int n, int max_h, int max_w) {
+  if (n <= 0 || max_h <= 0 || max_w <= 0) return 0;
+  return resize_ws_layout(n, max_h, max_w).total;
+}
+
+extern "C" int tise_resize_u8(tise_ctx* ctx, const uint8_t* d_imgs, const int64_t* h_offsets, const int32_t* h_hw,
+                              int uniform, int n, uint8_t* d_out, void* d_ws, size_t ws_bytes,
+                              tise_stream stream) {
+  if (!ctx) return TISE_ERR_INVALID;
+  if (n == 0) return TISE_OK;
+  if (!d_imgs || !h_hw || !d_out || !d_ws || n < 0) return fail(ctx, TISE_ERR_INVALID, "tise_resize_u8: null argument");
+  if (!uniform && !h_offsets) return fail(ctx, TISE_ERR_INVALID, "tise_resize_u8: ragged batch needs h_offsets");
+  cudaStream_t st = (cudaStream_t)stream;
+
+  int max_h = 0, max_w = 0;
+  for (int i = 0; i < (uniform ? 1 : n); ++i) {
+    const int h = h_hw[2 * i], w = h_hw[2 * i + 1];
+    if (h <= 0 || w <= 0) return fail(ctx, TISE_ERR_INVALID, "tise_resize_u8: image %d has size %dx%d", i, h, w);
+    max_h = h > max_h ? h : max_h;
+    max_w = w > max_w ? w : max_w;
+  }
+  const ResizeWs L = resize_ws_layout(n, max_h, max_w);
+  if (ws_bytes < L.total)
+    return fail(ctx, TISE_ERR_WORKSPACE, "tise_resize_u8: workspace %zu < %zu bytes", ws_bytes, L.total);
+  const int kmax = resize_ksize(max_h > max_w ? max_h : max_w);
+
+  // distinct sizes -> table indices
+  std::vector<ImgDesc> descs(n);
+  std::vector<int> sizes;
+  std::map<int, int> tab_of;
+  auto table = [&](int s) {
+    auto it = tab_of.find(s);
+    if (it != tab_of.end()) return it->second;
+    const int t = (int)sizes.size();
+    sizes.push_back(s);
+    tab_of[s] = t;
+    return t;
+  };
+  long long tmp_off = 0;
+  for (int i = 0; i < n; ++i) {
+    const int h = h_hw[uniform ? 0 : 2 * i], w = h_hw[uniform ? 1 : 2 * i + 1];
+    ImgDesc& d = descs[i];
+    d.h = h;
+    d.w = w;
+    d.src_off = uniform ? (long long)i * h * w * 3 : (long long)h_offsets[i];
+    d.tmp_off = tmp_off;
+    tmp_off += (long long)h * kOutSize * 3;
+    d.tab_x = table(w);
+    d.tab_y = table(h);
+  }
+  char* ws = (char*)d_ws;
+  ImgDesc* d_descs = (ImgDesc*)(ws + L.off_desc);
+  int* d_sizes = (int*)(ws + L.off_sizes);
+  int* d_tabs = (int*)(ws + L.off_tabs);
+  uint8_t* d_tmp = (uint8_t*)(ws + L.off_tmp);
+  TISE_CUDA(ctx, cudaMemcpyAsync(d_descs, descs.data(), sizeof(ImgDesc) * n, cudaMemcpyHostToDevice, st));
+  TISE_CUDA(ctx, cudaMemcpyAsync(d_sizes, sizes.data(), sizeof(int) * sizes.size(), cudaMemcpyHostToDevice, st));
+
+  resize_coeffs_kernel<<<(unsigned)sizes.size(), 320, 0, st>>>(d_sizes, kmax, d_tabs);
+  TISE_LAUNCH_CHECK(ctx);
+  const dim3 blk(256);
+  const unsigned gx = (kOutSize * 3 + 255) / 256;
+  // gridDim.z is limited to 65535: chunk the batch
+  for (int i0 = 0; i0 < n; i0 += 32768) {
+    const int cnt = n - i0 < 32768 ? n - i0 : 32768;
+    resize_h_kernel<<<dim3(gx, max_h, cnt), blk, 0, st>>>(d_imgs, d_descs + i0, d_tabs, kmax, d_tmp);
+    TISE_LAUNCH_CHECK(ctx);
+    resize_v_kernel<<<dim3(gx, kOutSize, cnt), blk, 0, st>>>(d_tmp, d_descs + i0, d_tabs, kmax,
+                                                             d_out + (size_t)i0 * kOutSize * kOutSize * 3);
+    TISE_LAUNCH_CHECK(ctx);
+  }
+  return TISE_OK;
+}
