@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+@pytest.fixture(scope="session")
+def state_dict():
+    from tise_toolbox_b200 import synth
+
+    return synth.inception_state_dict(0, num_classes=1000)
+
+
+@pytest.fixture(scope="session")
+def engine(state_dict):
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tise_toolbox_b200.engine import Engine
+
+    return Engine(state_dict, device="cuda:0", micro_batch=32)

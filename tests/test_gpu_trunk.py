@@ -1,0 +1,71 @@
+"""-m gpu: the Inception-v3 trunk through libtise_b200 against the CPU oracle (torchvision Inception3 fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate
+from tise_toolbox_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+# pool3 relative L2 bound of the fp16-activation x (hi+lo)-fp16-weight model: measured 1.4e-4 on CPU
+# emulation (tools/precision_probe.py); single fp16 pass: 5.9e-4.
+POOL3_REL_L2 = {2: 5e-4, 1: 2e-3}
+
+
+@pytest.fixture(scope="module")
+def batch():
+    imgs = torch.cat([synth.images(1, 0, 0, 5), synth.images(2, 1, 0, 4)])  # 9 images: odd batch, two sets
+    return imgs
+
+
+@pytest.fixture(scope="module")
+def oracle_blocks(batch, state_dict):
+    trunk = restate.Trunk(state_dict)
+    x = restate.preprocess([b.numpy() for b in batch], "fid")
+    return x, trunk.blocks(x)
+
+
+def _rel_l2(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.mark.parametrize("impl,passes", [("simt", 2), ("umma", 2), ("umma", 1)])
+def test_pool3_parity(engine, batch, oracle_blocks, impl, passes):
+    engine.set_conv_mode(impl, passes)
+    engine.set_variant("fid")
+    try:
+        got = engine.features(batch.cuda()).cpu().numpy()
+    finally:
+        engine.set_conv_mode("umma", 2)
+    ref = oracle_blocks[1][3].reshape(len(batch), -1).numpy()
+    assert got.shape == ref.shape == (9, 2048)
+    assert np.isfinite(got).all()
+    err = _rel_l2(got, ref)
+    assert err <= POOL3_REL_L2[passes], "pool3 rel L2 %.3e" % err
+
+
+@pytest.mark.parametrize("dims,block", [(64, 0), (192, 1), (768, 2)])
+def test_block_taps(engine, batch, oracle_blocks, dims, block):
+    got = engine.features(batch.cuda(), dims=dims).cpu().numpy()
+    ref = oracle_blocks[1][block].mean(dim=(2, 3)).numpy()
+    assert got.shape == ref.shape
+    assert _rel_l2(got, ref) <= 1e-3
+
+
+def test_float_input_path_matches_u8_path(engine, batch, oracle_blocks):
+    x = oracle_blocks[0]  # float32 [n,3,299,299], already normalised by the oracle
+    a = engine.features_from_float(x.cuda()).cpu().numpy()
+    b = engine.features(batch.cuda()).cpu().numpy()
+    assert np.array_equal(a, b)  # the LUT is bit-exact, so both inputs are the same floats
+
+
+def test_micro_batching_is_invisible(engine, batch):
+    full = engine.features(batch.cuda()).cpu().numpy()
+    keep = engine.micro_batch
+    engine.micro_batch = 4
+    try:
+        part = engine.features(batch.cuda()).cpu().numpy()
+    finally:
+        engine.micro_batch = keep
+    assert np.array_equal(full, part)

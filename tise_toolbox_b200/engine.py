@@ -1,0 +1,319 @@
+"""Host-side driver of the CUDA hot path: owns a libtise_b200 context, device workspaces and the
+running FID / IS statistics.  PyTorch is used for device memory, streams and
+``torch.distributed`` only; every arithmetic step is a kernel of libtise_b200.so.
+
+The reference-facing modules (``fid_score``, ``inception``, ``object_centric_inception_score``,
+``inception_score_star``) are thin wrappers over :class:`Engine`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+
+TAP_BY_DIM = {64: 0, 192: 1, 768: 2, 2048: 3}  # image_realism/FID/inception.py:14-19
+INPUT_VARIANTS = ("fid", "ois", "bird", "coco")
+
+T_COCO = 0.9091363549232483   # image_realism/IS/coco/inception_score_star_coco.py:107
+T_BIRD = 0.5980541706085205   # image_realism/IS/bird/inception_score_star_bird.py:192
+T_OIS = 2.1737587451934814    # object_fidelity/O-IS/object_centric_inception_score.py:55
+
+
+def input_lut(variant: str) -> torch.Tensor:
+    """float32 [3, 256] table: network input for each (channel, uint8 level), built with the op
+    sequence of the reference so the fused uint8 path is bit-identical to its float path:
+    fid  -- ToTensor (fid_score.py:211) + affine of image_realism/FID/inception.py:120-124;
+    ois  -- ToTensor + Normalize(.5, .5) (object_centric_inception_score.py:90-91);
+    bird -- x / 127.5 - 1 (inception_score_star_bird.py:70);
+    coco -- raw 0..255 into a graph that starts with (x - 128) / 128 (inception_score_star_coco.py:119)."""
+    lv = torch.arange(256, dtype=torch.float32)
+    if variant == "fid":
+        x = (lv / 255).view(1, 256).repeat(3, 1)
+        x[0] = x[0] * (0.229 / 0.5) + (0.485 - 0.5) / 0.5
+        x[1] = x[1] * (0.224 / 0.5) + (0.456 - 0.5) / 0.5
+        x[2] = x[2] * (0.225 / 0.5) + (0.406 - 0.5) / 0.5
+        return x.contiguous()
+    if variant == "ois":
+        x = (lv / 255).view(1, 256).repeat(3, 1)
+        return ((x - 0.5) / 0.5).contiguous()
+    if variant == "bird":
+        x = torch.from_numpy(np.arange(256).astype(np.float32) / 127.5 - 1.0).to(torch.float32)
+        return x.view(1, 256).repeat(3, 1).contiguous()
+    if variant == "coco":
+        return ((lv - 128.0) * (1.0 / 128.0)).view(1, 256).repeat(3, 1).contiguous()
+    raise ValueError("unknown input variant %r" % (variant,))
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Engine:
+    """One libtise_b200 context on one GPU with an Inception-v3 ``state_dict`` loaded."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: Union[int, str, torch.device, None] = None,
+                 variant: str = "fid", micro_batch: int = 128, conv_impl: str = "umma", passes: int = 2):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tise_toolbox_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("tise_toolbox_b200 runs on CUDA devices only, got %s" % dev)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.micro_batch = int(micro_batch)
+        ctx = _lib.c_ctx_p()
+        _lib.check(None, self.lib.tise_ctx_create(dev.index, C.byref(ctx)))
+        self.ctx = ctx
+        self._ws: Optional[torch.Tensor] = None
+        self._rs_ws: Optional[torch.Tensor] = None
+        self._u8: Optional[torch.Tensor] = None
+        self._fr_ws: Optional[torch.Tensor] = None
+        self.num_classes = 0
+        self.variant = None
+        self.set_conv_mode(conv_impl, passes)
+        self.load_state_dict(state_dict)
+        self.set_variant(variant)
+
+    # ------------------------------------------------------------------ setup
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.tise_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, status: int):
+        _lib.check(self.ctx, status)
+
+    def set_conv_mode(self, conv_impl: str = "umma", passes: int = 2):
+        self._check(self.lib.tise_set_conv_mode(self.ctx, {"umma": 0, "simt": 1}[conv_impl], int(passes)))
+        self.conv_impl, self.passes = conv_impl, int(passes)
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor]):
+        keep, descs = [], []
+        for name, t in state_dict.items():
+            if name.endswith("num_batches_tracked") or name.startswith("AuxLogits"):
+                continue  # the aux head is never evaluated in eval mode (torchvision Inception3._forward)
+            a = np.ascontiguousarray(t.detach().cpu().to(torch.float32).numpy())
+            keep.append(a)
+            descs.append(_lib.WeightDesc(name.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), a.size))
+        num_classes = int(state_dict["fc.weight"].shape[0]) if "fc.weight" in state_dict else 0
+        arr = (_lib.WeightDesc * len(descs))(*descs)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.tise_load_inception(self.ctx, arr, len(descs), num_classes))
+        self.num_classes = num_classes
+
+    def set_variant(self, variant: str):
+        if variant == self.variant:
+            return
+        lut = input_lut(variant).numpy()
+        self._check(self.lib.tise_set_input_lut(self.ctx, lut.ctypes.data))
+        self.variant = variant
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.tise_launch_count(self.ctx))
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, name: str, nbytes: int) -> torch.Tensor:
+        cur = getattr(self, name)
+        if cur is None or cur.numel() < nbytes:
+            cur = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+            setattr(self, name, cur)
+        return cur
+
+    # ------------------------------------------------------------------ A2 resize
+    def resize(self, images: Union[torch.Tensor, Sequence[torch.Tensor]], out: Optional[torch.Tensor] = None
+               ) -> torch.Tensor:
+        """uint8 HWC RGB images on the device -> uint8 [n, 299, 299, 3] (Pillow-exact bilinear).
+        ``images``: one [n, H, W, 3] tensor, or a sequence of [H_i, W_i, 3] tensors (ragged crops)."""
+        if torch.is_tensor(images):
+            assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] == 3
+            imgs = images.contiguous()
+            n, h, w = int(imgs.shape[0]), int(imgs.shape[1]), int(imgs.shape[2])
+            hw = np.array([h, w], dtype=np.int32)
+            offs_p, uniform, max_h, max_w = None, 1, h, w
+            src = imgs
+        else:
+            n = len(images)
+            hw = np.array([[int(t.shape[0]), int(t.shape[1])] for t in images], dtype=np.int32).reshape(-1)
+            sizes = hw.reshape(-1, 2).astype(np.int64)
+            nbytes = sizes[:, 0] * sizes[:, 1] * 3
+            offs = np.zeros(n, dtype=np.int64)
+            offs[1:] = np.cumsum(nbytes)[:-1]
+            src = torch.cat([t.reshape(-1) for t in images]) if n else torch.empty(0, dtype=torch.uint8, device=self.device)
+            assert src.dtype == torch.uint8
+            offs_p, uniform = offs.ctypes.data, 0
+            max_h, max_w = (int(sizes[:, 0].max()), int(sizes[:, 1].max())) if n else (1, 1)
+        if out is None:
+            out = torch.empty((n, 299, 299, 3), dtype=torch.uint8, device=self.device)
+        if n == 0:
+            return out
+        need = int(self.lib.tise_resize_workspace_bytes(n, max_h, max_w))
+        ws = self._buf("_rs_ws", need)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.tise_resize_u8(self.ctx, src.data_ptr(), offs_p, hw.ctypes.data, uniform, n,
+                                                out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        return out
+
+    # ------------------------------------------------------------------ A5 trunk
+    def _trunk(self, u8: Optional[torch.Tensor], f32: Optional[torch.Tensor], n: int, tap: int, feat: torch.Tensor):
+        need = int(self.lib.tise_inception_workspace_bytes(self.ctx, self.micro_batch))
+        ws = self._buf("_ws", need)
+        with torch.cuda.device(self.device):
+            for i0 in range(0, n, self.micro_batch):
+                m = min(self.micro_batch, n - i0)
+                self._check(self.lib.tise_inception_features(
+                    self.ctx, u8[i0:].data_ptr() if u8 is not None else None,
+                    f32[i0:].data_ptr() if f32 is not None else None, m, tap, feat[i0:].data_ptr(),
+                    ws.data_ptr(), ws.numel(), _stream()))
+
+    def features_from_resized(self, u8_299: torch.Tensor, dims: int = 2048) -> torch.Tensor:
+        """uint8 [n, 299, 299, 3] (already resized) -> float32 [n, dims] block features."""
+        assert u8_299.dtype == torch.uint8 and tuple(u8_299.shape[1:]) == (299, 299, 3)
+        n = int(u8_299.shape[0])
+        feat = torch.empty((n, dims), dtype=torch.float32, device=self.device)
+        self._trunk(u8_299.contiguous(), None, n, TAP_BY_DIM[dims], feat)
+        return feat
+
+    def features(self, images: Union[torch.Tensor, Sequence[torch.Tensor]], dims: int = 2048) -> torch.Tensor:
+        """uint8 HWC images (any size) -> float32 [n, dims]: resize -> LUT -> Inception-v3 -> pooled block output."""
+        return self.features_from_resized(self.resize(images), dims)
+
+    def features_from_float(self, x: torch.Tensor, dims: int = 2048) -> torch.Tensor:
+        """float32 [n, 3, 299, 299], already normalised (what Conv2d_1a_3x3 sees) -> float32 [n, dims]."""
+        assert x.dtype == torch.float32 and tuple(x.shape[1:]) == (3, 299, 299)
+        x = x.contiguous()
+        n = int(x.shape[0])
+        feat = torch.empty((n, dims), dtype=torch.float32, device=self.device)
+        self._trunk(None, x, n, TAP_BY_DIM[dims], feat)
+        return feat
+
+    def logits(self, feat: torch.Tensor, use_bias: bool = True) -> torch.Tensor:
+        assert feat.dtype == torch.float32 and feat.shape[1] == 2048
+        feat = feat.contiguous()
+        out = torch.empty((feat.shape[0], self.num_classes), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.tise_logits(self.ctx, feat.data_ptr(), int(feat.shape[0]), int(bool(use_bias)),
+                                             out.data_ptr(), _stream()))
+        return out
+
+    # ------------------------------------------------------------------ A9 Frechet distance
+    def frechet(self, mu1, sigma1, mu2, sigma2, eps: float = 1e-6) -> Tuple[float, int]:
+        d = int(np.asarray(mu1).shape[0]) if not torch.is_tensor(mu1) else int(mu1.shape[0])
+        to = lambda a: (a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))).to(
+            self.device, torch.float64).contiguous()
+        m1, s1, m2, s2 = to(mu1), to(sigma1), to(mu2), to(sigma2)
+        ws = self._buf("_fr_ws", int(self.lib.tise_frechet_workspace_bytes(d)))
+        out, flags = C.c_double(0.0), C.c_int(0)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.tise_frechet(self.ctx, m1.data_ptr(), s1.data_ptr(), m2.data_ptr(), s2.data_ptr(), d,
+                                              float(eps), C.byref(out), C.byref(flags), ws.data_ptr(), ws.numel(),
+                                              _stream()))
+        return float(out.value), int(flags.value)
+
+
+class Moments:
+    """Running sum_i x_i and sum_i x_i x_i^T (fp64, on the device) -> (mu, sigma) of np.mean / np.cov
+    (fid_score.py:194-195).  Additive across batches and across ranks."""
+
+    def __init__(self, engine: Engine, d: int = 2048):
+        self.e, self.d = engine, d
+        self.buf = torch.zeros(1 + d + d * d, dtype=torch.float64, device=engine.device)  # [count | sum | sxx]
+        self.count = 0
+
+    @property
+    def sum(self):
+        return self.buf[1:1 + self.d]
+
+    @property
+    def sxx(self):
+        return self.buf[1 + self.d:]
+
+    def update(self, feat: torch.Tensor):
+        assert feat.dtype == torch.float32 and feat.shape[1] == self.d
+        feat = feat.contiguous()
+        n = int(feat.shape[0])
+        with torch.cuda.device(self.e.device):
+            self.e._check(self.e.lib.tise_moments_update(self.e.ctx, feat.data_ptr(), n, self.d, self.sum.data_ptr(),
+                                                         self.sxx.data_ptr(), _stream()))
+        self.count += n
+
+    def allreduce(self, group=None):
+        """The path's one exchange step: sum the packed moments over all ranks."""
+        import torch.distributed as dist
+
+        self.buf[0] = float(self.count)
+        dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=group)
+        self.count = int(round(float(self.buf[0].item())))
+
+    def finalize_device(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        mu = torch.empty(self.d, dtype=torch.float64, device=self.e.device)
+        sigma = torch.empty((self.d, self.d), dtype=torch.float64, device=self.e.device)
+        with torch.cuda.device(self.e.device):
+            self.e._check(self.e.lib.tise_moments_finalize(self.e.ctx, self.sum.data_ptr(), self.sxx.data_ptr(),
+                                                           self.count, self.d, mu.data_ptr(), sigma.data_ptr(),
+                                                           _stream()))
+        return mu, sigma
+
+    def finalize(self) -> Tuple[np.ndarray, np.ndarray]:
+        mu, sigma = self.finalize_device()
+        return mu.cpu().numpy(), sigma.cpu().numpy()
+
+
+class ISPartials:
+    """Per-split partial sums of the inception score: sum_i sum_c p log p, sum_i p (marginal), count.
+    mean_i KL(p_i || m) = S / n - sum_c m_c log m_c with m = marg / n  (one-pass form)."""
+
+    def __init__(self, engine: Engine, n_classes: int, n_splits: int):
+        self.e, self.cs, self.s = engine, n_classes, n_splits
+        # [splogp S | marg S*Cs | cnt S | zeros 1] -- all float64 except the two int64 tails viewed below
+        self.f = torch.zeros(n_splits + n_splits * n_classes, dtype=torch.float64, device=engine.device)
+        self.i = torch.zeros(n_splits + 1, dtype=torch.int64, device=engine.device)
+
+    def update(self, logits: torch.Tensor, split_id: torch.Tensor, class_offset: int, temperature: float):
+        assert logits.dtype == torch.float32 and split_id.dtype == torch.int32
+        logits = logits.contiguous()
+        n, c = int(logits.shape[0]), int(logits.shape[1])
+        assert c - class_offset == self.cs and split_id.numel() == n
+        e = self.e
+        with torch.cuda.device(e.device):
+            e._check(e.lib.tise_is_update(e.ctx, logits.data_ptr(), n, c, int(class_offset), float(temperature),
+                                          split_id.contiguous().data_ptr(), self.s, self.f.data_ptr(),
+                                          self.f[self.s:].data_ptr(), self.i.data_ptr(), self.i[self.s:].data_ptr(),
+                                          _stream()))
+
+    def allreduce(self, group=None):
+        import torch.distributed as dist
+
+        dist.all_reduce(self.f, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(self.i, op=dist.ReduceOp.SUM, group=group)
+
+    def finalize(self, nan_on_zero: bool = False) -> Tuple[float, float, np.ndarray]:
+        """(mean, std (ddof=0), per-split scores).  ``nan_on_zero`` reproduces the IS* scripts' explicit
+        log: a probability that underflowed to 0 makes the score NaN (inception_score_star_coco.py:56),
+        whereas scipy.stats.entropy (O-IS) treats 0 log 0 as 0."""
+        f = self.f.cpu().numpy()
+        i = self.i.cpu().numpy()
+        splogp, marg = f[:self.s], f[self.s:].reshape(self.s, self.cs)
+        cnt, zeros = i[:self.s].astype(np.float64), int(i[self.s])
+        scores = np.full(self.s, np.nan)
+        for k in range(self.s):
+            if cnt[k] <= 0:
+                continue
+            m = marg[k] / cnt[k]
+            nz = m > 0
+            scores[k] = np.exp(splogp[k] / cnt[k] - float(np.sum(m[nz] * np.log(m[nz]))))
+        if nan_on_zero and zeros > 0:
+            scores[:] = np.nan
+        return float(np.mean(scores)), float(np.std(scores)), scores
