@@ -1,0 +1,112 @@
+"""CPU (-m "not gpu"): host-side logic of the path -- split assignment, sharding, result formats and
+the N>1 exchange step over gloo (world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import restate
+from tise_toolbox_b200 import inception_score as isc
+from tise_toolbox_b200 import pipeline
+
+
+@pytest.mark.parametrize("n,splits", [(23, 10), (100, 10), (7, 3), (30000, 10), (9, 10)])
+def test_split_ids_follow_the_reference_slicing(n, splits):
+    ois = isc.split_ids(n, splits, "ois")
+    star = isc.split_ids(n, splits, "coco")
+    per = n // splits
+    for k in range(splits):
+        assert np.array_equal(np.nonzero(ois == k)[0], np.arange(k * per, (k + 1) * per))  # O-IS :73
+        assert np.array_equal(np.nonzero(star == k)[0], np.arange(k * n // splits, (k + 1) * n // splits))  # coco :55
+    assert (ois[per * splits:] == -1).all() and (star >= 0).all()
+
+
+def test_split_ids_are_independent_of_sharding():
+    n = 1003
+    full = isc.split_ids(n, 10, "coco")
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = pipeline.shard_range(n, r, world)
+            parts.append(isc.split_ids(n, 10, "coco", lo, hi - lo))
+        assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 30000, 200001):
+        for world in (1, 2, 4, 8):
+            r = [pipeline.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
+
+
+def test_kept_images_bird_drops_partial_batch():
+    assert isc.kept_images(130, "bird") == 128 and isc.kept_images(130, "coco") == 130
+
+
+def test_one_pass_is_equals_reference_two_pass():
+    rng = np.random.RandomState(0)
+    logits = torch.from_numpy(rng.randn(97, 80).astype(np.float32) * 2)
+    preds = restate.ois_preds(logits)
+    ref = restate.ois_inception_score(preds, 10)
+    sid = isc.split_ids(97, 10, "ois")
+    scores = []
+    for k in range(10):
+        part = preds[sid == k]
+        m = part.mean(0)
+        scores.append(np.exp((part * np.log(part)).sum() / len(part) - (m * np.log(m)).sum()))
+    assert abs(np.mean(scores) - ref[0]) <= 1e-8 * ref[0] and abs(np.std(scores) - ref[1]) <= 1e-6 * ref[1]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, d, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(1)
+    x = rng.rand(n, d) + 1.5
+    lo, hi = pipeline.shard_range(n, rank, world)
+    # the packed exchange buffer of the path: [count | sum x | sum x x^T]  (engine.Moments.buf)
+    buf = torch.zeros(1 + d + d * d, dtype=torch.float64)
+    xs = torch.from_numpy(x[lo:hi])
+    buf[0] = hi - lo
+    buf[1:1 + d] = xs.sum(0)
+    buf[1 + d:] = (xs.t() @ xs).reshape(-1)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        cnt = buf[0].item()
+        mu = buf[1:1 + d] / cnt
+        sigma = (buf[1 + d:].view(d, d) - cnt * torch.outer(mu, mu)) / (cnt - 1)
+        torch.save({"mu": mu, "sigma": sigma, "cnt": cnt}, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_moment_exchange_over_gloo(tmp_path):
+    n, d = 101, 16
+    out = str(tmp_path / "r.pt")
+    mp.spawn(_worker, args=(2, _free_port(), n, d, out), nprocs=2, join=True)
+    r = torch.load(out)
+    rng = np.random.RandomState(1)
+    x = rng.rand(n, d) + 1.5
+    assert r["cnt"] == n
+    assert np.allclose(r["mu"].numpy(), x.mean(0), rtol=1e-13)
+    assert np.allclose(r["sigma"].numpy(), np.cov(x, rowvar=False), rtol=1e-9, atol=1e-13)
+
+
+def test_result_file_formats(tmp_path):
+    assert pipeline.format_result("fid", 26.581254719518654) == "FID: 26.581254719518654"
+    assert pipeline.format_result("ofid", -2.6147972675971687e-12) == "O-FID: -2.6147972675971687e-12"
+    assert pipeline.format_result("coco", 54.63, 1.54) == "[Inception Score] mean: 54.63000 std: 1.54000"
+    assert pipeline.format_result("bird", 15.13, 0.2) == "IS = 15.13  +-  0.2"
+    assert pipeline.format_result("ois", 8.63, 0.06) == "O-IS: 8.63 +-  0.06"

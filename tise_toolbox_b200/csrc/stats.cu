@@ -112,7 +112,7 @@ __global__ void moments_finalize_kernel(const double* __restrict__ sum, const do
   const int a = (int)(idx / d), b = (int)(idx % d);
   const double ma = sum[a] / count, mb = sum[b] / count;
   const double s = a >= b ? sxx[(size_t)a * d + b] : sxx[(size_t)b * d + a];
-  sigma[idx] = (s - count * ma * mb) / (count - 1.0);
+  sigma[idx] = (s - count * (ma * mb)) / (count - 1.0);  // (ma * mb) first: exactly symmetric
   if (b == 0) mu[a] = ma;
 }
 

@@ -55,8 +55,9 @@ def _stream() -> int:
 class Engine:
     """One libtise_b200 context on one GPU with an Inception-v3 ``state_dict`` loaded."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device: Union[int, str, torch.device, None] = None,
-                 variant: str = "fid", micro_batch: int = 128, conv_impl: str = "umma", passes: int = 2):
+    def __init__(self, state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 device: Union[int, str, torch.device, None] = None, variant: str = "fid", micro_batch: int = 128,
+                 conv_impl: str = "umma", passes: int = 2):
         if not torch.cuda.is_available():
             raise RuntimeError("tise_toolbox_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -77,7 +78,8 @@ class Engine:
         self.num_classes = 0
         self.variant = None
         self.set_conv_mode(conv_impl, passes)
-        self.load_state_dict(state_dict)
+        if state_dict is not None:  # statistics-only use (moments, Frechet distance) needs no weights
+            self.load_state_dict(state_dict)
         self.set_variant(variant)
 
     # ------------------------------------------------------------------ setup
@@ -221,6 +223,19 @@ class Engine:
                                               float(eps), C.byref(out), C.byref(flags), ws.data_ptr(), ws.numel(),
                                               _stream()))
         return float(out.value), int(flags.value)
+
+
+_DEFAULT_ENGINES: Dict[int, Engine] = {}
+
+
+def default_engine(device: Union[int, str, torch.device, None] = None) -> Engine:
+    """A weight-less engine per device for the statistics entry points (moments, Frechet distance)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("tise_toolbox_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    if idx not in _DEFAULT_ENGINES:
+        _DEFAULT_ENGINES[idx] = Engine(None, device=torch.device("cuda", idx))
+    return _DEFAULT_ENGINES[idx]
 
 
 class Moments:

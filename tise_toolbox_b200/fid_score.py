@@ -1,0 +1,142 @@
+#!/usr/bin/env python3
+"""Drop-in for image_realism/FID/fid_score.py and object_fidelity/O-FID/fid_score.py on B200.
+
+Same functions, arguments, error behaviour, CLI flags and result-file format as the reference;
+underneath, feature extraction, the activation statistics and the Frechet distance run as CUDA
+kernels of libtise_b200.so.  ``--ofid`` switches the result prefix to ``O-FID:``
+(object_fidelity/O-FID/fid_score.py:219-222); the network weights decide which metric it is.
+"""
+import os
+import warnings
+from argparse import ArgumentDefaultsHelpFormatter, ArgumentParser
+
+import numpy as np
+import torch
+import torch.utils.data
+
+from . import img_data
+from .engine import Moments, default_engine
+from .inception import InceptionV3
+
+warnings.filterwarnings("ignore")
+
+parser = ArgumentParser(formatter_class=ArgumentDefaultsHelpFormatter)
+parser.add_argument("--batch-size", type=int, default=64, help="Batch size to use")
+parser.add_argument("--dims", type=int, default=2048, choices=list(InceptionV3.BLOCK_INDEX_BY_DIM),
+                    help=("Dimensionality of Inception features to use. " "By default, uses pool3 features"))
+parser.add_argument("-c", "--gpu", default="", type=str, help="GPU to use (leave blank for CPU only)")
+parser.add_argument("--path1", type=str, default=64)
+parser.add_argument("--path2", type=str, default=64)
+parser.add_argument("--saved_file", type=str, default="")
+parser.add_argument("--weights", type=str, default=None, help="torchvision Inception3 state_dict (.pth)")
+parser.add_argument("--ofid", action="store_true", help="write 'O-FID:' instead of 'FID:'")
+
+
+def _batch_features(batch, model, dims):
+    """One batch -> device float32 [B, dims].  uint8 HWC batches (tensor or ragged list) take the fused
+    GPU path; float Bx3xHxW batches in [0,1] take the reference's ``model(batch)[0]`` contract."""
+    if isinstance(batch, (list, tuple)) or batch.dtype == torch.uint8:
+        return model.features_u8(batch, dims=dims)
+    pred = model(batch)[0]
+    return pred.reshape(pred.shape[0], -1)
+
+
+def get_activations(images, model, batch_size=64, dims=2048, cuda=False, verbose=True):
+    """fid_score.py:67-118.  ``images`` is an iterable of batches with ``__len__`` = number of batches
+    (a DataLoader with drop_last=True); returns (len(images) * batch_size, dims) float64."""
+    model.eval()
+    d0 = images.__len__() * batch_size
+    if batch_size > d0:
+        print(("Warning: batch size is bigger than the data size. " "Setting batch size to data size"))
+        batch_size = d0
+    n_batches = d0 // batch_size if batch_size else 0
+    n_used_imgs = n_batches * batch_size
+    pred_arr = np.empty((n_used_imgs, dims))
+    for i, batch in enumerate(images):
+        start = i * batch_size
+        end = start + batch_size
+        pred_arr[start:end] = _batch_features(batch, model, dims).cpu().numpy().reshape(batch_size, -1)
+    if verbose:
+        print(" done")
+    return pred_arr
+
+
+def calculate_frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
+    """fid_score.py:121-171: d^2 = |mu1 - mu2|^2 + Tr(C1 + C2 - 2 sqrt(C1 C2)), evaluated in fp64 on the GPU
+    (libtise_b200 ``tise_frechet``).  Same asserts; the eps retry and the ValueError on a large imaginary
+    component are reported by the kernel's flags."""
+    mu1 = np.atleast_1d(mu1)
+    mu2 = np.atleast_1d(mu2)
+    sigma1 = np.atleast_2d(sigma1)
+    sigma2 = np.atleast_2d(sigma2)
+    assert mu1.shape == mu2.shape, "Training and test mean vectors have different lengths"
+    assert sigma1.shape == sigma2.shape, "Training and test covariances have different dimensions"
+    value, flags = default_engine().frechet(mu1, sigma1, mu2, sigma2, eps)
+    if flags & 1:
+        print(("fid calculation produces singular product; " "adding %s to diagonal of cov estimates") % eps)
+    if flags & 2:
+        raise ValueError("Imaginary component: sqrt(sigma1 sigma2) has eigenvalues with |Im| > 1e-3")
+    return np.float64(value)
+
+
+def calculate_activation_statistics(images, model, batch_size=64, dims=2048, cuda=False, verbose=True):
+    """fid_score.py:174-196, one pass: the batches' sum(x) and sum(x x^T) accumulate in fp64 on the device
+    and only (mu, sigma) come back -- the N x dims activation matrix is never materialised."""
+    model.eval()
+    mom = Moments(model.engine, dims)
+    for batch in images:
+        if len(batch) != batch_size:
+            raise ValueError("calculate_activation_statistics: batch of %d, expected %d (drop_last=True, "
+                             "fid_score.py:216)" % (len(batch), batch_size))
+        mom.update(_batch_features(batch, model, dims))
+    if verbose:
+        print(" done")
+    return mom.finalize()
+
+
+def _compute_statistics_of_path(path, model, batch_size, dims, cuda):
+    if path.endswith(".npz"):
+        f = np.load(path, allow_pickle=True)  # fid_score.py:200-203
+        m, s = f["mu"][:], f["sigma"][:]
+        f.close()
+    else:
+        # fid_score.py:206-217 with the Resize/ToTensor transform moved onto the GPU: workers only decode
+        dataset = img_data.Dataset(path, raw_u8=True)
+        dataloader = torch.utils.data.DataLoader(dataset=dataset, batch_size=batch_size, shuffle=False,
+                                                 drop_last=True, num_workers=8, collate_fn=img_data.collate_u8)
+        m, s = calculate_activation_statistics(dataloader, model, batch_size, dims, cuda)
+    return m, s
+
+
+def calculate_fid_given_paths(paths, batch_size, cuda, dims, model=None):
+    """Calculates the FID of two paths (fid_score.py:223-238)."""
+    for p in paths:
+        if not os.path.exists(p):
+            raise RuntimeError("Invalid path: %s" % p)
+    block_idx = InceptionV3.BLOCK_INDEX_BY_DIM[dims]
+    if model is None:
+        model = InceptionV3([block_idx])
+    m1, s1 = _compute_statistics_of_path(paths[0], model, batch_size, dims, cuda)
+    m2, s2 = _compute_statistics_of_path(paths[1], model, batch_size, dims, cuda)
+    return calculate_frechet_distance(m1, s1, m2, s2)
+
+
+def save_statistics(path, mu, sigma):
+    """Writes the .npz cache _compute_statistics_of_path reads (keys ``mu``, ``sigma``)."""
+    np.savez(path, mu=mu, sigma=sigma)
+
+
+if __name__ == "__main__":
+    args = parser.parse_args()
+    if args.gpu != "":
+        os.environ["CUDA_VISIBLE_DEVICES"] = args.gpu
+    if args.weights:
+        os.environ["TISE_INCEPTION_WEIGHTS"] = args.weights
+    paths = [args.path1, args.path2]
+    print(paths)
+    fid_value = calculate_fid_given_paths(paths, args.batch_size, args.gpu, args.dims).item()
+    tag = "O-FID" if args.ofid else "FID"
+    if args.saved_file:
+        with open(args.saved_file, "w") as f:
+            f.write(f"{tag}: {fid_value}")
+    print(f"{tag}: {fid_value}")

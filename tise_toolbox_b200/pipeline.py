@@ -1,0 +1,100 @@
+"""The fused, sharded form of the hot path: uint8 images in HBM -> resize -> Inception-v3 -> FID moments
+and IS partial sums, one process per GPU, a single end-of-run all-reduce.
+
+``RealismJob`` is what bench.py times and what a multi-GPU evaluation script would drive; the
+reference-facing modules (fid_score, ...) give the same numbers through the reference's call surface.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import inception_score as _is
+from .engine import Engine, ISPartials, Moments
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous global index range [lo, hi) of ``rank``: rank r gets [r n / R, (r + 1) n / R)."""
+    return (rank * n) // world, ((rank + 1) * n) // world
+
+
+def format_result(kind: str, a: float, b: Optional[float] = None) -> str:
+    """The one-line result files of the reference, byte for byte."""
+    if kind == "fid":
+        return f"FID: {a}"  # image_realism/FID/fid_score.py:251-252
+    if kind == "ofid":
+        return f"O-FID: {a}"  # object_fidelity/O-FID/fid_score.py:219-222
+    if kind == "coco":
+        return "[Inception Score] mean: {:.5f} std: {:.5f}".format(a, b)  # inception_score_star_coco.py:153
+    if kind == "bird":
+        return f"IS = {a}  +-  {b}"  # inception_score_star_bird.py:209
+    if kind == "ois":
+        return f"O-IS: {a} +-  {b}"  # object_centric_inception_score.py:127
+    raise ValueError(kind)
+
+
+class RealismJob:
+    """Streams batches of uint8 images through the trunk and keeps the additive statistics.
+
+    n_total / start: global number of images of the set and the global index of this rank's first
+    image -- they fix the split of every image independently of the number of ranks.
+    is_variant: None (FID only) or "ois" / "coco" / "bird"."""
+
+    def __init__(self, engine: Engine, n_total: int, start: int = 0, is_variant: Optional[str] = None,
+                 splits: int = 10, input_variant: str = "fid", want_moments: bool = True):
+        self.e = engine
+        self.n_total, self.pos = int(n_total), int(start)
+        self.is_variant = is_variant
+        self.input_variant = input_variant
+        self.moments = Moments(engine, 2048) if want_moments else None
+        self.parts = None
+        if is_variant is not None:
+            _, off, _, _ = _is.VARIANTS[is_variant]
+            self.parts = ISPartials(engine, engine.num_classes - off, splits)
+
+    def step(self, images: Union[torch.Tensor, Sequence[torch.Tensor]]) -> torch.Tensor:
+        """One batch (device uint8 [B,H,W,3] or list of [H,W,3]); returns the batch's pool3 features."""
+        e = self.e
+        e.set_variant(self.input_variant)
+        feat = e.features(images)
+        if self.moments is not None:
+            self.moments.update(feat)
+        if self.parts is not None:
+            _, _, use_bias, _ = _is.VARIANTS[self.is_variant]
+            logits = e.logits(feat, use_bias=use_bias)
+            _is.update_from_logits(e, self.parts, logits, self.is_variant, self.n_total, self.pos)
+        self.pos += int(feat.shape[0])
+        return feat
+
+    def step_from_host(self, pinned: torch.Tensor, staging: torch.Tensor) -> torch.Tensor:
+        """End-to-end step: async H2D copy of a pinned uint8 batch into ``staging``, then ``step``."""
+        staging[:pinned.shape[0]].copy_(pinned, non_blocking=True)
+        return self.step(staging[:pinned.shape[0]])
+
+    def finish(self, group=None) -> Dict[str, object]:
+        """All-reduce (if ``group`` / torch.distributed is initialised) and finalise on every rank."""
+        import torch.distributed as dist
+
+        use_dist = dist.is_available() and dist.is_initialized()
+        out: Dict[str, object] = {}
+        if self.moments is not None:
+            if use_dist:
+                self.moments.allreduce(group)
+            out["count"] = self.moments.count
+            out["mu"], out["sigma"] = self.moments.finalize_device()
+        if self.parts is not None:
+            if use_dist:
+                self.parts.allreduce(group)
+            _, _, _, nan_on_zero = _is.VARIANTS[self.is_variant]
+            m, s, scores = self.parts.finalize(nan_on_zero=nan_on_zero)
+            out["is_mean"], out["is_std"], out["is_scores"] = m, s, scores
+        return out
+
+
+def fid_from_stats(engine: Engine, a: Dict[str, object], b: Dict[str, object], eps: float = 1e-6) -> float:
+    value, flags = engine.frechet(a["mu"], a["sigma"], b["mu"], b["sigma"], eps)
+    if flags & 2:
+        raise ValueError("Imaginary component: sqrt(sigma1 sigma2) has eigenvalues with |Im| > 1e-3")
+    return value

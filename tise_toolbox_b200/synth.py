@@ -141,3 +141,27 @@ def inception_state_dict(seed: int = 0, num_classes: int = 1000, fc_std: float =
             v = torch.randn(shape, generator=g) * 0.01
         out[name] = v.to(torch.float32).contiguous()
     return out
+
+
+def calibrate_head(state_dict: Dict[str, torch.Tensor], feats: torch.Tensor, temperature: float,
+                   target_std: float = 2.5, seed: int = 0, class_offset: int = 0) -> Dict[str, torch.Tensor]:
+    """Returns a copy of ``state_dict`` whose fc head makes the inception score informative.
+
+    With a random head the image-independent part of the logits, W . mean(pool3), dwarfs the
+    image-dependent part (post-ReLU features have mean >> std), every image gets the same arg-max and
+    IS ~ 1.0000x -- a vacuous parity target.  Given pool3 features ``feats`` [n, 2048] of
+    some calibration images, the fc rows are redrawn orthogonal to the mean feature and scaled so that
+    logits / temperature vary with ``target_std`` across images; the bias is small noise."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(7919 * seed + 13)
+    c = int(state_dict["fc.weight"].shape[0])
+    f = feats.detach().cpu().double()
+    m = f.mean(0)
+    w = torch.randn(c, f.shape[1], generator=g, dtype=torch.float64)
+    w = w - (w @ m)[:, None] * m[None, :] / (m @ m)
+    z = (f - m) @ w.t()
+    w = w * (target_std * temperature / z[:, class_offset:].std(0).mean().clamp_min(1e-12))
+    out = dict(state_dict)
+    out["fc.weight"] = w.float().contiguous()
+    out["fc.bias"] = (torch.randn(c, generator=g) * 0.1).float()
+    return out
