@@ -1,0 +1,323 @@
+#!/usr/bin/env python3
+"""Benchmark of the image-realism hot path on B200 (contract: see the task prompt / DESIGN.md §Measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+One "step" = one batch of B synthetic 256x256 uint8 images per rank through the whole path:
+Pillow-exact resize -> Inception-v3 trunk (tcgen05) -> pool3 -> FID moments + fc head + IS* partial sums.
+N = 1 is BASELINE.json configs[1] (IS* on CUB-shaped images, bird head, 10 splits; the FID moments ride
+along), N > 1 is configs[2] (FID + IS* sharded, one all-reduce at the end, outside the steady state).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONV_FLOP_PER_IMAGE = 2 * 5711168096  # 94 convolutions of torchvision Inception3 at 299x299
+IMG_BYTES = 256 * 256 * 3
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--batch", type=int, default=1024, help="images per rank per step")
+    p.add_argument("--micro-batch", type=int, default=256)
+    p.add_argument("--pool", type=int, default=2048, help="distinct synthetic images resident per rank")
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--passes", type=int, default=2)
+    p.add_argument("--cpu-sample", type=int, default=96)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-frechet", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"tflops": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1398.3))),
+                "hbm_gbs": float(d.get("hbm_gbs", 6551.0)), "source": "MEASURED_PEAKS.json (sustained cuBLAS bf16)"}
+    return {"tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback of B200_PROFILING.md"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md 'clocks line')."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+# --------------------------------------------------------------------------------------------- CPU arms
+def cpu_pipeline_images_per_s(n_images, seed=1, threads=None, repeats=1):
+    """The oracle (port of the reference's CPU path: PIL resize, ToTensor + affine, torchvision Inception3
+    fp32, fc head, float64 statistics) on the host cores.  Returns (img/s, seconds, threads)."""
+    from PIL import Image
+
+    from oracle import restate
+    from tise_toolbox_b200 import synth
+
+    if threads:
+        torch.set_num_threads(threads)
+    sd = synth.inception_state_dict(0, num_classes=51)
+    trunk = restate.Trunk(sd, num_classes=51)
+    imgs = synth.images(seed, 0, 0, n_images).numpy()
+    lut = restate.input_lut("bird")
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        feats = []
+        for i0 in range(0, n_images, 32):
+            chunk = imgs[i0:i0 + 32]
+            x = torch.empty(len(chunk), 3, 299, 299)
+            for j, im in enumerate(chunk):  # transforms.Resize -> Pillow, as fid_score.py:210 does
+                r = torch.from_numpy(np.asarray(Image.fromarray(im).resize((299, 299), Image.BILINEAR))).long()
+                for c in range(3):
+                    x[j, c] = lut[c][r[:, :, c]]
+            f = trunk.pool3(x)
+            feats.append(f)
+        f = torch.cat(feats)
+        act = f.numpy().astype(np.float64)
+        if n_images > 1:
+            restate.calculate_activation_statistics(act)
+        preds = restate.bird_preds(trunk.net.fc(f))
+        restate.isstar_inception_score(preds, min(10, n_images))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_images / best, best, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU path on the host cores (rank 0 only); each step is a bounded sample."""
+    if rank != 0:
+        return
+    per_step = 32
+    for _ in range(max(args.warmup, 0)):
+        cpu_pipeline_images_per_s(per_step)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_pipeline_images_per_s(per_step)
+    dt = time.perf_counter() - t0
+    v = per_step * args.steps / dt
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": "FID/IS* images/sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: IS* bird head + FID moments, 256x256 uint8 synthetic (CPU oracle port of the "
+                                   "reference path; the Python reference itself cannot travel to the GPU box)",
+                       "images_per_step": per_step},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": "%d steps x %d images, torch CPU fp32, os.cpu_count()=%s" % (args.steps, per_step, os.cpu_count())},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+
+    from tise_toolbox_b200 import synth
+    from tise_toolbox_b200.engine import Engine, T_BIRD
+    from tise_toolbox_b200.pipeline import RealismJob, shard_range
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch, args.steps, args.warmup
+    n_total = world * B * (K + W)
+    lo, _ = shard_range(n_total, rank, world)
+
+    # ---- setup (untimed): weights, resident image pool, calibrated IS head
+    sd = synth.inception_state_dict(0, num_classes=51)
+    eng = Engine(sd, device=dev, variant="bird", micro_batch=args.micro_batch, passes=args.passes)
+    pool = torch.cat([synth.images(1, 0, rank * args.pool + i, min(256, args.pool - i), device=dev)
+                      for i in range(0, args.pool, 256)])
+    calib = eng.features(pool[:64])
+    sd = synth.calibrate_head(sd, calib.cpu(), T_BIRD, class_offset=1)
+    eng.load_state_dict(sd)
+    job = RealismJob(eng, n_total=n_total, start=lo, is_variant="bird", splits=10, input_variant="bird")
+
+    def batch_of(step):
+        o = (step * B) % args.pool
+        if o + B <= args.pool:
+            return pool[o:o + B]
+        return torch.cat([pool[o:], pool[:o + B - args.pool]])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(W):
+        job.step(batch_of(s))
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(K):
+        job.step(batch_of(W + s))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    launches = eng.launches - l0
+    barrier()
+    if sampler:
+        sampler.stop_flag = True
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    value = world * B * K / (ms / 1e3)
+
+    # ---- the path's one exchange step + finalisation (outside the steady state; reported, not timed in `value`)
+    t0 = time.perf_counter()
+    res = job.finish()
+    torch.cuda.synchronize()
+    finish_ms = 1e3 * (time.perf_counter() - t0)
+
+    # ---- end-to-end: same step through the public API from pinned host memory, result read back every step
+    host = torch.empty((min(args.pool, 2 * B), 256, 256, 3), dtype=torch.uint8).pin_memory()
+    host.copy_(pool[:host.shape[0]].cpu())
+    staging = torch.empty((B, 256, 256, 3), dtype=torch.uint8, device=dev)
+    job2 = RealismJob(eng, n_total=world * B * (K + W), start=lo, is_variant="bird", splits=10, input_variant="bird")
+    d2h = torch.empty(job2.parts.f.numel(), dtype=torch.float64).pin_memory()
+
+    def e2e_step(s):
+        o = (s * B) % max(1, host.shape[0] - B + 1)
+        job2.step_from_host(host[o:o + B], staging)
+        d2h.copy_(job2.parts.f, non_blocking=True)  # the step's running IS partial sums -> host
+        torch.cuda.current_stream().synchronize()
+
+    for s in range(min(W, 2)):
+        e2e_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for s in range(K):
+        e2e_step(s)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    barrier()
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (float(e2e_ms.item()) / 1e3)
+
+    # ---- roofline of the dominant kernel (conv_umma_kernel): CUDA events around every launch, 2 extra steps
+    pk = peaks()
+    eng.profile(True)
+    for s in range(2):
+        job2.step(batch_of(s))
+    prof = eng.profile_read()
+    eng.profile(False)
+    conv_ms, conv_launches, conv_flops = prof["conv"]
+    trunk_ms = sum(v[0] for v in prof.values())
+    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel", "achieved": achieved, "peak": pk["tflops"],
+                "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["source"],
+                "launches_per_step": conv_launches // 2, "avg_launch_us": 1e3 * conv_ms / max(1, conv_launches),
+                "algorithmic_gflop_per_image": conv_flops / (2 * B) / 1e9,
+                "share_of_trunk_time": conv_ms / trunk_ms if trunk_ms else None,
+                "other_kernels_ms_per_step": {k: v[0] / 2 for k, v in prof.items() if k != "conv"},
+                "how": "cudaEvent pairs on the launch stream around each launch, summed over 2 steps after the timed region"}
+
+    line = {"metric": "FID/IS* images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 x (f16 hi + f16 lo) operands, f32 accumulate" if args.passes == 2 else "f16, f32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": ("cfg2: IS* (bird head, T=0.598, 10 splits) + FID moments" if world == 1 else
+                                    "cfg3: FID + IS* sharded over %d GPUs, one all-reduce at the end" % world),
+                       "image": "256x256x3 uint8", "images_per_step_per_gpu": B, "micro_batch": args.micro_batch,
+                       "resident_pool_images": args.pool, "l2": "inputs (%.0f MB/step) larger than L2" % (B * IMG_BYTES / 1e6),
+                       "random_init": "seeded He-normal Inception3, calibrated 51-way head"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * IMG_BYTES,
+                    "d2h_bytes_per_step": int(d2h.numel() * 8)},
+            "gpu_launches": int(launches), "roofline": roofline,
+            "finish_ms": finish_ms, "is_mean": res.get("is_mean"), "count": res.get("count")}
+    if rank == 0:
+        line["clocks"] = sampler.summary()
+        if world == 1 and not args.no_cpu_baseline:
+            v, secs, cores = cpu_pipeline_images_per_s(args.cpu_sample)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": "%d of the same synthetic images, %.1f s, torch CPU fp32 (oracle port of the "
+                                              "reference path), os.cpu_count()=%s" % (args.cpu_sample, secs, os.cpu_count())}
+        if not args.no_frechet:
+            line["frechet"] = frechet_latency(eng, res, world == 1 and not args.no_cpu_baseline)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def frechet_latency(eng, res, with_cpu):
+    """Frechet 'sqrtm' latency at d = 2048 on this run's own statistics against a perturbed copy."""
+    mu, sigma = res["mu"], res["sigma"]
+    g = torch.Generator(device="cpu").manual_seed(3)
+    d = mu.shape[0]
+    q = torch.randn(d, 64, generator=g, dtype=torch.float64).to(mu.device) * 0.02
+    sigma2 = sigma * 1.1 + q @ q.t()
+    mu2 = mu + 0.05
+    eng.frechet(mu, sigma, mu2, sigma2)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    v, _ = eng.frechet(mu, sigma, mu2, sigma2)
+    gpu_ms = 1e3 * (time.perf_counter() - t0)
+    out = {"d": int(d), "gpu_ms": gpu_ms, "value": v}
+    if with_cpu:
+        from oracle import restate
+        a = [t.cpu().numpy() for t in (mu, sigma, mu2, sigma2)]
+        t0 = time.perf_counter()
+        ref = float(restate.calculate_frechet_distance(*a))
+        out["cpu_scipy_sqrtm_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["rel_diff_vs_scipy"] = abs(v - ref) / abs(ref)
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -152,6 +152,14 @@ int tise_debug_conv(tise_ctx* ctx, int impl, int passes, const void* d_x, int n,
                     const float* h_w, const float* h_scale, const float* h_shift, int cout, int kh, int kw,
                     int stride, int pad_h, int pad_w, int relu, void* d_y);
 
+/* Per-kernel-kind device timing of tise_inception_features, taken with CUDA events recorded on the
+ * launch stream around every kernel (kinds: 0 stem conv, 1 tcgen05/SIMT conv, 2 max pool, 3 avg pool,
+ * 4 global avg pool).  Enabling clears earlier records; tise_profile_read waits for the recorded events
+ * and fills three arrays of 8: total milliseconds, launches, and algorithmic FLOPs (2 M N K of the
+ * convolutions, padding channels excluded).  bench.py derives roofline.achieved from these. */
+int tise_profile_enable(tise_ctx* ctx, int on);
+int tise_profile_read(tise_ctx* ctx, double* ms_by_kind, long long* launches_by_kind, double* flops_by_kind);
+
 /* Number of kernels this library has launched on this ctx since creation (for bench.py's gpu_launches). */
 long long tise_launch_count(const tise_ctx* ctx);
 

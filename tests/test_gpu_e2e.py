@@ -1,0 +1,205 @@
+"""-m gpu: the reference-facing entry points end to end against the oracle and the golden vectors
+produced by the reference's own code (tests/golden, tools/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate
+from tise_toolbox_b200 import fid_score, synth
+from tise_toolbox_b200.engine import Engine, Moments
+from tise_toolbox_b200.inception import InceptionV3
+from tise_toolbox_b200.pipeline import RealismJob, fid_from_stats
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(os.path.join(GOLD, "golden.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def model(state_dict):
+    return InceptionV3([3], state_dict=state_dict, micro_batch=32)
+
+
+class Batches(list):
+    pass
+
+
+def _float_batches(imgs, bs):
+    """What the reference's DataLoader yields: PIL-resized, ToTensor'd float batches in [0, 1]."""
+    t = torch.stack([torch.from_numpy(restate.pillow_resize_bilinear(im.numpy())).permute(2, 0, 1).float().div(255)
+                     for im in imgs])
+    return Batches([t[i:i + bs] for i in range(0, len(t) - bs + 1, bs)])
+
+
+def test_get_activations_matches_reference_golden(model, golden):
+    sets = [synth.images(1, 0, 0, 16), synth.images(2, 1, 0, 16)]
+    ref = np.load(os.path.join(GOLD, "pool3_ref.npy"))
+    acts = [fid_score.get_activations(_float_batches(s, 8), model, batch_size=8, dims=2048, cuda=True, verbose=False)
+            for s in sets]
+    assert acts[0].shape == (16, 2048) and acts[0].dtype == np.float64
+    got = np.concatenate([acts[0][:4], acts[1][:4]])
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 5e-4
+    # uint8 fast path == float path (the LUT is bit exact)
+    u8 = fid_score.get_activations(Batches([sets[0][:8], sets[0][8:]]), model, batch_size=8, verbose=False)
+    assert np.array_equal(u8, acts[0])
+    # FID of the reference on the same 2 x 16 images (rank-deficient, scipy returns complex): tolerance 1e-3
+    st = [fid_score.calculate_activation_statistics(_float_batches(s, 8), model, batch_size=8, verbose=False)
+          for s in sets]
+    v = fid_score.calculate_frechet_distance(st[0][0], st[0][1], st[1][0], st[1][1])
+    assert isinstance(v, np.float64)
+    assert abs(v - golden["fid_2x16"]["value"]) <= 1e-3 * golden["fid_2x16"]["value"]
+
+
+def _d192():
+    rng = np.random.RandomState(5)
+    d = 192
+    xa, xb = rng.randn(400, d) * rng.rand(d) + rng.randn(d), rng.randn(500, d) * rng.rand(d) * 1.3 + rng.randn(d)
+    return xa.mean(0), np.cov(xa, rowvar=False), xb.mean(0), np.cov(xb, rowvar=False)
+
+
+def test_frechet_matches_reference_golden(golden):
+    ma, sa, mb, sb = _d192()
+    v = fid_score.calculate_frechet_distance(ma, sa, mb, sb)
+    assert abs(v - golden["frechet_d192"]["value"]) <= 1e-9 * golden["frechet_d192"]["value"]
+    assert abs(fid_score.calculate_frechet_distance(ma, sa, ma, sa)) <= 1e-7  # FID(X, X) ~ 0 known answer
+
+
+@pytest.mark.parametrize("d,n1,n2", [(64, 300, 200), (768, 1500, 900), (2048, 2500, 2300), (2048, 300, 400)])
+def test_frechet_matches_scipy(d, n1, n2):
+    rng = np.random.RandomState(d + n1)
+    basis = rng.randn(d, d) / np.sqrt(d)
+    xa = (rng.randn(n1, d) * np.linspace(0.05, 1.0, d)) @ basis + 1.7
+    xb = (rng.randn(n2, d) * np.linspace(0.08, 1.2, d)) @ basis + 1.8
+    ma, sa, mb, sb = xa.mean(0), np.cov(xa, rowvar=False), xb.mean(0), np.cov(xb, rowvar=False)
+    ref = float(restate.calculate_frechet_distance(ma, sa, mb, sb))
+    got = float(fid_score.calculate_frechet_distance(ma, sa, mb, sb))
+    assert abs(got - ref) <= 1e-6 * abs(ref), (got, ref)
+
+
+def test_frechet_error_behaviour():
+    ma, sa, mb, sb = _d192()
+    with pytest.raises(AssertionError):
+        fid_score.calculate_frechet_distance(ma[:-1], sa, mb, sb)
+    with pytest.raises(AssertionError):
+        fid_score.calculate_frechet_distance(ma, sa[:-1, :-1], mb, sb)
+    with pytest.raises(RuntimeError):
+        fid_score.calculate_fid_given_paths(["/nonexistent/a", "/nonexistent/b"], 50, "0", 2048)
+
+
+def test_fid_cli_on_png_folders(tmp_path, model, state_dict):
+    """cfg1 in miniature through the file interface: 2 x 40 PNGs, batch 8 (drop_last), .npz cache."""
+    from PIL import Image
+
+    sets = [synth.images(1, 0, 200, 20), synth.images(2, 1, 200, 21)]  # 21: one image is dropped by drop_last
+    dirs = []
+    for k, s in enumerate(sets):
+        d = tmp_path / ("set%d" % k)
+        d.mkdir()
+        for i, im in enumerate(s):
+            Image.fromarray(im.numpy()).save(str(d / ("img_%05d.png" % i)))
+        dirs.append(str(d))
+    v = fid_score.calculate_fid_given_paths(dirs, 10, "0", 2048, model=model)
+    # oracle on the same files in os.walk order
+    trunk = restate.Trunk(state_dict)
+    from tise_toolbox_b200 import img_data
+    stats = []
+    for d in dirs:
+        names = img_data.Dataset(d).file_names
+        ims = [np.asarray(Image.open(n).convert("RGB")) for n in names]
+        ims = ims[:len(ims) // 10 * 10]
+        x = restate.preprocess(ims, "fid")
+        act = restate.get_activations([x[i:i + 10] for i in range(0, len(ims), 10)], trunk, 10)
+        stats.append(restate.calculate_activation_statistics(act))
+    ref = float(restate.calculate_frechet_distance(stats[0][0], stats[0][1], stats[1][0], stats[1][1]))
+    assert abs(v - ref) <= 1e-3 * abs(ref), (v, ref)
+    # .npz cache round trip (fid_score.py:200-203)
+    m, s = fid_score._compute_statistics_of_path(dirs[0], model, 10, 2048, "0")
+    fid_score.save_statistics(str(tmp_path / "real.npz"), m, s)
+    v2 = fid_score.calculate_fid_given_paths([str(tmp_path / "real.npz"), dirs[1]], 10, "0", 2048, model=model)
+    assert abs(v2 - v) <= 1e-9 * abs(v)
+
+
+@pytest.mark.parametrize("variant,classes", [("ois", 80), ("bird", 51), ("coco", 1008)])
+def test_inception_score_variants_against_oracle(variant, classes):
+    from tise_toolbox_b200 import inception_score as isc
+
+    t, off, use_bias, _ = isc.VARIANTS[variant]
+    sd = synth.inception_state_dict(4, num_classes=classes)
+    imgs = torch.cat([synth.images(1, 0, 300, 32), synth.images(2, 1, 300, 32)])
+    x = restate.preprocess([im.numpy() for im in imgs], variant)
+    trunk = restate.Trunk(sd, num_classes=classes)
+    sd = synth.calibrate_head(sd, trunk.pool3(x), t, seed=classes, class_offset=off)
+    trunk = restate.Trunk(sd, num_classes=classes)
+    pool3 = trunk.pool3(x)
+    if variant == "ois":
+        ref = restate.ois_inception_score(restate.ois_preds(trunk.net.fc(pool3)), 10)
+    elif variant == "coco":
+        ref = restate.isstar_inception_score(restate.coco_preds(pool3, sd["fc.weight"]), 10)
+    else:
+        ref = restate.isstar_inception_score(restate.bird_preds(trunk.net.fc(pool3)), 10)
+    eng = Engine(sd, device="cuda:0", variant=variant, micro_batch=32)
+    job = RealismJob(eng, n_total=len(imgs), is_variant=variant, splits=10, input_variant=variant, want_moments=False)
+    job.step(imgs[:40].cuda())
+    job.step(imgs[40:].cuda())
+    res = job.finish()
+    assert ref[0] > 1.5, "vacuous IS target"
+    assert abs(res["is_mean"] - ref[0]) <= 1e-3 * ref[0], (res["is_mean"], ref)
+    assert abs(res["is_std"] - ref[1]) <= 2e-2 * ref[1] + 1e-4, (res["is_std"], ref)
+
+
+def test_ois_golden_through_reference_facing_module(golden):
+    from tise_toolbox_b200 import object_centric_inception_score as ois
+
+    sd80 = synth.inception_state_dict(3, num_classes=80)
+    head = np.load(os.path.join(GOLD, "ois_head.npy"))
+    sd80["fc.weight"] = torch.from_numpy(head[:, :2048].copy())
+    sd80["fc.bias"] = torch.from_numpy(head[:, 2048].copy())
+    imgs = torch.cat([synth.images(1, 0, 100, 20), synth.images(2, 1, 100, 20)])
+    x = restate.preprocess([im.numpy() for im in imgs], "ois")  # what IgnoreLabelDataset yields
+    m, s = ois.inception_score(list(x), cuda=True, batch_size=8, resize=False, splits=4, state_dict=sd80)
+    assert abs(m - golden["ois_40"]["mean"]) <= 1e-3 * golden["ois_40"]["mean"], (m, golden["ois_40"])
+    with pytest.raises(AssertionError):
+        ois.inception_score(list(x[:4]), batch_size=8, state_dict=sd80)  # N > batch_size (:27)
+
+
+def test_fid_parity_100_vs_100(state_dict):
+    """BASELINE.json configs[0] in miniature (100 vs 100, batch 50): FID within 1e-3 of the CPU path."""
+    a, b = synth.images(1, 0, 1000, 100), synth.images(2, 1, 1000, 100)
+    trunk = restate.Trunk(state_dict)
+    st = []
+    for s in (a, b):
+        x = restate.preprocess([im.numpy() for im in s], "fid")
+        st.append(restate.calculate_activation_statistics(restate.get_activations([x[:50], x[50:]], trunk, 50)))
+    ref = float(restate.calculate_frechet_distance(st[0][0], st[0][1], st[1][0], st[1][1]))
+    eng = Engine(state_dict, device="cuda:0", micro_batch=64)
+    res = []
+    for s in (a, b):
+        job = RealismJob(eng, n_total=100)
+        job.step(s[:50].cuda())
+        job.step(s[50:].cuda())
+        res.append(job.finish())
+    got = fid_from_stats(eng, res[0], res[1])
+    assert abs(got - ref) <= 1e-3 * abs(ref), (got, ref)
+
+
+def test_ragged_crops_path(state_dict):
+    """cfg4 in miniature: variable-size crops (up- and down-scaling) through resize + trunk."""
+    sizes = synth.crop_sizes(8, 0, 10)
+    crops = [synth.images(5, 1, i, 1, h, w)[0] for i, (h, w) in enumerate(sizes)]
+    eng = Engine(state_dict, device="cuda:0", micro_batch=8)
+    got = eng.features([c.cuda() for c in crops]).cpu().numpy()
+    ref = restate.Trunk(state_dict).pool3(restate.preprocess([c.numpy() for c in crops], "fid")).numpy()
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 5e-4
+
+
+def test_empty_batch(engine):
+    f = engine.features(torch.empty((0, 64, 64, 3), dtype=torch.uint8, device="cuda"))
+    assert tuple(f.shape) == (0, 2048)

@@ -52,6 +52,8 @@ _SIGNATURES = {
     "tise_debug_conv": (C.c_int, [c_ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_void_p]),
+    "tise_profile_enable": (C.c_int, [c_ctx_p, C.c_int]),
+    "tise_profile_read": (C.c_int, [c_ctx_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
     "tise_launch_count": (C.c_longlong, [c_ctx_p]),
 }
 

@@ -147,3 +147,34 @@ extern "C" int tise_debug_conv(tise_ctx* ctx, int impl, int passes, const void* 
   for (void* p : allocs) cudaFree(p);
   return rc;
 }
+
+extern "C" int tise_profile_enable(tise_ctx* ctx, int on) {
+  if (!ctx) return TISE_ERR_INVALID;
+  for (auto& r : ctx->prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  ctx->prof.clear();
+  ctx->profiling = on != 0;
+  return TISE_OK;
+}
+
+extern "C" int tise_profile_read(tise_ctx* ctx, double* ms_by_kind, long long* launches_by_kind, double* flops_by_kind) {
+  if (!ctx || !ms_by_kind || !launches_by_kind || !flops_by_kind) return TISE_ERR_INVALID;
+  for (int k = 0; k < 8; ++k) {
+    ms_by_kind[k] = 0.0;
+    launches_by_kind[k] = 0;
+    flops_by_kind[k] = 0.0;
+  }
+  for (auto& r : ctx->prof) {
+    TISE_CUDA(ctx, cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    TISE_CUDA(ctx, cudaEventElapsedTime(&ms, r.a, r.b));
+    if (r.kind >= 0 && r.kind < 8) {
+      ms_by_kind[r.kind] += ms;
+      launches_by_kind[r.kind] += 1;
+      flops_by_kind[r.kind] += r.flops;
+    }
+  }
+  return TISE_OK;
+}

@@ -31,6 +31,14 @@ struct tise_ctx {
   float* d_lut = nullptr;  // 768 floats
   bool lut_set = false;
   tise::Net* net = nullptr;
+  // optional per-step timing of tise_inception_features (tise_profile_enable / tise_profile_read)
+  bool profiling = false;
+  struct ProfRec {
+    int kind;
+    cudaEvent_t a, b;
+    double flops;
+  };
+  std::vector<ProfRec> prof;
 };
 
 namespace tise {

@@ -437,6 +437,15 @@ int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, i
   int rc = get_plan(ctx, d_ws, n, tap, &plan);
   if (rc) return rc;
   for (Step& s : plan->steps) {
+    tise_ctx::ProfRec rec{(int)s.kind, nullptr, nullptr, 0.0};
+    if (ctx->profiling) {
+      TISE_CUDA(ctx, cudaEventCreate(&rec.a));
+      TISE_CUDA(ctx, cudaEventCreate(&rec.b));
+      if (s.kind == STEP_CONV)  // algorithmic FLOPs: 2 * M * Cout * (R * S * Cin), padding channels excluded
+        rec.flops = 2.0 * (double)s.conv.n * s.conv.ho * s.conv.wo * s.layer->cout * s.layer->R * s.layer->S * s.layer->cin;
+      if (s.kind == STEP_STEM) rec.flops = 2.0 * (double)n * 149 * 149 * 32 * 27;
+      TISE_CUDA(ctx, cudaEventRecord(rec.a, st));
+    }
     switch (s.kind) {
       case STEP_STEM:
         rc = launch_stem(ctx, d_u8, d_f32, n, net->d_stem_w, net->d_stem_scale, net->d_stem_shift, (__half*)s.out, st);
@@ -462,6 +471,10 @@ int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, i
         break;
     }
     if (rc) return rc;
+    if (ctx->profiling) {
+      TISE_CUDA(ctx, cudaEventRecord(rec.b, st));
+      ctx->prof.push_back(rec);
+    }
   }
   return TISE_OK;
 }

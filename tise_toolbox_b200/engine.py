@@ -126,6 +126,18 @@ class Engine:
     def launches(self) -> int:
         return int(self.lib.tise_launch_count(self.ctx))
 
+    def profile(self, on: bool):
+        self._check(self.lib.tise_profile_enable(self.ctx, int(bool(on))))
+
+    def profile_read(self):
+        """{kind: (ms, launches, algorithmic flops)} for kinds stem / conv / maxpool / avgpool / gap."""
+        ms = (C.c_double * 8)()
+        ln = (C.c_longlong * 8)()
+        fl = (C.c_double * 8)()
+        self._check(self.lib.tise_profile_read(self.ctx, ms, ln, fl))
+        names = ["stem", "conv", "maxpool", "avgpool", "gap"]
+        return {n: (ms[i], int(ln[i]), fl[i]) for i, n in enumerate(names)}
+
     # ------------------------------------------------------------------ buffers
     def _buf(self, name: str, nbytes: int) -> torch.Tensor:
         cur = getattr(self, name)
