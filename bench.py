@@ -106,7 +106,7 @@ def cpu_pipeline_images_per_s(n_images, seed=1, threads=None, repeats=1):
             chunk = imgs[i0:i0 + 32]
             x = torch.empty(len(chunk), 3, 299, 299)
             for j, im in enumerate(chunk):  # transforms.Resize -> Pillow, as fid_score.py:210 does
-                r = torch.from_numpy(np.asarray(Image.fromarray(im).resize((299, 299), Image.BILINEAR))).long()
+                r = torch.from_numpy(np.array(Image.fromarray(im).resize((299, 299), Image.BILINEAR))).long()
                 for c in range(3):
                     x[j, c] = lut[c][r[:, :, c]]
             f = trunk.pool3(x)
@@ -115,7 +115,8 @@ def cpu_pipeline_images_per_s(n_images, seed=1, threads=None, repeats=1):
         act = f.numpy().astype(np.float64)
         if n_images > 1:
             restate.calculate_activation_statistics(act)
-        preds = restate.bird_preds(trunk.net.fc(f))
+        with torch.no_grad():
+            preds = restate.bird_preds(trunk.net.fc(f))
         restate.isstar_inception_score(preds, min(10, n_images))
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)

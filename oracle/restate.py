@@ -233,7 +233,7 @@ T_OIS = 2.1737587451934814    # object_centric_inception_score.py:55
 
 def ois_preds(logits: torch.Tensor) -> np.ndarray:
     """object_centric_inception_score.py:54-57: softmax(logits / T) -> float64 rows of preds."""
-    x = logits / T_OIS
+    x = logits.detach() / T_OIS
     return F.softmax(x, dim=1).data.cpu().numpy().astype(np.float64)
 
 
@@ -253,14 +253,14 @@ def ois_inception_score(preds: np.ndarray, splits: int) -> Tuple[float, float]:
 
 def coco_preds(pool3: torch.Tensor, w: torch.Tensor) -> np.ndarray:
     """inception_score_star_coco.py:104-108: matmul(pool3, W) (no bias), / T, softmax, float32."""
-    logits = pool3 @ w.t()
+    logits = pool3.detach() @ w.detach().t()
     logits = logits / torch.tensor(T_COCO, dtype=torch.float32)
     return F.softmax(logits, dim=1).numpy()
 
 
 def bird_preds(logits51: torch.Tensor) -> np.ndarray:
     """inception_score_star_bird.py:187-194: drop background class 0, / T, softmax, float32."""
-    known = logits51[:, 1:]
+    known = logits51.detach()[:, 1:]
     known = known / torch.tensor(T_BIRD, dtype=torch.float32)
     return F.softmax(known, dim=1).numpy()
 

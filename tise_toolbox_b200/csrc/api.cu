@@ -1,4 +1,6 @@
 // C ABI glue of libtise_b200.so (see include/tise_b200.h).
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "net.cuh"
@@ -166,15 +168,19 @@ extern "C" int tise_profile_read(tise_ctx* ctx, double* ms_by_kind, long long* l
     launches_by_kind[k] = 0;
     flops_by_kind[k] = 0.0;
   }
+  const char* dump = getenv("TISE_PROFILE_DUMP");  // optional per-launch listing: "<ms> <GFLOP> <tag>"
+  FILE* df = dump ? fopen(dump, "w") : nullptr;
   for (auto& r : ctx->prof) {
     TISE_CUDA(ctx, cudaEventSynchronize(r.b));
     float ms = 0.f;
     TISE_CUDA(ctx, cudaEventElapsedTime(&ms, r.a, r.b));
+    if (df) fprintf(df, "%.4f %.4f %s\n", ms, r.flops * 1e-9, r.tag);
     if (r.kind >= 0 && r.kind < 8) {
       ms_by_kind[r.kind] += ms;
       launches_by_kind[r.kind] += 1;
       flops_by_kind[r.kind] += r.flops;
     }
   }
+  if (df) fclose(df);
   return TISE_OK;
 }

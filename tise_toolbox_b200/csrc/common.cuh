@@ -37,6 +37,7 @@ struct tise_ctx {
     int kind;
     cudaEvent_t a, b;
     double flops;
+    char tag[96];
   };
   std::vector<ProfRec> prof;
 };

@@ -437,8 +437,13 @@ int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, i
   int rc = get_plan(ctx, d_ws, n, tap, &plan);
   if (rc) return rc;
   for (Step& s : plan->steps) {
-    tise_ctx::ProfRec rec{(int)s.kind, nullptr, nullptr, 0.0};
+    tise_ctx::ProfRec rec{(int)s.kind, nullptr, nullptr, 0.0, {0}};
     if (ctx->profiling) {
+      if (s.kind == STEP_CONV)
+        snprintf(rec.tag, sizeof(rec.tag), "conv n%d %dx%d cin%d cout%d k%dx%d s%d", s.conv.n, s.conv.h, s.conv.w,
+                 s.layer->cin, s.layer->cout, s.layer->R, s.layer->S, s.layer->stride);
+      else
+        snprintf(rec.tag, sizeof(rec.tag), "kind%d n%d %dx%d c%d", (int)s.kind, s.n, s.h, s.w, s.c);
       TISE_CUDA(ctx, cudaEventCreate(&rec.a));
       TISE_CUDA(ctx, cudaEventCreate(&rec.b));
       if (s.kind == STEP_CONV)  // algorithmic FLOPs: 2 * M * Cout * (R * S * Cin), padding channels excluded
