@@ -125,10 +125,12 @@ extern "C" int tise_debug_conv(tise_ctx* ctx, int impl, int passes, const void* 
     a.h = h;
     a.w = w;
     a.in_stride = cin;
-    a.out = d_y;
-    a.out_stride = cout;
+    a.n_segs = 1;
+    a.segs[0].out = d_y;
+    a.segs[0].out_stride = cout;
+    a.segs[0].c = cout;
+    a.segs[0].relu = relu;
     a.out_f32 = 0;
-    a.relu = relu;
     a.ho = conv_out_dim(h, kh, stride, pad_h);
     a.wo = conv_out_dim(w, kw, stride, pad_w);
     if (impl == TISE_CONV_UMMA) {

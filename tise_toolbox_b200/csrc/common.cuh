@@ -81,15 +81,23 @@ struct ConvLayer {
   float* d_shift = nullptr;  // [cout]  beta - mean * gamma / sqrt(var + eps)
 };
 
-// A conv launch: NHWC fp16 input view -> NHWC output view (fp16, or fp32 if out_f32).
+// A conv launch: NHWC fp16 input view -> up to kMaxSegs NHWC destinations.  The layer's output channels
+// are split into consecutive segments, each written into its own tensor / channel slice (this is how
+// sibling 1x1 convolutions that read the same input run as one GEMM, and how torch.cat costs nothing).
+constexpr int kMaxSegs = 4;
+struct ConvSeg {
+  void* out = nullptr;  // base of the destination tensor with the channel offset already applied
+  int out_stride = 0;   // elements per destination pixel
+  int c = 0;            // channels in this segment
+  int relu = 1;         // 0: raw scale/shift only (branch_pool convs, pooled + BN + ReLU afterwards)
+};
 struct ConvArgs {
   const __half* in = nullptr;  // base of the input tensor (channel 0 of the view)
   int n = 0, h = 0, w = 0;     // input spatial dims
   int in_stride = 0;           // elements per input pixel (>= cin)
-  void* out = nullptr;         // base of the output tensor + channel offset already applied
-  int out_stride = 0;          // elements per output pixel
-  int out_f32 = 0;
-  int relu = 1;
+  ConvSeg segs[kMaxSegs];
+  int n_segs = 0;
+  int out_f32 = 0;  // all segments fp32 (Mixed_7c) or all fp16
   int ho = 0, wo = 0;
 };
 
@@ -102,6 +110,9 @@ struct UmmaPlan {  // tensor maps are tied to pointers, so a plan is built once 
   alignas(64) CUtensorMap tm_a;
   alignas(64) CUtensorMap tm_bhi;
   alignas(64) CUtensorMap tm_blo;
+  alignas(64) CUtensorMap tm_out[kMaxSegs];  // 2D (channels of the segment, all output pixels) store maps
+  int nt = 0;     // output channels per tile
+  int box_w = 0;  // channels per TMA store box (16 or 32)
   bool valid = false;
 };
 int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPlan* plan);
@@ -117,6 +128,9 @@ int launch_maxpool3s2(tise_ctx* ctx, const __half* in, int n, int h, int w, int 
                       int out_stride, cudaStream_t st);
 int launch_avgpool3s1p1(tise_ctx* ctx, const __half* in, int n, int h, int w, int c, int in_stride, __half* out,
                         int out_stride, cudaStream_t st);
+// avg_pool2d(3, 1, 1) of a raw (pre-BN) fp16 tensor followed by scale/shift + ReLU into a channel slice
+int launch_avgpool_bn(tise_ctx* ctx, const __half* in, int n, int h, int w, int c, const float* scale,
+                      const float* shift, void* out, int out_stride, int out_f32, cudaStream_t st);
 int launch_global_avgpool(tise_ctx* ctx, const void* in, int in_f32, int n, int hw, int c, int in_stride,
                           float* out, cudaStream_t st);
 

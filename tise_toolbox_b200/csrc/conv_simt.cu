@@ -14,9 +14,10 @@ struct SimtParams {
   const __half* wlo;
   const float* scale;
   const float* shift;
-  void* out;
+  void* seg_out[kMaxSegs];
+  int seg_end[kMaxSegs], seg_stride[kMaxSegs], seg_relu[kMaxSegs];
   int n, h, w, in_stride, cin, cin_pad, ktot;
-  int cout, R, S, stride, pad_h, pad_w, ho, wo, out_stride, out_f32, relu, passes;
+  int cout, R, S, stride, pad_h, pad_w, ho, wo, out_f32, passes;
   long long M;
 };
 
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(SimtParams p) {
     for (int s = 0; s < p.S; ++s) {
       const int iy = loy * p.stride - p.pad_h + r, ix = lox * p.stride - p.pad_w + s;
       const bool inb = lvalid && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
-      const __half* arow = p.in + (((size_t)limg * p.h + iy) * p.w + ix) * p.in_stride;
+      const __half* arow = inb ? p.in + (((size_t)limg * p.h + iy) * p.w + ix) * p.in_stride : p.in;
       const size_t wbase = (size_t)lco * p.ktot + (size_t)(r * p.S + s) * p.cin_pad;
       for (int c0 = 0; c0 < p.cin; c0 += SBK) {
 #pragma unroll
@@ -94,11 +95,14 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(SimtParams p) {
       const int co = n0 + tx * 4 + j;
       if (co >= p.cout) continue;
       float v = fmaf(acc[i][j], p.scale[co], p.shift[co]);
-      if (p.relu) v = fmaxf(v, 0.f);
+      int sg = 0;
+      while (co >= p.seg_end[sg]) ++sg;
+      const int c = co - (sg ? p.seg_end[sg - 1] : 0);
+      if (p.seg_relu[sg]) v = fmaxf(v, 0.f);
       if (p.out_f32)
-        ((float*)p.out)[(size_t)m * p.out_stride + co] = v;
+        ((float*)p.seg_out[sg])[(size_t)m * p.seg_stride[sg] + c] = v;
       else
-        ((__half*)p.out)[(size_t)m * p.out_stride + co] = __float2half_rn(fminf(v, 65504.f));
+        ((__half*)p.seg_out[sg])[(size_t)m * p.seg_stride[sg] + c] = __float2half_rn(fminf(v, 65504.f));
     }
   }
 }
@@ -110,7 +114,14 @@ int launch_conv_simt(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, cudaS
   p.wlo = L.d_wlo;
   p.scale = L.d_scale;
   p.shift = L.d_shift;
-  p.out = a.out;
+  int end = 0;
+  for (int i = 0; i < kMaxSegs; ++i) {
+    if (i < a.n_segs) end += a.segs[i].c;
+    p.seg_out[i] = a.segs[i < a.n_segs ? i : 0].out;
+    p.seg_stride[i] = a.segs[i < a.n_segs ? i : 0].out_stride;
+    p.seg_relu[i] = i < a.n_segs ? a.segs[i].relu : 0;
+    p.seg_end[i] = i < a.n_segs ? end : 0x7fffffff;
+  }
   p.n = a.n;
   p.h = a.h;
   p.w = a.w;
@@ -126,9 +137,7 @@ int launch_conv_simt(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, cudaS
   p.pad_w = L.pad_w;
   p.ho = a.ho;
   p.wo = a.wo;
-  p.out_stride = a.out_stride;
   p.out_f32 = a.out_f32;
-  p.relu = a.relu;
   p.passes = ctx->passes;
   p.M = (long long)a.n * a.ho * a.wo;
   dim3 grid((unsigned)((p.M + SBM - 1) / SBM), (unsigned)((L.cout + SBN - 1) / SBN));

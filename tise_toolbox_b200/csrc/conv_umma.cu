@@ -13,8 +13,11 @@
 //   K = 16) -- for every K step once against W_hi and once against W_lo into the same fp32 TMEM
 //   accumulator ("2 passes": fp16 activations x ~22-bit weights; FID stays within 1e-4 of fp32).
 // * Epilogue: 4 warps read the accumulator with tcgen05.ld (one output pixel per thread), apply
-//   scale/shift (folded BN), ReLU, convert to fp16 and store into a channel slice of the NHWC
-//   destination -- so torch.cat of the Inception branches costs nothing.
+//   scale/shift (folded BN) from shared memory, ReLU, convert to fp16, stage 128 x 16|32-channel boxes in
+//   swizzled shared memory and hand them to TMA stores (cp.async.bulk.tensor...global.shared::cta) that
+//   write channel slices of the NHWC destinations -- coalesced, clipped at the tensor end, and torch.cat of
+//   the Inception branches costs nothing.  Output channels may be split into segments with different
+//   destinations (sibling 1x1 convolutions of a block run as ONE GEMM over the shared input).
 // * Persistent: grid = #SMs, each CTA strides over (m tile, n tile) pairs; TMEM holds two
 //   accumulators (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
 //   shared memory holds a 3-6 stage TMA<->MMA ring.
@@ -34,12 +37,18 @@ constexpr int kMaxStages = 8;
 constexpr int kAccumCols = 256;                     // TMEM columns per accumulator stage
 constexpr int kNumThreads = 192;
 
+constexpr int kEpiBufBytes = 128 * 64;              // one staged store box: 128 rows x 64 bytes
+constexpr int kMaxNt = 256;
+
 struct UmmaParams {
   const float* scale;
   const float* shift;
-  void* out;
   long long M;
-  int out_stride, out_f32, relu;
+  int out_f32;
+  int n_segs;
+  int seg_end[kMaxSegs];   // exclusive end column of each segment within the layer's cout
+  int seg_relu[kMaxSegs];
+  int box_w;               // channels per store box: 32 or 16 (fp16), 16 (fp32) -> 64- or 32-byte rows
   int ho_wo, wo, stride, pad_h, pad_w;
   int R, S, n_chunks, last_ksteps, cin_pad;
   int nt, n_ntiles, num_tiles;
@@ -123,6 +132,36 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -141,10 +180,15 @@ __device__ __forceinline__ uint32_t make_instr_desc(int n) {
 // ----------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_bhi,
-                 const __grid_constant__ CUtensorMap tm_blo, const UmmaParams p) {
+                 const __grid_constant__ CUtensorMap tm_blo, const __grid_constant__ CUtensorMap tm_o0,
+                 const __grid_constant__ CUtensorMap tm_o1, const __grid_constant__ CUtensorMap tm_o2,
+                 const __grid_constant__ CUtensorMap tm_o3, const UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
-  const uint32_t bar_base = smem_base + (uint32_t)p.stages * (uint32_t)p.stage_bytes;
+  // layout: [stages x (A | B_hi | B_lo)] [2 epilogue store boxes] [scale nt | shift nt] [barriers] [tmem slot]
+  const uint32_t epi_base = smem_base + (uint32_t)p.stages * (uint32_t)p.stage_bytes;
+  const uint32_t ss_base = epi_base + 2u * kEpiBufBytes;
+  const uint32_t bar_base = ss_base + 2u * kMaxNt * 4u;
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base address word
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
@@ -256,52 +300,97 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ===================================================================== epilogue (warps 2..5)
     const int quarter = warp & 3;  // TMEM lanes [32 * quarter, 32 * quarter + 32) are accessible to this warp
     const int row = quarter * 32 + lane;
+    const int etid = threadIdx.x - 64;  // 0..127
+    float* s_scale = reinterpret_cast<float*>(smem_raw + (ss_base - smem_u32(smem_raw)));
+    float* s_shift = s_scale + kMaxNt;
+    const CUtensorMap* omaps[kMaxSegs] = {&tm_o0, &tm_o1, &tm_o2, &tm_o3};
+    const int w = p.box_w;
+    const int row_bytes = w * (p.out_f32 ? 4 : 2);  // 64 or 32
+    // Swizzle<B,4,3> phase of this row inside the staged box: 64-byte rows XOR chunk bits with (row >> 1) & 3,
+    // 32-byte rows with (row >> 2) & 1 -- the pattern TMA expects for SWIZZLE_64B / SWIZZLE_32B boxes.
+    const uint32_t swz = row_bytes == 64 ? (uint32_t)((row >> 1) & 3) : (uint32_t)((row >> 2) & 1);
     int as = 0;
     uint32_t aphase = 0;
+    uint32_t box_it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
-      const long long m = (long long)m_tile * kBlockM + row;
-      const bool valid = m < p.M;
+      const int m0 = m_tile * kBlockM;
       const int co0 = n_tile * p.nt;
+      // every epilogue thread is past its last read of s_scale/s_shift of the previous tile (barrier 2 of its last box)
+      for (int c = etid; c < p.nt; c += 128) {
+        s_scale[c] = __ldg(p.scale + co0 + c);
+        s_shift[c] = __ldg(p.shift + co0 + c);
+      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccumCols);
-      for (int c0 = 0; c0 < p.nt; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        float f[16];
+      int seg = 0;
+      for (int c0 = 0; c0 < p.nt; c0 += w, ++box_it) {
+        const int col = co0 + c0;
+        while (col >= p.seg_end[seg]) ++seg;
+        const int seg_col = col - (seg ? p.seg_end[seg - 1] : 0);
+        const bool relu = p.seg_relu[seg] != 0;
+        const uint32_t buf = epi_base + (box_it & 1u) * kEpiBufBytes;
+        if (etid == 0) bulk_wait_read<1>();  // the store that used this buffer two boxes ago has read it
+        epi_bar(1);                          // ... and s_scale / s_shift of this tile are visible
+        float f[32];
+        if (w == 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c0, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int co = co0 + c0 + j;
-          float y = fmaf(__uint_as_float(v[j]), __ldg(p.scale + co), __ldg(p.shift + co));
-          if (p.relu) y = fmaxf(y, 0.f);
-          f[j] = y;
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        } else {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
         }
-        if (valid) {
-          if (p.out_f32) {
-            float4* dst = reinterpret_cast<float4*>((float*)p.out + (size_t)m * p.out_stride + co0 + c0);
+        if (c0 + w >= p.nt) {  // accumulator fully read: hand it back to the MMA warp before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            __half2 h[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              h[j] = __floats2half2_rn(fminf(f[2 * j], 65504.f), fminf(f[2 * j + 1], 65504.f));
-            uint4* dst = reinterpret_cast<uint4*>((__half*)p.out + (size_t)m * p.out_stride + co0 + c0);
-            dst[0] = *reinterpret_cast<uint4*>(&h[0]);
-            dst[1] = *reinterpret_cast<uint4*>(&h[4]);
+        for (int j = 0; j < 32; ++j) {
+          if (j < w) {
+            float y = fmaf(f[j], s_scale[c0 + j], s_shift[c0 + j]);
+            f[j] = relu ? fmaxf(y, 0.f) : y;
           }
         }
+        const uint32_t rbase = buf + (uint32_t)row * (uint32_t)row_bytes;
+        if (p.out_f32) {  // w == 16: 64-byte rows, 4 chunks of 4 floats
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(rbase + (((uint32_t)j ^ swz) << 4), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                         __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+        } else if (w == 32) {  // 64-byte rows, 4 chunks of 8 halves
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(rbase + (((uint32_t)j ^ swz) << 4), pack_h2(f[8 * j], f[8 * j + 1]),
+                         pack_h2(f[8 * j + 2], f[8 * j + 3]), pack_h2(f[8 * j + 4], f[8 * j + 5]),
+                         pack_h2(f[8 * j + 6], f[8 * j + 7]));
+        } else {  // w == 16 fp16: 32-byte rows, 2 chunks
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            st_shared_v4(rbase + (((uint32_t)j ^ swz) << 4), pack_h2(f[8 * j], f[8 * j + 1]),
+                         pack_h2(f[8 * j + 2], f[8 * j + 3]), pack_h2(f[8 * j + 4], f[8 * j + 5]),
+                         pack_h2(f[8 * j + 6], f[8 * j + 7]));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA
+        epi_bar(2);
+        if (etid == 0) {
+          tma_store_2d(omaps[seg], buf, seg_col, m0);  // rows beyond M are clipped by the tensor map
+          bulk_commit();
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
       if (++as == 2) {
         as = 0;
         aphase ^= 1u;
       }
     }
+    if (etid == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -330,16 +419,23 @@ static int load_driver_entry_points(tise_ctx* ctx) {
   return TISE_OK;
 }
 
-static int n_tile_of(int cout) { return cout <= 256 ? cout : cout / 2; }
+// Largest divisor of cout that is a multiple of 16 and at most 256.
+static int n_tile_of(int cout) {
+  for (int nt = 256; nt >= 16; nt -= 16)
+    if (cout % nt == 0) return nt;
+  return 0;
+}
 
 int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPlan* plan) {
   int rc = load_driver_entry_points(ctx);
   if (rc) return rc;
-  if (L.cout % 16 || (L.cout > 256 && (L.cout / 2) % 16) || L.cout > 512)
-    return fail(ctx, TISE_ERR_INVALID, "umma conv: unsupported cout %d", L.cout);
+  const int nt = n_tile_of(L.cout);
+  if (L.cout % 16 || nt == 0) return fail(ctx, TISE_ERR_INVALID, "umma conv: unsupported cout %d", L.cout);
   if (L.cin % 16) return fail(ctx, TISE_ERR_INVALID, "umma conv: cin %d is not a multiple of 16", L.cin);
   if (a.in_stride % 8 || ((uintptr_t)a.in & 15))
     return fail(ctx, TISE_ERR_INVALID, "umma conv: input view is not 16-byte aligned");
+  if (a.n_segs < 1 || a.n_segs > kMaxSegs) return fail(ctx, TISE_ERR_INVALID, "umma conv: %d segments", a.n_segs);
+  plan->nt = nt;
 
   // ---- A: im2col map over the NHWC input view, dims (C, W, H, N)
   {
@@ -364,7 +460,6 @@ int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPl
     if (drv <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(&plan->tm_a)[1] &= ~(1ull << 21);
   }
   // ---- B: weights [cout][ktot], box 64 x nt
-  const int nt = n_tile_of(L.cout);
   for (int hl = 0; hl < 2; ++hl) {
     cuuint64_t dims[2] = {(cuuint64_t)L.ktot, (cuuint64_t)L.cout};
     cuuint64_t strides[1] = {(cuuint64_t)L.ktot * 2};
@@ -376,6 +471,32 @@ int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPl
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, TISE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for weights", (int)r);
   }
+  // ---- outputs: one 2D store map per segment, dims (channels of the segment, all output pixels)
+  int box_w = a.out_f32 ? 16 : 32;
+  int csum = 0;
+  for (int i = 0; i < a.n_segs; ++i) {
+    if (a.segs[i].c % 16) return fail(ctx, TISE_ERR_INVALID, "umma conv: segment of %d channels", a.segs[i].c);
+    csum += a.segs[i].c;
+    if (!a.out_f32 && (csum % 32 || nt % 32)) box_w = 16;
+  }
+  if (csum != L.cout) return fail(ctx, TISE_ERR_INVALID, "umma conv: segments cover %d of %d channels", csum, L.cout);
+  plan->box_w = box_w;
+  const int elt = a.out_f32 ? 4 : 2;
+  const long long M = (long long)a.n * a.ho * a.wo;
+  for (int i = 0; i < kMaxSegs; ++i) {
+    const ConvSeg& sg = a.segs[i < a.n_segs ? i : 0];  // unused slots repeat segment 0 (never dereferenced)
+    if (((uintptr_t)sg.out & 15) || (sg.out_stride * elt) % 16)
+      return fail(ctx, TISE_ERR_INVALID, "umma conv: output slice is not 16-byte aligned");
+    cuuint64_t dims[2] = {(cuuint64_t)sg.c, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)sg.out_stride * elt};
+    cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)kBlockM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&plan->tm_out[i], a.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                                2, sg.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                box_w * elt == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, TISE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for output %d", (int)r, i);
+  }
   plan->valid = true;
   return TISE_OK;
 }
@@ -386,11 +507,16 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   UmmaParams p;
   p.scale = L.d_scale;
   p.shift = L.d_shift;
-  p.out = a.out;
   p.M = (long long)a.n * a.ho * a.wo;
-  p.out_stride = a.out_stride;
   p.out_f32 = a.out_f32;
-  p.relu = a.relu;
+  p.n_segs = a.n_segs;
+  int end = 0;
+  for (int i = 0; i < kMaxSegs; ++i) {
+    if (i < a.n_segs) end += a.segs[i].c;
+    p.seg_end[i] = i < a.n_segs ? end : 0x7fffffff;
+    p.seg_relu[i] = i < a.n_segs ? a.segs[i].relu : 0;
+  }
+  p.box_w = plan.box_w;
   p.ho_wo = a.ho * a.wo;
   p.wo = a.wo;
   p.stride = L.stride;
@@ -401,7 +527,7 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   p.n_chunks = L.cin_pad / kBlockK;
   p.last_ksteps = (L.cin - (p.n_chunks - 1) * kBlockK + 15) / 16;
   p.cin_pad = L.cin_pad;
-  p.nt = n_tile_of(L.cout);
+  p.nt = plan.nt;
   p.n_ntiles = L.cout / p.nt;
   const int m_tiles = cdiv(p.M, kBlockM);
   p.num_tiles = m_tiles * p.n_ntiles;
@@ -414,14 +540,15 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
     TISE_CUDA(ctx, cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
     configured_smem = smem_limit;
   }
-  const int reserve = 1024 /*alignment*/ + 8 * (2 * kMaxStages + 4) + 16;
+  const int reserve = 1024 /*alignment*/ + 2 * kEpiBufBytes + 2 * kMaxNt * 4 + 8 * (2 * kMaxStages + 4) + 16;
   int stages = (smem_limit - reserve) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(ctx, TISE_ERR_INVALID, "umma conv: tile does not fit shared memory");
   p.stages = stages;
   const int grid = p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms;
   // always request the full opt-in size: one CTA per SM, so the 512-column TMEM allocation never contends
-  conv_umma_kernel<<<grid, kNumThreads, smem_limit, st>>>(plan.tm_a, plan.tm_bhi, plan.tm_blo, p);
+  conv_umma_kernel<<<grid, kNumThreads, smem_limit, st>>>(plan.tm_a, plan.tm_bhi, plan.tm_blo, plan.tm_out[0],
+                                                         plan.tm_out[1], plan.tm_out[2], plan.tm_out[3], p);
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;
 }

@@ -128,17 +128,48 @@ struct Builder {
     return ws + b.off * (size_t)n + (size_t)v.choff * (b.f32 ? 4 : 2);
   }
 
-  const ConvLayer* layer(const std::string& name, int cin, int cout, int R, int S, int stride, int ph, int pw) {
-    auto it = net->convs.find(name);
+  // One member of a (possibly fused) convolution: a torchvision BasicConv2d by name, its destination view,
+  // and whether it is written raw (branch_pool: BN + ReLU are applied after the average pooling).
+  struct Member {
+    std::string name;
+    View out;
+    bool raw;
+  };
+
+  // Creates (once) the packed layer holding the members' output channels back to back.
+  const ConvLayer* layer(const std::string& key, const std::vector<Member>& ms, int cin, int R, int S, int stride, int ph,
+                         int pw) {
+    auto it = net->convs.find(key);
     if (it != net->convs.end()) return &it->second;
-    auto wt = net->raw.find(name + ".conv.weight");
-    if (wt == net->raw.end() || wt->second.size() != (size_t)cout * cin * R * S) {
-      rc = fail(ctx, TISE_ERR_INVALID, "state_dict: missing or mis-sized %s.conv.weight (want %dx%dx%dx%d)",
-                name.c_str(), cout, cin, R, S);
-      return nullptr;
+    const int taps = R * S;
+    int cout = 0;
+    for (const Member& m : ms) cout += m.out.c;
+    std::vector<float> w((size_t)cout * cin * taps), scale(cout), shift(cout);
+    int co = 0;
+    for (const Member& m : ms) {
+      auto wt = net->raw.find(m.name + ".conv.weight");
+      if (wt == net->raw.end() || wt->second.size() != (size_t)m.out.c * cin * taps) {
+        rc = fail(ctx, TISE_ERR_INVALID, "state_dict: missing or mis-sized %s.conv.weight (want %dx%dx%dx%d)",
+                  m.name.c_str(), m.out.c, cin, R, S);
+        return nullptr;
+      }
+      std::copy(wt->second.begin(), wt->second.end(), w.begin() + (size_t)co * cin * taps);
+      std::vector<float> sc, sh;
+      if ((rc = fold_bn(ctx, net, m.name, m.out.c, &sc, &sh))) return nullptr;
+      if (m.raw) {  // conv output stays un-normalised; keep the BN for the pooling step
+        PoolBN pb;
+        if ((rc = dev_alloc(ctx, &net->device_allocs, (void**)&pb.d_scale, sc.size() * 4))) return nullptr;
+        if ((rc = dev_alloc(ctx, &net->device_allocs, (void**)&pb.d_shift, sh.size() * 4))) return nullptr;
+        cudaMemcpy(pb.d_scale, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(pb.d_shift, sh.data(), sh.size() * 4, cudaMemcpyHostToDevice);
+        net->pool_bn[m.name] = pb;
+        std::fill(sc.begin(), sc.end(), 1.0f);
+        std::fill(sh.begin(), sh.end(), 0.0f);
+      }
+      std::copy(sc.begin(), sc.end(), scale.begin() + co);
+      std::copy(sh.begin(), sh.end(), shift.begin() + co);
+      co += m.out.c;
     }
-    std::vector<float> scale, shift;
-    if ((rc = fold_bn(ctx, net, name, cout, &scale, &shift))) return nullptr;
     ConvLayer L;
     L.cin = cin;
     L.cout = cout;
@@ -147,23 +178,22 @@ struct Builder {
     L.stride = stride;
     L.pad_h = ph;
     L.pad_w = pw;
-    if ((rc = pack_conv_layer(ctx, &L, wt->second.data(), scale.data(), shift.data(), &net->device_allocs)))
-      return nullptr;
-    return &(net->convs[name] = L);
+    if ((rc = pack_conv_layer(ctx, &L, w.data(), scale.data(), shift.data(), &net->device_allocs))) return nullptr;
+    return &(net->convs[key] = L);
   }
 
-  void conv(const std::string& name, View in, View out, int R = 1, int S = 1, int stride = 1, int ph = 0, int pw = 0) {
+  void conv_multi(const std::string& key, View in, const std::vector<Member>& ms, int R = 1, int S = 1, int stride = 1,
+                  int ph = 0, int pw = 0) {
     if (rc) return;
     const Buf& bi = bufs[in.buf];
-    const Buf& bo = bufs[out.buf];
-    const ConvLayer* L = layer(name, in.c, out.c, R, S, stride, ph, pw);
+    const ConvLayer* L = layer(key, ms, in.c, R, S, stride, ph, pw);
     if (!L) return;
     const int ho = conv_out_dim(bi.h, R, stride, ph), wo = conv_out_dim(bi.w, S, stride, pw);
-    if (ho != bo.h || wo != bo.w) {
-      rc = fail(ctx, TISE_ERR_INVALID, "internal: %s output %dx%d does not match buffer %dx%d", name.c_str(), ho, wo,
-                bo.h, bo.w);
-      return;
-    }
+    for (const Member& m : ms)
+      if (bufs[m.out.buf].h != ho || bufs[m.out.buf].w != wo || bufs[m.out.buf].f32 != bufs[ms[0].out.buf].f32) {
+        rc = fail(ctx, TISE_ERR_INVALID, "internal: %s output %dx%d does not match its buffer", m.name.c_str(), ho, wo);
+        return;
+      }
     if (!plan) return;
     Step s;
     s.kind = STEP_CONV;
@@ -173,13 +203,20 @@ struct Builder {
     s.conv.h = bi.h;
     s.conv.w = bi.w;
     s.conv.in_stride = bi.c;
-    s.conv.out = ptr(out);
-    s.conv.out_stride = bo.c;
-    s.conv.out_f32 = bo.f32;
-    s.conv.relu = 1;
+    s.conv.n_segs = (int)ms.size();
+    for (size_t i = 0; i < ms.size(); ++i) {
+      s.conv.segs[i].out = ptr(ms[i].out);
+      s.conv.segs[i].out_stride = bufs[ms[i].out.buf].c;
+      s.conv.segs[i].c = ms[i].out.c;
+      s.conv.segs[i].relu = ms[i].raw ? 0 : 1;
+    }
+    s.conv.out_f32 = bufs[ms[0].out.buf].f32;
     s.conv.ho = ho;
     s.conv.wo = wo;
     plan->steps.push_back(s);
+  }
+  void conv(const std::string& name, View in, View out, int R = 1, int S = 1, int stride = 1, int ph = 0, int pw = 0) {
+    conv_multi(name, in, {Member{name, out, false}}, R, S, stride, ph, pw);
   }
   void pool(StepKind kind, View in, View out) {
     if (rc || !plan) return;
@@ -197,6 +234,27 @@ struct Builder {
     s.out_stride = bo.c;
     plan->steps.push_back(s);
   }
+  // avg_pool2d(3,1,1) + BN + ReLU of the raw branch_pool convolution `name` (buffer `in`, all channels) -> out
+  void pool_bn(const std::string& name, int in, View out) {
+    if (rc || !plan) return;
+    const Buf& bi = bufs[in];
+    const Buf& bo = bufs[out.buf];
+    const PoolBN& pb = net->pool_bn[name];
+    Step s;
+    s.kind = STEP_AVGPOOL_BN;
+    s.in = ptr(all(in));
+    s.out = ptr(out);
+    s.n = n;
+    s.h = bi.h;
+    s.w = bi.w;
+    s.c = bi.c;
+    s.in_stride = bi.c;
+    s.out_stride = bo.c;
+    s.out_f32 = bo.f32;
+    s.pool_scale = pb.d_scale;
+    s.pool_shift = pb.d_shift;
+    plan->steps.push_back(s);
+  }
   void gap(View in) {
     if (rc || !plan) return;
     const Buf& bi = bufs[in.buf];
@@ -212,21 +270,22 @@ struct Builder {
     plan->steps.push_back(s);
   }
 
+  // In every block the 1x1 convolutions that read the block input run as ONE GEMM (one A-operand pass, wider N),
+  // and branch_pool's avg_pool -> conv1x1 -> BN -> ReLU is evaluated as conv1x1 (raw) -> avg_pool -> BN -> ReLU,
+  // which is the same function (both linear, zero padding, no bias) on pf instead of cin channels.
+
   // torchvision InceptionA (models/inception.py): cat[branch1x1 64, branch5x5 64, branch3x3dbl 96, branch_pool pf]
   int inceptionA(const std::string& p, int in, int pf) {
-    const int hw = bufs[in].h, cin = bufs[in].c;
+    const int hw = bufs[in].h;
     const int out = buf(hw, hw, 224 + pf);
-    conv(p + ".branch1x1", all(in), View{out, 0, 64});
-    const int t5 = buf(hw, hw, 48);
-    conv(p + ".branch5x5_1", all(in), all(t5));
+    const int t5 = buf(hw, hw, 48), d1 = buf(hw, hw, 64), d2 = buf(hw, hw, 96), tp = buf(hw, hw, pf);
+    conv_multi(p + ".fused1x1", all(in),
+               {Member{p + ".branch1x1", View{out, 0, 64}, false}, Member{p + ".branch5x5_1", all(t5), false},
+                Member{p + ".branch3x3dbl_1", all(d1), false}, Member{p + ".branch_pool", all(tp), true}});
     conv(p + ".branch5x5_2", all(t5), View{out, 64, 64}, 5, 5, 1, 2, 2);
-    const int d1 = buf(hw, hw, 64), d2 = buf(hw, hw, 96);
-    conv(p + ".branch3x3dbl_1", all(in), all(d1));
     conv(p + ".branch3x3dbl_2", all(d1), all(d2), 3, 3, 1, 1, 1);
     conv(p + ".branch3x3dbl_3", all(d2), View{out, 128, 96}, 3, 3, 1, 1, 1);
-    const int tp = buf(hw, hw, cin);
-    pool(STEP_AVGPOOL, all(in), all(tp));
-    conv(p + ".branch_pool", all(tp), View{out, 224, pf});
+    pool_bn(p + ".branch_pool", tp, View{out, 224, pf});
     return out;
   }
   // InceptionB: cat[branch3x3 384 (s2), branch3x3dbl 96 (s2), maxpool cin]
@@ -244,22 +303,21 @@ struct Builder {
   }
   // InceptionC: cat[branch1x1 192, branch7x7 192, branch7x7dbl 192, branch_pool 192]
   int inceptionC(const std::string& p, int in, int c7) {
-    const int hw = bufs[in].h, cin = bufs[in].c;
+    const int hw = bufs[in].h;
     const int out = buf(hw, hw, 768);
-    conv(p + ".branch1x1", all(in), View{out, 0, 192});
     const int a1 = buf(hw, hw, c7), a2 = buf(hw, hw, c7);
-    conv(p + ".branch7x7_1", all(in), all(a1));
+    const int b1 = buf(hw, hw, c7), b2 = buf(hw, hw, c7), b3 = buf(hw, hw, c7), b4 = buf(hw, hw, c7);
+    const int tp = buf(hw, hw, 192);
+    conv_multi(p + ".fused1x1", all(in),
+               {Member{p + ".branch1x1", View{out, 0, 192}, false}, Member{p + ".branch7x7_1", all(a1), false},
+                Member{p + ".branch7x7dbl_1", all(b1), false}, Member{p + ".branch_pool", all(tp), true}});
     conv(p + ".branch7x7_2", all(a1), all(a2), 1, 7, 1, 0, 3);
     conv(p + ".branch7x7_3", all(a2), View{out, 192, 192}, 7, 1, 1, 3, 0);
-    const int b1 = buf(hw, hw, c7), b2 = buf(hw, hw, c7), b3 = buf(hw, hw, c7), b4 = buf(hw, hw, c7);
-    conv(p + ".branch7x7dbl_1", all(in), all(b1));
     conv(p + ".branch7x7dbl_2", all(b1), all(b2), 7, 1, 1, 3, 0);
     conv(p + ".branch7x7dbl_3", all(b2), all(b3), 1, 7, 1, 0, 3);
     conv(p + ".branch7x7dbl_4", all(b3), all(b4), 7, 1, 1, 3, 0);
     conv(p + ".branch7x7dbl_5", all(b4), View{out, 384, 192}, 1, 7, 1, 0, 3);
-    const int tp = buf(hw, hw, cin);
-    pool(STEP_AVGPOOL, all(in), all(tp));
-    conv(p + ".branch_pool", all(tp), View{out, 576, 192});
+    pool_bn(p + ".branch_pool", tp, View{out, 576, 192});
     return out;
   }
   // InceptionD: cat[branch3x3 320 (s2), branch7x7x3 192 (s2), maxpool cin]
@@ -267,11 +325,10 @@ struct Builder {
     const int hw = bufs[in].h, cin = bufs[in].c;
     const int ho = (hw - 3) / 2 + 1;
     const int out = buf(ho, ho, 320 + 192 + cin);
-    const int a1 = buf(hw, hw, 192);
-    conv(p + ".branch3x3_1", all(in), all(a1));
+    const int a1 = buf(hw, hw, 192), b1 = buf(hw, hw, 192), b2 = buf(hw, hw, 192), b3 = buf(hw, hw, 192);
+    conv_multi(p + ".fused1x1", all(in),
+               {Member{p + ".branch3x3_1", all(a1), false}, Member{p + ".branch7x7x3_1", all(b1), false}});
     conv(p + ".branch3x3_2", all(a1), View{out, 0, 320}, 3, 3, 2, 0, 0);
-    const int b1 = buf(hw, hw, 192), b2 = buf(hw, hw, 192), b3 = buf(hw, hw, 192);
-    conv(p + ".branch7x7x3_1", all(in), all(b1));
     conv(p + ".branch7x7x3_2", all(b1), all(b2), 1, 7, 1, 0, 3);
     conv(p + ".branch7x7x3_3", all(b2), all(b3), 7, 1, 1, 3, 0);
     conv(p + ".branch7x7x3_4", all(b3), View{out, 320, 192}, 3, 3, 2, 0, 0);
@@ -280,21 +337,25 @@ struct Builder {
   }
   // InceptionE: cat[branch1x1 320, branch3x3 (2a|2b) 768, branch3x3dbl (3a|3b) 768, branch_pool 192]
   int inceptionE(const std::string& p, int in, int out_f32) {
-    const int hw = bufs[in].h, cin = bufs[in].c;
+    const int hw = bufs[in].h;
     const int out = buf(hw, hw, 2048, out_f32);
-    conv(p + ".branch1x1", all(in), View{out, 0, 320});
-    const int a1 = buf(hw, hw, 384);
-    conv(p + ".branch3x3_1", all(in), all(a1));
+    const int a1 = buf(hw, hw, 384), b1 = buf(hw, hw, 448), b2 = buf(hw, hw, 384), tp = buf(hw, hw, 192);
+    if (out_f32) {  // the fp32 destination of branch1x1 cannot share a launch with the fp16 temporaries
+      conv(p + ".branch1x1", all(in), View{out, 0, 320});
+      conv_multi(p + ".fused1x1", all(in),
+                 {Member{p + ".branch3x3_1", all(a1), false}, Member{p + ".branch3x3dbl_1", all(b1), false},
+                  Member{p + ".branch_pool", all(tp), true}});
+    } else {
+      conv_multi(p + ".fused1x1", all(in),
+                 {Member{p + ".branch1x1", View{out, 0, 320}, false}, Member{p + ".branch3x3_1", all(a1), false},
+                  Member{p + ".branch3x3dbl_1", all(b1), false}, Member{p + ".branch_pool", all(tp), true}});
+    }
     conv(p + ".branch3x3_2a", all(a1), View{out, 320, 384}, 1, 3, 1, 0, 1);
     conv(p + ".branch3x3_2b", all(a1), View{out, 704, 384}, 3, 1, 1, 1, 0);
-    const int b1 = buf(hw, hw, 448), b2 = buf(hw, hw, 384);
-    conv(p + ".branch3x3dbl_1", all(in), all(b1));
     conv(p + ".branch3x3dbl_2", all(b1), all(b2), 3, 3, 1, 1, 1);
     conv(p + ".branch3x3dbl_3a", all(b2), View{out, 1088, 384}, 1, 3, 1, 0, 1);
     conv(p + ".branch3x3dbl_3b", all(b2), View{out, 1472, 384}, 3, 1, 1, 1, 0);
-    const int tp = buf(hw, hw, cin);
-    pool(STEP_AVGPOOL, all(in), all(tp));
-    conv(p + ".branch_pool", all(tp), View{out, 1856, 192});
+    pool_bn(p + ".branch_pool", tp, View{out, 1856, 192});
     return out;
   }
 
@@ -470,6 +531,10 @@ int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, i
       case STEP_AVGPOOL:
         rc = launch_avgpool3s1p1(ctx, (const __half*)s.in, s.n, s.h, s.w, s.c, s.in_stride, (__half*)s.out,
                                  s.out_stride, st);
+        break;
+      case STEP_AVGPOOL_BN:
+        rc = launch_avgpool_bn(ctx, (const __half*)s.in, s.n, s.h, s.w, s.c, s.pool_scale, s.pool_shift, s.out,
+                               s.out_stride, s.out_f32, st);
         break;
       case STEP_GAP:
         rc = launch_global_avgpool(ctx, s.in, s.in_f32, s.n, s.h * s.w, s.c, s.in_stride, d_feat, st);

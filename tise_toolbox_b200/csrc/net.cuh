@@ -7,7 +7,7 @@
 
 namespace tise {
 
-enum StepKind { STEP_STEM = 0, STEP_CONV, STEP_MAXPOOL, STEP_AVGPOOL, STEP_GAP };
+enum StepKind { STEP_STEM = 0, STEP_CONV, STEP_MAXPOOL, STEP_AVGPOOL, STEP_GAP, STEP_AVGPOOL_BN };
 
 struct Step {
   StepKind kind;
@@ -17,7 +17,9 @@ struct Step {
   // pools
   const void* in = nullptr;
   void* out = nullptr;
-  int n = 0, h = 0, w = 0, c = 0, in_stride = 0, out_stride = 0, in_f32 = 0;
+  int n = 0, h = 0, w = 0, c = 0, in_stride = 0, out_stride = 0, in_f32 = 0, out_f32 = 0;
+  const float* pool_scale = nullptr;  // STEP_AVGPOOL_BN
+  const float* pool_shift = nullptr;
 };
 
 struct Plan {
@@ -28,9 +30,15 @@ struct Plan {
   float* feat_dst = nullptr;  // patched per call (GAP output)
 };
 
+struct PoolBN {
+  float* d_scale = nullptr;
+  float* d_shift = nullptr;
+};
+
 struct Net {
   std::map<std::string, std::vector<float>> raw;  // host copy of the state_dict (fp32)
-  std::map<std::string, ConvLayer> convs;         // by torchvision module prefix
+  std::map<std::string, ConvLayer> convs;         // by torchvision module prefix (or "<block>.fused1x1")
+  std::map<std::string, PoolBN> pool_bn;          // BN of the branch_pool convs, applied after the pooling
   float* d_stem_w = nullptr;                      // [27][32]
   float* d_stem_scale = nullptr;
   float* d_stem_shift = nullptr;

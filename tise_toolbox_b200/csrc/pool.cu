@@ -76,6 +76,59 @@ __global__ void avgpool3s1p1_kernel(const __half* __restrict__ in, int n, int h,
   }
 }
 
+// branch_pool of InceptionA/C/E with the 1x1 convolution commuted in front of the pooling: the input is the
+// RAW (pre-BN) fp16 output of that convolution (pf = 32..192 channels instead of the block's 192..2048), so
+// avg_pool2d(3,1,1)(count_include_pad) + BN scale/shift + ReLU is applied here.  Exact: conv1x1 and the
+// zero-padded average are both linear and the convolution has no bias.
+template <bool kF32>
+__global__ void avgpool_bn_kernel(const __half* __restrict__ in, int n, int h, int w, int c8,
+                                  const float* __restrict__ scale, const float* __restrict__ shift,
+                                  void* __restrict__ out, int out_stride) {
+  const long long total = (long long)n * h * w * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % c8);
+    long long p = i / c8;
+    const int ox = (int)(p % w);
+    p /= w;
+    const int oy = (int)(p % h);
+    const int img = (int)(p / h);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int r = -1; r <= 1; ++r)
+#pragma unroll
+      for (int s = -1; s <= 1; ++s) {
+        const int y = oy + r, x = ox + s;
+        if (y < 0 || y >= h || x < 0 || x >= w) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(in + (((size_t)img * h + y) * w + x) * (c8 * 8) + g * 8);
+        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(hv[j]);
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
+        }
+      }
+    float y8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      y8[j] = fmaxf(fmaf(acc[j] / 9.0f, __ldg(scale + g * 8 + j), __ldg(shift + g * 8 + j)), 0.f);
+    const size_t o = (((size_t)img * h + oy) * w + ox) * out_stride + g * 8;
+    if (kF32) {
+      float4* dst = reinterpret_cast<float4*>((float*)out + o);
+      dst[0] = make_float4(y8[0], y8[1], y8[2], y8[3]);
+      dst[1] = make_float4(y8[4], y8[5], y8[6], y8[7]);
+    } else {
+      __half2 hh[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hh[j] = __floats2half2_rn(fminf(y8[2 * j], 65504.f), fminf(y8[2 * j + 1], 65504.f));
+      *reinterpret_cast<uint4*>((__half*)out + o) = *reinterpret_cast<uint4*>(hh);
+    }
+  }
+}
+
 // out[img][ch] = mean over hw positions.  Consecutive threads -> consecutive channels (coalesced).
 template <typename T>
 __global__ void global_avgpool_kernel(const T* __restrict__ in, int n, int hw, int c, int in_stride,
@@ -110,6 +163,19 @@ int launch_avgpool3s1p1(tise_ctx* ctx, const __half* in, int n, int h, int w, in
   const long long total = (long long)n * h * w * (c / 8);
   avgpool3s1p1_kernel<<<grid_for(total, 256, ctx->num_sms), 256, 0, st>>>(in, n, h, w, c / 8, in_stride, out,
                                                                          out_stride);
+  TISE_LAUNCH_CHECK(ctx);
+  return TISE_OK;
+}
+
+int launch_avgpool_bn(tise_ctx* ctx, const __half* in, int n, int h, int w, int c, const float* scale,
+                      const float* shift, void* out, int out_stride, int out_f32, cudaStream_t st) {
+  const long long total = (long long)n * h * w * (c / 8);
+  if (out_f32)
+    avgpool_bn_kernel<true><<<grid_for(total, 256, ctx->num_sms), 256, 0, st>>>(in, n, h, w, c / 8, scale, shift, out,
+                                                                              out_stride);
+  else
+    avgpool_bn_kernel<false><<<grid_for(total, 256, ctx->num_sms), 256, 0, st>>>(in, n, h, w, c / 8, scale, shift, out,
+                                                                               out_stride);
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;
 }
