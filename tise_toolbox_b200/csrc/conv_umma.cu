@@ -38,6 +38,7 @@ constexpr int kAccumCols = 256;                     // TMEM columns per accumula
 constexpr int kNumThreads = 192;
 
 constexpr int kEpiBufBytes = 128 * 64;              // one staged store box: 128 rows x 64 bytes
+constexpr int kEpiBufs = 3;                         // boxes in flight (TMA store read latency ~1 us)
 constexpr int kMaxNt = 256;
 
 struct UmmaParams {
@@ -106,6 +107,18 @@ __device__ __forceinline__ void tma_load_im2col(const CUtensorMap* map, uint32_t
       "[%2], {%7, %8};" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
+}
+// One lane of a converged warp (elect.sync): true in exactly one lane.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -185,9 +198,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                  const __grid_constant__ CUtensorMap tm_o3, const UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
-  // layout: [stages x (A | B_hi | B_lo)] [2 epilogue store boxes] [scale nt | shift nt] [barriers] [tmem slot]
+  // layout: [stages x (A | B_hi | B_lo)] [3 epilogue store boxes] [scale nt | shift nt] [barriers] [tmem slot]
   const uint32_t epi_base = smem_base + (uint32_t)p.stages * (uint32_t)p.stage_bytes;
-  const uint32_t ss_base = epi_base + 2u * kEpiBufBytes;
+  const uint32_t ss_base = epi_base + (uint32_t)kEpiBufs * kEpiBufBytes;
   const uint32_t bar_base = ss_base + 2u * kMaxNt * 4u;
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base address word
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
@@ -227,73 +240,79 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t b_bytes = (uint32_t)p.nt * 128u;
   const uint32_t tx_bytes = (uint32_t)kABytes + (uint32_t)p.passes * b_bytes;
 
+  // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the mbarriers and compute the
+  // descriptors, which therefore live in uniform registers); only the TMA / tcgen05 instructions themselves
+  // are predicated on one elected lane.  A single-lane `if (lane == 0)` loop makes ptxas wrap every
+  // uniform-datapath instruction in an election loop (~700 cycles per K block, measured).
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
-        const long long m0 = (long long)m_tile * kBlockM;
-        const int img = (int)(m0 / p.ho_wo);
-        const int rem = (int)(m0 - (long long)img * p.ho_wo);
-        const int oy = rem / p.wo, ox = rem - oy * p.wo;
-        const int wc = ox * p.stride - p.pad_w, hc = oy * p.stride - p.pad_h;  // base pixel (tap 0,0)
-        for (int r = 0; r < p.R; ++r)
-          for (int s = 0; s < p.S; ++s)
-            for (int ch = 0; ch < p.n_chunks; ++ch) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
-              const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
+      const long long m0 = (long long)m_tile * kBlockM;
+      const int img = (int)(m0 / p.ho_wo);
+      const int rem = (int)(m0 - (long long)img * p.ho_wo);
+      const int oy = rem / p.wo, ox = rem - oy * p.wo;
+      const int wc = ox * p.stride - p.pad_w, hc = oy * p.stride - p.pad_h;  // base pixel (tap 0,0)
+      for (int r = 0; r < p.R; ++r)
+        for (int s = 0; s < p.S; ++s)
+          for (int ch = 0; ch < p.n_chunks; ++ch) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
+            const int kcol = (r * p.S + s) * p.cin_pad + ch * kBlockK;
+            if (elect_one()) {
               mbar_expect_tx(full_bar(stage), tx_bytes);
               tma_load_im2col(&tm_a, sa, full_bar(stage), ch * kBlockK, wc, hc, img, (uint16_t)s, (uint16_t)r);
-              const int kcol = (r * p.S + s) * p.cin_pad + ch * kBlockK;
               tma_load_2d(&tm_bhi, sa + kABytes, full_bar(stage), kcol, n_tile * p.nt);
               if (p.passes == 2) tma_load_2d(&tm_blo, sa + kABytes + b_bytes, full_bar(stage), kcol, n_tile * p.nt);
-              if (++stage == p.stages) {
-                stage = 0;
-                phase ^= 1u;
-              }
             }
-      }
+            __syncwarp();
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_instr_desc(p.nt);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
+    const uint32_t idesc = make_instr_desc(p.nt);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccumCols);
+      int chunk = 0;
+      for (int kb = 0; kb < kb_per_tile; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccumCols);
-        int chunk = 0;
-        for (int kb = 0; kb < kb_per_tile; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
-          const uint64_t adesc = make_smem_desc(sa);
-          const uint64_t bhi = make_smem_desc(sa + kABytes);
-          const uint64_t blo = make_smem_desc(sa + kABytes + b_bytes);
-          const int ksteps = (chunk == p.n_chunks - 1) ? p.last_ksteps : (kBlockK / 16);
+        const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
+        const uint64_t adesc = make_smem_desc(sa);
+        const uint64_t bhi = make_smem_desc(sa + kABytes);
+        const uint64_t blo = make_smem_desc(sa + kABytes + b_bytes);
+        const int ksteps = (chunk == p.n_chunks - 1) ? p.last_ksteps : (kBlockK / 16);
+        if (elect_one()) {
           for (int k = 0; k < ksteps; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (>>4) address field
             umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
             if (p.passes == 2) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc, 1u);
           }
           umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
-          if (++chunk == p.n_chunks) chunk = 0;
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          if (kb == kb_per_tile - 1) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
         }
-        umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
-        if (++as == 2) {
-          as = 0;
-          aphase ^= 1u;
+        __syncwarp();
+        if (++chunk == p.n_chunks) chunk = 0;
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
         }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
       }
     }
   } else {
@@ -330,8 +349,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         while (col >= p.seg_end[seg]) ++seg;
         const int seg_col = col - (seg ? p.seg_end[seg - 1] : 0);
         const bool relu = p.seg_relu[seg] != 0;
-        const uint32_t buf = epi_base + (box_it & 1u) * kEpiBufBytes;
-        if (etid == 0) bulk_wait_read<1>();  // the store that used this buffer two boxes ago has read it
+        const uint32_t buf = epi_base + (box_it % (uint32_t)kEpiBufs) * kEpiBufBytes;
+        if (etid == 0) bulk_wait_read<kEpiBufs - 1>();  // the store that used this buffer kEpiBufs boxes ago has read it
         epi_bar(1);                          // ... and s_scale / s_shift of this tile are visible
         float f[32];
         if (w == 32) {
@@ -540,7 +559,7 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
     TISE_CUDA(ctx, cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
     configured_smem = smem_limit;
   }
-  const int reserve = 1024 /*alignment*/ + 2 * kEpiBufBytes + 2 * kMaxNt * 4 + 8 * (2 * kMaxStages + 4) + 16;
+  const int reserve = 1024 /*alignment*/ + kEpiBufs * kEpiBufBytes + 2 * kMaxNt * 4 + 8 * (2 * kMaxStages + 4) + 16;
   int stages = (smem_limit - reserve) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(ctx, TISE_ERR_INVALID, "umma conv: tile does not fit shared memory");
