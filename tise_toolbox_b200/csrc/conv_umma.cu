@@ -13,47 +13,51 @@
 //   K = 16) -- for every K step once against W_hi and once against W_lo into the same fp32 TMEM
 //   accumulator ("2 passes": fp16 activations x ~22-bit weights; FID stays within 1e-4 of fp32).
 // * Epilogue: 4 warps read the accumulator with tcgen05.ld (one output pixel per thread), apply
-//   scale/shift (folded BN) from shared memory, ReLU, convert to fp16, stage 128 x 16|32-channel boxes in
-//   swizzled shared memory and hand them to TMA stores (cp.async.bulk.tensor...global.shared::cta) that
-//   write channel slices of the NHWC destinations -- coalesced, clipped at the tensor end, and torch.cat of
-//   the Inception branches costs nothing.  Output channels may be split into segments with different
-//   destinations (sibling 1x1 convolutions of a block run as ONE GEMM over the shared input).
+//   scale/shift (folded BN) from shared memory, ReLU, convert to fp16 and stage 128 x 32-channel boxes in
+//   bank-conflict-free swizzled shared memory; the same 128 threads then write the box out with
+//   16-byte stores in which 4 consecutive lanes cover one pixel's 64 contiguous bytes (full sectors),
+//   into channel slices of the NHWC destinations -- torch.cat of the Inception branches costs nothing.
+//   Output channels may be split into segments with different destinations (sibling 1x1 convolutions
+//   of a block run as ONE GEMM over the shared input).  (TMA stores of such narrow boxes were measured
+//   at ~12 cycles per 64-byte row and made the epilogue the bottleneck; see profiles/.)
+// * K blocks are grouped: one mbarrier stage carries `group` consecutive (tap, chunk) blocks, so layers with few
+//   channels (small N, small K per tap) do not pay the ~500-cycle barrier round trip per 64-deep block.
 // * Persistent: grid = #SMs, each CTA strides over (m tile, n tile) pairs; TMEM holds two
 //   accumulators (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
-//   shared memory holds a 3-6 stage TMA<->MMA ring.
+//   shared memory holds a 2-8 stage TMA<->MMA ring.
 //
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5 epilogue.
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace tise {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;                         // fp16 elements = one 128-byte swizzle row
-constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KiB
+constexpr int kBlockK = 64;                     // fp16 elements = one 128-byte swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
-constexpr int kAccumCols = 256;                     // TMEM columns per accumulator stage
+constexpr int kAccumCols = 256;  // TMEM columns per accumulator stage
 constexpr int kNumThreads = 192;
-
-constexpr int kEpiBufBytes = 128 * 64;              // one staged store box: 128 rows x 64 bytes
-constexpr int kEpiBufs = 3;                         // boxes in flight (TMA store read latency ~1 us)
 constexpr int kMaxNt = 256;
+constexpr int kEpiBufBytes = 128 * 64;  // staged output box: 128 pixels x 64 bytes (32 fp16 or 16 fp32 channels)
 
 struct UmmaParams {
   const float* scale;
   const float* shift;
-  long long M;
-  int out_f32;
-  int n_segs;
-  int seg_end[kMaxSegs];   // exclusive end column of each segment within the layer's cout
+  void* seg_out[kMaxSegs];   // destination of each output-channel segment (channel offset applied)
+  int seg_stride[kMaxSegs];  // elements per destination pixel
+  int seg_end[kMaxSegs];     // exclusive end column of the segment within the layer's cout
   int seg_relu[kMaxSegs];
-  int box_w;               // channels per store box: 32 or 16 (fp16), 16 (fp32) -> 64- or 32-byte rows
+  long long M;
   int ho_wo, wo, stride, pad_h, pad_w;
   int R, S, n_chunks, last_ksteps, cin_pad;
   int nt, n_ntiles, num_tiles;
   int passes, stages, stage_bytes;
+  int group, kb_bytes;  // K blocks per pipeline stage, bytes of one K block (A + B planes)
+  int debug;            // timing ablations (TISE_UMMA_DEBUG): 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip epilogue
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -156,18 +160,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -191,16 +189,15 @@ __device__ __forceinline__ uint32_t make_instr_desc(int n) {
 }
 
 // ----------------------------------------------------------------------------- kernel
+template <bool kF32>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_bhi,
-                 const __grid_constant__ CUtensorMap tm_blo, const __grid_constant__ CUtensorMap tm_o0,
-                 const __grid_constant__ CUtensorMap tm_o1, const __grid_constant__ CUtensorMap tm_o2,
-                 const __grid_constant__ CUtensorMap tm_o3, const UmmaParams p) {
+                 const __grid_constant__ CUtensorMap tm_blo, const UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
-  // layout: [stages x (A | B_hi | B_lo)] [3 epilogue store boxes] [scale nt | shift nt] [barriers] [tmem slot]
+  // layout: [stages x group x (A | B_hi | B_lo)] [2 staged output boxes] [scale nt | shift nt] [barriers] [tmem slot]
   const uint32_t epi_base = smem_base + (uint32_t)p.stages * (uint32_t)p.stage_bytes;
-  const uint32_t ss_base = epi_base + (uint32_t)kEpiBufs * kEpiBufBytes;
+  const uint32_t ss_base = epi_base + 2u * kEpiBufBytes;
   const uint32_t bar_base = ss_base + 2u * kMaxNt * 4u;
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base address word
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
@@ -238,7 +235,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   const int kb_per_tile = p.R * p.S * p.n_chunks;
   const uint32_t b_bytes = (uint32_t)p.nt * 128u;
-  const uint32_t tx_bytes = (uint32_t)kABytes + (uint32_t)p.passes * b_bytes;
+  const uint32_t kb_tx = ((p.debug & 1) ? 0u : (uint32_t)kABytes) + ((p.debug & 2) ? 0u : (uint32_t)p.passes * b_bytes);
 
   // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the mbarriers and compute the
   // descriptors, which therefore live in uniform registers); only the TMA / tcgen05 instructions themselves
@@ -255,24 +252,43 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int rem = (int)(m0 - (long long)img * p.ho_wo);
       const int oy = rem / p.wo, ox = rem - oy * p.wo;
       const int wc = ox * p.stride - p.pad_w, hc = oy * p.stride - p.pad_h;  // base pixel (tap 0,0)
-      for (int r = 0; r < p.R; ++r)
-        for (int s = 0; s < p.S; ++s)
-          for (int ch = 0; ch < p.n_chunks; ++ch) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
-            const int kcol = (r * p.S + s) * p.cin_pad + ch * kBlockK;
-            if (elect_one()) {
-              mbar_expect_tx(full_bar(stage), tx_bytes);
-              tma_load_im2col(&tm_a, sa, full_bar(stage), ch * kBlockK, wc, hc, img, (uint16_t)s, (uint16_t)r);
-              tma_load_2d(&tm_bhi, sa + kABytes, full_bar(stage), kcol, n_tile * p.nt);
-              if (p.passes == 2) tma_load_2d(&tm_blo, sa + kABytes + b_bytes, full_bar(stage), kcol, n_tile * p.nt);
+      const int ncol = n_tile * p.nt;
+      for (int kb0 = 0; kb0 < kb_per_tile; kb0 += p.group) {
+        const int g = min(p.group, kb_per_tile - kb0);
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sbase = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
+        if (elect_one()) {
+          if (kb_tx)
+            mbar_expect_tx(full_bar(stage), (uint32_t)g * kb_tx);
+          else
+            mbar_arrive(full_bar(stage));
+          int ch = kb0 % p.n_chunks;
+          const int tap = kb0 / p.n_chunks;
+          int r = tap / p.S, sx = tap - r * p.S;
+          for (int j = 0; j < g; ++j) {
+            const uint32_t sa = sbase + (uint32_t)j * (uint32_t)p.kb_bytes;
+            const int kcol = (r * p.S + sx) * p.cin_pad + ch * kBlockK;
+            if (!(p.debug & 1))
+              tma_load_im2col(&tm_a, sa, full_bar(stage), ch * kBlockK, wc, hc, img, (uint16_t)sx, (uint16_t)r);
+            if (!(p.debug & 2)) {
+              tma_load_2d(&tm_bhi, sa + kABytes, full_bar(stage), kcol, ncol);
+              if (p.passes == 2) tma_load_2d(&tm_blo, sa + kABytes + b_bytes, full_bar(stage), kcol, ncol);
             }
-            __syncwarp();
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
+            if (++ch == p.n_chunks) {
+              ch = 0;
+              if (++sx == p.S) {
+                sx = 0;
+                ++r;
+              }
             }
           }
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
@@ -285,26 +301,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccumCols);
-      int chunk = 0;
-      for (int kb = 0; kb < kb_per_tile; ++kb) {
+      for (int kb0 = 0; kb0 < kb_per_tile; kb0 += p.group) {
+        const int g = min(p.group, kb_per_tile - kb0);
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
-        const uint64_t adesc = make_smem_desc(sa);
-        const uint64_t bhi = make_smem_desc(sa + kABytes);
-        const uint64_t blo = make_smem_desc(sa + kABytes + b_bytes);
-        const int ksteps = (chunk == p.n_chunks - 1) ? p.last_ksteps : (kBlockK / 16);
+        const uint32_t sbase = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
         if (elect_one()) {
-          for (int k = 0; k < ksteps; ++k) {
-            // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (>>4) address field
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-            if (p.passes == 2) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc, 1u);
+          int chunk = kb0 % p.n_chunks;
+          for (int j = 0; j < g; ++j) {
+            const uint32_t sa = sbase + (uint32_t)j * (uint32_t)p.kb_bytes;
+            const uint64_t adesc = make_smem_desc(sa);
+            const uint64_t bhi = make_smem_desc(sa + kABytes);
+            const uint64_t blo = make_smem_desc(sa + kABytes + b_bytes);
+            const int ksteps = (p.debug & 4) ? 0 : ((chunk == p.n_chunks - 1) ? p.last_ksteps : (kBlockK / 16));
+            for (int k = 0; k < ksteps; ++k) {
+              // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (>>4) address field
+              umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), idesc, (kb0 | j | k) != 0 ? 1u : 0u);
+              if (p.passes == 2) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc, 1u);
+            }
+            if (++chunk == p.n_chunks) chunk = 0;
           }
           umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
-          if (kb == kb_per_tile - 1) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+          if (kb0 + g >= kb_per_tile) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
         }
         __syncwarp();
-        if (++chunk == p.n_chunks) chunk = 0;
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
@@ -317,91 +337,111 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
-    const int quarter = warp & 3;  // TMEM lanes [32 * quarter, 32 * quarter + 32) are accessible to this warp
+    constexpr int W = kF32 ? 16 : 32;  // channels per staged box (64-byte rows)
+    constexpr int CPC = kF32 ? 4 : 8;  // channels per 16-byte chunk
+    const int quarter = warp & 3;      // TMEM lanes [32 * quarter, 32 * quarter + 32) are accessible to this warp
     const int row = quarter * 32 + lane;
     const int etid = threadIdx.x - 64;  // 0..127
     float* s_scale = reinterpret_cast<float*>(smem_raw + (ss_base - smem_u32(smem_raw)));
     float* s_shift = s_scale + kMaxNt;
-    const CUtensorMap* omaps[kMaxSegs] = {&tm_o0, &tm_o1, &tm_o2, &tm_o3};
-    const int w = p.box_w;
-    const int row_bytes = w * (p.out_f32 ? 4 : 2);  // 64 or 32
-    // Swizzle<B,4,3> phase of this row inside the staged box: 64-byte rows XOR chunk bits with (row >> 1) & 3,
-    // 32-byte rows with (row >> 2) & 1 -- the pattern TMA expects for SWIZZLE_64B / SWIZZLE_32B boxes.
-    const uint32_t swz = row_bytes == 64 ? (uint32_t)((row >> 1) & 3) : (uint32_t)((row >> 2) & 1);
+    // staged box: row r at r * 64 bytes, its 16-byte chunk j stored at slot j ^ ((r >> 1) & 3): conflict-free both
+    // for the row-per-thread writes and for the 4-lanes-per-row reads of the store phase
+    const uint32_t wr_off = (uint32_t)row * 64u;
+    const uint32_t wr_swz = (uint32_t)((row >> 1) & 3);
+    const int st_chunk = etid & 3, st_row0 = etid >> 2;  // store phase: chunk st_chunk of rows st_row0 + 32 i
     int as = 0;
     uint32_t aphase = 0;
     uint32_t box_it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
-      const int m0 = m_tile * kBlockM;
+      const long long m0 = (long long)m_tile * kBlockM;
       const int co0 = n_tile * p.nt;
-      // every epilogue thread is past its last read of s_scale/s_shift of the previous tile (barrier 2 of its last box)
+      // (every thread finished reading the previous tile's scale/shift before the barrier of its last box)
       for (int c = etid; c < p.nt; c += 128) {
         s_scale[c] = __ldg(p.scale + co0 + c);
         s_shift[c] = __ldg(p.shift + co0 + c);
       }
+      epi_bar(2);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccumCols);
-      int seg = 0;
-      for (int c0 = 0; c0 < p.nt; c0 += w, ++box_it) {
-        const int col = co0 + c0;
-        while (col >= p.seg_end[seg]) ++seg;
-        const int seg_col = col - (seg ? p.seg_end[seg - 1] : 0);
-        const bool relu = p.seg_relu[seg] != 0;
-        const uint32_t buf = epi_base + (box_it % (uint32_t)kEpiBufs) * kEpiBufBytes;
-        if (etid == 0) bulk_wait_read<kEpiBufs - 1>();  // the store that used this buffer kEpiBufs boxes ago has read it
-        epi_bar(1);                          // ... and s_scale / s_shift of this tile are visible
-        float f[32];
-        if (w == 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)c0, v);
+      if (p.debug & 8) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      }
+      for (int c0 = 0; c0 < ((p.debug & 8) ? 0 : p.nt); c0 += W, ++box_it) {
+        const uint32_t buf = epi_base + (box_it & 1u) * kEpiBufBytes;
+        float f[W];
+        {
+          uint32_t v[W];
+          if (kF32) {
+            tmem_ld16(taddr + (uint32_t)c0, reinterpret_cast<uint32_t(&)[16]>(v));
+          } else {
+            tmem_ld32(taddr + (uint32_t)c0, reinterpret_cast<uint32_t(&)[32]>(v));
+          }
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        } else {
-          uint32_t v[16];
-          tmem_ld16(taddr + (uint32_t)c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < W; ++j) f[j] = __uint_as_float(v[j]);
         }
-        if (c0 + w >= p.nt) {  // accumulator fully read: hand it back to the MMA warp before the stores
+        if (c0 + W >= p.nt) {  // accumulator fully read: hand it back to the MMA warp before the stores
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
+        // scale / shift / ReLU (the ReLU flag can change every 16 channels: segment boundaries)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < w) {
-            float y = fmaf(f[j], s_scale[c0 + j], s_shift[c0 + j]);
-            f[j] = relu ? fmaxf(y, 0.f) : y;
+        for (int h = 0; h < W / 16; ++h) {
+          const int col = co0 + c0 + 16 * h;
+          int sg = 0;
+          while (sg < kMaxSegs - 1 && col >= p.seg_end[sg]) ++sg;
+          const bool relu = p.seg_relu[sg] != 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 16 * h + 4 * q);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + 16 * h + 4 * q);
+            float* y = f + 16 * h + 4 * q;
+            y[0] = fmaf(y[0], sc.x, sh.x);
+            y[1] = fmaf(y[1], sc.y, sh.y);
+            y[2] = fmaf(y[2], sc.z, sh.z);
+            y[3] = fmaf(y[3], sc.w, sh.w);
+            if (relu) {
+              y[0] = fmaxf(y[0], 0.f);
+              y[1] = fmaxf(y[1], 0.f);
+              y[2] = fmaxf(y[2], 0.f);
+              y[3] = fmaxf(y[3], 0.f);
+            }
           }
         }
-        const uint32_t rbase = buf + (uint32_t)row * (uint32_t)row_bytes;
-        if (p.out_f32) {  // w == 16: 64-byte rows, 4 chunks of 4 floats
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            st_shared_v4(rbase + (((uint32_t)j ^ swz) << 4), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
-                         __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
-        } else if (w == 32) {  // 64-byte rows, 4 chunks of 8 halves
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            st_shared_v4(rbase + (((uint32_t)j ^ swz) << 4), pack_h2(f[8 * j], f[8 * j + 1]),
-                         pack_h2(f[8 * j + 2], f[8 * j + 3]), pack_h2(f[8 * j + 4], f[8 * j + 5]),
-                         pack_h2(f[8 * j + 6], f[8 * j + 7]));
-        } else {  // w == 16 fp16: 32-byte rows, 2 chunks
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            st_shared_v4(rbase + (((uint32_t)j ^ swz) << 4), pack_h2(f[8 * j], f[8 * j + 1]),
-                         pack_h2(f[8 * j + 2], f[8 * j + 3]), pack_h2(f[8 * j + 4], f[8 * j + 5]),
-                         pack_h2(f[8 * j + 6], f[8 * j + 7]));
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t dst = buf + wr_off + (((uint32_t)j ^ wr_swz) << 4);
+          if (kF32)
+            st_shared_v4(dst, __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                         __float_as_uint(f[4 * j + 3]));
+          else
+            st_shared_v4(dst, pack_h2(f[8 * j], f[8 * j + 1]), pack_h2(f[8 * j + 2], f[8 * j + 3]),
+                         pack_h2(f[8 * j + 4], f[8 * j + 5]), pack_h2(f[8 * j + 6], f[8 * j + 7]));
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA
-        epi_bar(2);
-        if (etid == 0) {
-          tma_store_2d(omaps[seg], buf, seg_col, m0);  // rows beyond M are clipped by the tensor map
-          bulk_commit();
+        epi_bar(1);  // box staged; also orders the reads of this buffer (box_it - 2) before these writes
+        // store phase: thread -> (chunk, 4 rows); 4 consecutive lanes write one pixel's 64 contiguous bytes
+        const int ccol = c0 + st_chunk * CPC;
+        if (ccol < p.nt) {
+          const int gcol = co0 + ccol;
+          int sg = 0;
+          while (sg < kMaxSegs - 1 && gcol >= p.seg_end[sg]) ++sg;
+          const int scol = gcol - (sg ? p.seg_end[sg - 1] : 0);
+          char* obase = reinterpret_cast<char*>(p.seg_out[sg]) + (size_t)scol * (kF32 ? 4 : 2);
+          const size_t pitch = (size_t)p.seg_stride[sg] * (kF32 ? 4 : 2);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = st_row0 + 32 * i;
+            const long long m = m0 + r;
+            if (m < p.M) {
+              const uint4 v = ld_shared_v4(buf + (uint32_t)r * 64u + (((uint32_t)st_chunk ^ (uint32_t)((r >> 1) & 3)) << 4));
+              *reinterpret_cast<uint4*>(obase + (size_t)m * pitch) = v;
+            }
+          }
         }
       }
       if (++as == 2) {
@@ -409,7 +449,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         aphase ^= 1u;
       }
     }
-    if (etid == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -490,32 +529,14 @@ int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPl
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, TISE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for weights", (int)r);
   }
-  // ---- outputs: one 2D store map per segment, dims (channels of the segment, all output pixels)
-  int box_w = a.out_f32 ? 16 : 32;
   int csum = 0;
   for (int i = 0; i < a.n_segs; ++i) {
     if (a.segs[i].c % 16) return fail(ctx, TISE_ERR_INVALID, "umma conv: segment of %d channels", a.segs[i].c);
+    if (((uintptr_t)a.segs[i].out & 15) || (a.segs[i].out_stride * (a.out_f32 ? 4 : 2)) % 16)
+      return fail(ctx, TISE_ERR_INVALID, "umma conv: output slice is not 16-byte aligned");
     csum += a.segs[i].c;
-    if (!a.out_f32 && (csum % 32 || nt % 32)) box_w = 16;
   }
   if (csum != L.cout) return fail(ctx, TISE_ERR_INVALID, "umma conv: segments cover %d of %d channels", csum, L.cout);
-  plan->box_w = box_w;
-  const int elt = a.out_f32 ? 4 : 2;
-  const long long M = (long long)a.n * a.ho * a.wo;
-  for (int i = 0; i < kMaxSegs; ++i) {
-    const ConvSeg& sg = a.segs[i < a.n_segs ? i : 0];  // unused slots repeat segment 0 (never dereferenced)
-    if (((uintptr_t)sg.out & 15) || (sg.out_stride * elt) % 16)
-      return fail(ctx, TISE_ERR_INVALID, "umma conv: output slice is not 16-byte aligned");
-    cuuint64_t dims[2] = {(cuuint64_t)sg.c, (cuuint64_t)M};
-    cuuint64_t strides[1] = {(cuuint64_t)sg.out_stride * elt};
-    cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)kBlockM};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&plan->tm_out[i], a.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-                                2, sg.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                box_w * elt == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
-                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ctx, TISE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for output %d", (int)r, i);
-  }
   plan->valid = true;
   return TISE_OK;
 }
@@ -527,15 +548,15 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   p.scale = L.d_scale;
   p.shift = L.d_shift;
   p.M = (long long)a.n * a.ho * a.wo;
-  p.out_f32 = a.out_f32;
-  p.n_segs = a.n_segs;
   int end = 0;
   for (int i = 0; i < kMaxSegs; ++i) {
-    if (i < a.n_segs) end += a.segs[i].c;
+    const ConvSeg& sg = a.segs[i < a.n_segs ? i : a.n_segs - 1];
+    if (i < a.n_segs) end += sg.c;
+    p.seg_out[i] = sg.out;
+    p.seg_stride[i] = sg.out_stride;
     p.seg_end[i] = i < a.n_segs ? end : 0x7fffffff;
-    p.seg_relu[i] = i < a.n_segs ? a.segs[i].relu : 0;
+    p.seg_relu[i] = sg.relu;
   }
-  p.box_w = plan.box_w;
   p.ho_wo = a.ho * a.wo;
   p.wo = a.wo;
   p.stride = L.stride;
@@ -551,23 +572,41 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   const int m_tiles = cdiv(p.M, kBlockM);
   p.num_tiles = m_tiles * p.n_ntiles;
   p.passes = passes;
-  p.stage_bytes = kABytes + passes * p.nt * 128;
+  p.kb_bytes = kABytes + passes * p.nt * 128;
+  static int debug_env = -1;
+  if (debug_env < 0) debug_env = getenv("TISE_UMMA_DEBUG") ? atoi(getenv("TISE_UMMA_DEBUG")) : 0;
+  p.debug = debug_env;
 
   static int configured_smem = 0;
   const int smem_limit = ctx->smem_optin > 0 ? ctx->smem_optin : 232448;
   if (configured_smem != smem_limit) {
-    TISE_CUDA(ctx, cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
+    TISE_CUDA(ctx, cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
+    TISE_CUDA(ctx, cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
     configured_smem = smem_limit;
   }
-  const int reserve = 1024 /*alignment*/ + kEpiBufs * kEpiBufBytes + 2 * kMaxNt * 4 + 8 * (2 * kMaxStages + 4) + 16;
-  int stages = (smem_limit - reserve) / p.stage_bytes;
+  const int reserve = 1024 /*alignment*/ + 2 * kEpiBufBytes + 2 * kMaxNt * 4 + 8 * (2 * kMaxStages + 4) + 16;
+  const int budget = smem_limit - reserve;
+  // K blocks per stage: enough MMA work (~1000 tensor cycles: one K block is 4 * passes MMAs of nt/2 cycles) to
+  // amortise the barrier round trip, as long as two stages still fit
+  const int kb_per_tile = L.R * L.S * p.n_chunks;
+  int group = (1000 + 2 * passes * p.nt - 1) / (2 * passes * p.nt);
+  if (group > budget / 2 / p.kb_bytes) group = budget / 2 / p.kb_bytes;
+  if (group > kb_per_tile) group = kb_per_tile;
+  if (group < 1) group = 1;
+  const char* genv = getenv("TISE_UMMA_GROUP");
+  if (genv && atoi(genv) > 0 && atoi(genv) <= budget / 2 / p.kb_bytes) group = atoi(genv) < kb_per_tile ? atoi(genv) : kb_per_tile;
+  p.group = group;
+  p.stage_bytes = group * p.kb_bytes;
+  int stages = budget / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(ctx, TISE_ERR_INVALID, "umma conv: tile does not fit shared memory");
   p.stages = stages;
   const int grid = p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms;
   // always request the full opt-in size: one CTA per SM, so the 512-column TMEM allocation never contends
-  conv_umma_kernel<<<grid, kNumThreads, smem_limit, st>>>(plan.tm_a, plan.tm_bhi, plan.tm_blo, plan.tm_out[0],
-                                                         plan.tm_out[1], plan.tm_out[2], plan.tm_out[3], p);
+  if (a.out_f32)
+    conv_umma_kernel<true><<<grid, kNumThreads, smem_limit, st>>>(plan.tm_a, plan.tm_bhi, plan.tm_blo, p);
+  else
+    conv_umma_kernel<false><<<grid, kNumThreads, smem_limit, st>>>(plan.tm_a, plan.tm_bhi, plan.tm_blo, p);
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;
 }
