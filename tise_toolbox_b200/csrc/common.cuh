@@ -68,18 +68,28 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 // ---------------------------------------------------------------------------------------------
 // One convolution layer, packed for the device (net.cu / conv_*.cu).
-// Weights are K-major [cout][taps * cin_pad] fp16 with k = (r * S + s) * cin_pad + ci, split into
-// hi = fp16(w * 2^e[co]) and lo = fp16(w * 2^e[co] - hi); scale already contains 2^-e[co].
+// K is walked as (filter tap, channel chunk of kc = 64 | 32 | 16 channels): kc is the largest of these that
+// divides cin (so no zero padding is ever moved), except cin = 48 which stays one padded 64-chunk.
+// Weights: fp16, K-major rows of ktot = taps * cin_pad elements with k = (r * S + s) * cin_pad + ci, split into
+// hi = fp16(w * 2^e[co]) and lo = fp16(w * 2^e[co] - hi) (scale already contains 2^-e[co]).  Rows are grouped
+// per output tile of nt channels as [tile][hi nt rows | lo nt rows], so the B operand of one tile is one
+// contiguous block of 2 * nt rows: row(co, plane) = ((co / nt) * 2 + plane) * nt + co % nt.
 // ---------------------------------------------------------------------------------------------
 struct ConvLayer {
   int cin = 0, cout = 0, R = 1, S = 1, stride = 1, pad_h = 0, pad_w = 0;
-  int cin_pad = 0;          // cin rounded up to 64
+  int kc = 64;              // channels per K chunk
+  int cin_pad = 0;          // cin rounded up to kc
   int ktot = 0;             // R * S * cin_pad
-  __half* d_whi = nullptr;  // [cout][ktot]
-  __half* d_wlo = nullptr;
+  int nt = 0;               // output channels per tile (divides cout, multiple of 16, <= 256)
+  __half* d_w = nullptr;    // [2 * cout][ktot], see above
   float* d_scale = nullptr;  // [cout]  gamma / sqrt(var + eps) * 2^-e
   float* d_shift = nullptr;  // [cout]  beta - mean * gamma / sqrt(var + eps)
 };
+int conv_chunk_of(int cin);
+int conv_ntile_of(int cout);
+static inline size_t conv_weight_row(const ConvLayer& L, int co, int plane) {
+  return ((size_t)(co / L.nt) * 2 + plane) * L.nt + co % L.nt;
+}
 
 // A conv launch: NHWC fp16 input view -> up to kMaxSegs NHWC destinations.  The layer's output channels
 // are split into consecutive segments, each written into its own tensor / channel slice (this is how
@@ -107,12 +117,9 @@ int conv_out_dim(int in, int k, int stride, int pad);
 int launch_conv_simt(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, cudaStream_t st);
 // conv_umma.cu
 struct UmmaPlan {  // tensor maps are tied to pointers, so a plan is built once per (layer, buffers)
-  alignas(64) CUtensorMap tm_a;
-  alignas(64) CUtensorMap tm_bhi;
-  alignas(64) CUtensorMap tm_blo;
-  alignas(64) CUtensorMap tm_out[kMaxSegs];  // 2D (channels of the segment, all output pixels) store maps
-  int nt = 0;     // output channels per tile
-  int box_w = 0;  // channels per TMA store box (16 or 32)
+  alignas(64) CUtensorMap tm_a;    // im2col map of the input view, box kc channels x 128 pixels
+  alignas(64) CUtensorMap tm_b;    // weights, box kc x nt rows
+  alignas(64) CUtensorMap tm_b2;   // weights, box kc x 2 nt rows (hi + lo in one load; only if 2 nt <= 256)
   bool valid = false;
 };
 int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPlan* plan);

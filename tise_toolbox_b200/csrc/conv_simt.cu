@@ -10,13 +10,12 @@ constexpr int SBM = 64, SBN = 64, SBK = 16;
 
 struct SimtParams {
   const __half* in;
-  const __half* whi;
-  const __half* wlo;
+  const __half* wt;  // packed rows, see ConvLayer
   const float* scale;
   const float* shift;
   void* seg_out[kMaxSegs];
   int seg_end[kMaxSegs], seg_stride[kMaxSegs], seg_relu[kMaxSegs];
-  int n, h, w, in_stride, cin, cin_pad, ktot;
+  int n, h, w, in_stride, cin, cin_pad, ktot, nt;
   int cout, R, S, stride, pad_h, pad_w, ho, wo, out_f32, passes;
   long long M;
 };
@@ -53,7 +52,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(SimtParams p) {
       const int iy = loy * p.stride - p.pad_h + r, ix = lox * p.stride - p.pad_w + s;
       const bool inb = lvalid && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
       const __half* arow = inb ? p.in + (((size_t)limg * p.h + iy) * p.w + ix) * p.in_stride : p.in;
-      const size_t wbase = (size_t)lco * p.ktot + (size_t)(r * p.S + s) * p.cin_pad;
+      const size_t whi = ((size_t)(lco / p.nt) * 2 * p.nt + lco % p.nt) * p.ktot + (size_t)(r * p.S + s) * p.cin_pad;
+      const size_t wlo = whi + (size_t)p.nt * p.ktot;
       for (int c0 = 0; c0 < p.cin; c0 += SBK) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(SimtParams p) {
           if (ci < p.cin) {
             if (inb) a = __half2float(arow[ci]);
             if (lco < p.cout) {
-              b = __half2float(p.whi[wbase + ci]);
-              if (p.passes == 2) b += __half2float(p.wlo[wbase + ci]);
+              b = __half2float(p.wt[whi + ci]);
+              if (p.passes == 2) b += __half2float(p.wt[wlo + ci]);
             }
           }
           sA[lq * 4 + j][lrow] = a;
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(SimtParams p) {
 int launch_conv_simt(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, cudaStream_t st) {
   SimtParams p;
   p.in = a.in;
-  p.whi = L.d_whi;
-  p.wlo = L.d_wlo;
+  p.wt = L.d_w;
+  p.nt = L.nt;
   p.scale = L.d_scale;
   p.shift = L.d_shift;
   int end = 0;

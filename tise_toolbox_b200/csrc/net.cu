@@ -31,16 +31,33 @@ static int dev_alloc(tise_ctx* ctx, std::vector<void*>* allocs, void** p, size_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// Packing: w [cout][cin][R][S] fp32 -> hi/lo fp16 planes [cout][(r*S+s)*cin_pad + ci], each output
-// channel scaled by 2^e so that its largest |w| lands in [2^11, 2^12): the lo plane then stays in
+// Packing: w [cout][cin][R][S] fp32 -> fp16 hi/lo rows in the layout described at ConvLayer (common.cuh).  Each
+// output channel is scaled by 2^e so that its largest |w| lands in [2^11, 2^12): the lo plane then stays in
 // fp16's normal range, and 2^-e is folded into the epilogue scale (exact).
 // ---------------------------------------------------------------------------------------------
+int conv_chunk_of(int cin) {
+  if (cin % 64 == 0) return 64;
+  if (cin % 32 == 0) return 32;
+  if (cin == 48) return 64;  // one padded chunk beats three 16-deep ones (TMA issue rate)
+  return 16;
+}
+// Largest divisor of cout that is a multiple of 16 and at most 256.
+int conv_ntile_of(int cout) {
+  for (int nt = 256; nt >= 16; nt -= 16)
+    if (cout % nt == 0) return nt;
+  return 0;
+}
+
 int pack_conv_layer(tise_ctx* ctx, ConvLayer* L, const float* w, const float* scale, const float* shift,
                     std::vector<void*>* allocs) {
-  L->cin_pad = (L->cin + 63) / 64 * 64;
+  L->kc = conv_chunk_of(L->cin);
+  L->cin_pad = (L->cin + L->kc - 1) / L->kc * L->kc;
   L->ktot = L->R * L->S * L->cin_pad;
-  const size_t n = (size_t)L->cout * L->ktot;
-  std::vector<__half> hi(n, __float2half_rn(0.f)), lo(n, __float2half_rn(0.f));
+  L->nt = conv_ntile_of(L->cout);
+  if (L->cout % 16 || L->cin % 16 || L->nt == 0)
+    return fail(ctx, TISE_ERR_INVALID, "conv layer %d -> %d channels: both must be multiples of 16", L->cin, L->cout);
+  const size_t n = (size_t)2 * L->cout * L->ktot;
+  std::vector<__half> wp(n, __float2half_rn(0.f));
   std::vector<float> sc(L->cout), sh(L->cout);
   const int taps = L->R * L->S;
   for (int co = 0; co < L->cout; ++co) {
@@ -49,25 +66,24 @@ int pack_conv_layer(tise_ctx* ctx, ConvLayer* L, const float* w, const float* sc
     for (int i = 0; i < L->cin * taps; ++i) maxabs = fmaxf(maxabs, fabsf(wc[i]));
     int e = 0;
     if (maxabs > 0.f && isfinite(maxabs)) e = 11 - ilogbf(maxabs);
+    __half* hi = wp.data() + conv_weight_row(*L, co, 0) * L->ktot;
+    __half* lo = wp.data() + conv_weight_row(*L, co, 1) * L->ktot;
     for (int ci = 0; ci < L->cin; ++ci)
       for (int t = 0; t < taps; ++t) {
         const float v = ldexpf(wc[(size_t)ci * taps + t], e);
         const __half h = __float2half_rn(v);
-        const __half l = __float2half_rn(v - __half2float(h));
-        const size_t k = (size_t)co * L->ktot + (size_t)t * L->cin_pad + ci;
+        const size_t k = (size_t)t * L->cin_pad + ci;
         hi[k] = h;
-        lo[k] = l;
+        lo[k] = __float2half_rn(v - __half2float(h));
       }
     sc[co] = ldexpf(scale[co], -e);
     sh[co] = shift[co];
   }
   int rc;
-  if ((rc = dev_alloc(ctx, allocs, (void**)&L->d_whi, n * sizeof(__half)))) return rc;
-  if ((rc = dev_alloc(ctx, allocs, (void**)&L->d_wlo, n * sizeof(__half)))) return rc;
+  if ((rc = dev_alloc(ctx, allocs, (void**)&L->d_w, n * sizeof(__half)))) return rc;
   if ((rc = dev_alloc(ctx, allocs, (void**)&L->d_scale, L->cout * sizeof(float)))) return rc;
   if ((rc = dev_alloc(ctx, allocs, (void**)&L->d_shift, L->cout * sizeof(float)))) return rc;
-  TISE_CUDA(ctx, cudaMemcpy(L->d_whi, hi.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
-  TISE_CUDA(ctx, cudaMemcpy(L->d_wlo, lo.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+  TISE_CUDA(ctx, cudaMemcpy(L->d_w, wp.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
   TISE_CUDA(ctx, cudaMemcpy(L->d_scale, sc.data(), L->cout * sizeof(float), cudaMemcpyHostToDevice));
   TISE_CUDA(ctx, cudaMemcpy(L->d_shift, sh.data(), L->cout * sizeof(float), cudaMemcpyHostToDevice));
   return TISE_OK;
