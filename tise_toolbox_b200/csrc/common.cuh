@@ -120,6 +120,7 @@ struct UmmaPlan {  // tensor maps are tied to pointers, so a plan is built once 
   alignas(64) CUtensorMap tm_a;    // im2col map of the input view, box kc channels x 128 pixels
   alignas(64) CUtensorMap tm_b;    // weights, box kc x nt rows
   alignas(64) CUtensorMap tm_b2;   // weights, box kc x 2 nt rows (hi + lo in one load; only if 2 nt <= 256)
+  alignas(64) CUtensorMap tm_bs;   // weights, box kc x nt / 2 rows: the slices of the cluster multicast
   bool valid = false;
 };
 int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPlan* plan);

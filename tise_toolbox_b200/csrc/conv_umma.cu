@@ -61,6 +61,9 @@ struct UmmaParams {
   int nt, n_ntiles, num_tiles;
   int passes, stages, stage_bytes;
   int group, kb_bytes;  // K blocks per pipeline stage, bytes of one K block (A + B planes)
+  int cs;               // CTAs per cluster (1, 2, 4): they work on cs consecutive M tiles of the same N tile and
+                        // each loads 1/cs of the weight rows, multicast to all (TMA cost is per row)
+  int m_tiles;
   int debug;            // timing ablations (TISE_UMMA_DEBUG): 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip epilogue
 };
 
@@ -107,6 +110,28 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mcast(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, "
+      "%5}], [%2], %3;" ::"r"(dst),
+      "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_load_im2col(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c, int w, int h,
                                                 int n, uint16_t off_w, uint16_t off_h) {
@@ -199,7 +224,8 @@ __device__ __forceinline__ uint32_t make_instr_desc(int n) {
 template <bool kF32>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const __grid_constant__ CUtensorMap tm_b2, const UmmaParams p) {
+                 const __grid_constant__ CUtensorMap tm_b2, const __grid_constant__ CUtensorMap tm_bs,
+                 const UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   // layout: [stages x group x (A | B_hi | B_lo)] [2 staged output boxes] [scale cout | shift cout] [barriers] [tmem slot]
@@ -221,7 +247,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), (uint32_t)p.cs);  // every CTA of the cluster must have consumed the multicast weights
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -237,8 +263,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cs > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const int crank = p.cs > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / p.cs, num_clusters = gridDim.x / p.cs;
+  const int num_super = ((p.m_tiles + p.cs - 1) / p.cs) * p.n_ntiles;  // (group of cs M tiles, N tile) work items
+  const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
 
   const int kb_per_tile = p.R * p.S * p.n_chunks;
   const uint32_t a_bytes = (uint32_t)p.a_bytes, b_bytes = (uint32_t)p.b_bytes;
@@ -253,8 +284,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ===================================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
+    // cluster mode: the passes * nt weight rows of a K block are cut into slices of nt / 2 rows; this CTA loads
+    // n_slices of them and multicasts each to every CTA of the cluster
+    const int half_rows = p.nt / 2;
+    const int n_slices = 2 * p.passes / p.cs;
+    const uint32_t half_bytes = (uint32_t)(half_rows * p.kc * 2);
+    for (int st = cluster_id; st < num_super; st += num_clusters) {
+      const int m_group = st / p.n_ntiles, n_tile = st - m_group * p.n_ntiles;
+      const int m_tile = m_group * p.cs + crank;  // may be past the end in the last group: loads zero-fill, nothing is stored
       const long long m0 = (long long)m_tile * kBlockM;
       const int img = (int)(m0 / p.ho_wo);
       const int rem = (int)(m0 - (long long)img * p.ho_wo);
@@ -279,7 +316,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (!(p.debug & 1))
               tma_load_im2col(&tm_a, sa, full_bar(stage), ch * p.kc, wc, hc, img, (uint16_t)sx, (uint16_t)r);
             if (!(p.debug & 2)) {
-              if (wide2) {
+              if (p.cs > 1) {
+                for (int i = 0; i < n_slices; ++i) {
+                  const int sl = crank * n_slices + i;
+                  tma_load_2d_mcast(&tm_bs, sa + a_bytes + (uint32_t)sl * half_bytes, full_bar(stage), kcol,
+                                    brow + sl * half_rows, cmask);
+                }
+              } else if (wide2) {
                 tma_load_2d(&tm_b2, sa + a_bytes, full_bar(stage), kcol, brow);  // hi and lo rows in one box
               } else {
                 tma_load_2d(&tm_b, sa + a_bytes, full_bar(stage), kcol, brow);
@@ -310,7 +353,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int st = cluster_id; st < num_super; st += num_clusters) {
       mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccumCols);
@@ -335,7 +378,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
             if (++chunk == p.n_chunks) chunk = 0;
           }
-          umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+          // frees the smem stage once these MMAs have read it -- in every CTA of the cluster, whose multicasts land here
+          if (p.cs > 1) umma_commit_mcast(empty_bar(stage), cmask); else umma_commit(empty_bar(stage));
           if (kb0 + g >= kb_per_tile) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
         }
         __syncwarp();
@@ -372,9 +416,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     int as = 0;
     uint32_t aphase = 0;
     uint32_t box_it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_ntiles, n_tile = tile - m_tile * p.n_ntiles;
-      const long long m0 = (long long)m_tile * kBlockM;
+    for (int st = cluster_id; st < num_super; st += num_clusters) {
+      const int m_group = st / p.n_ntiles, n_tile = st - m_group * p.n_ntiles;
+      const long long m0 = (long long)(m_group * p.cs + crank) * kBlockM;
       const int co0 = n_tile * p.nt;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
@@ -477,6 +521,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (p.cs > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or signal its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -551,6 +596,17 @@ int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPl
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, TISE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for weights", (int)r);
   }
+  // weight slices of nt / 2 rows for the cluster multicast
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)L.ktot, (cuuint64_t)2 * L.cout};
+    cuuint64_t strides[1] = {(cuuint64_t)L.ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)L.kc, (cuuint32_t)(L.nt / 2)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&plan->tm_bs, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)L.d_w, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(L.kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, TISE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for weight slices", (int)r);
+  }
   int csum = 0;
   for (int i = 0; i < a.n_segs; ++i) {
     if (a.segs[i].c % 16) return fail(ctx, TISE_ERR_INVALID, "umma conv: segment of %d channels", a.segs[i].c);
@@ -599,7 +655,16 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   p.sbo = 8 * L.kc * 2;
   p.wide = 2 * L.nt <= 256 ? 1 : 0;
   const int m_tiles = cdiv(p.M, kBlockM);
+  p.m_tiles = m_tiles;
   p.num_tiles = m_tiles * p.n_ntiles;
+  // cluster size: with two passes every CTA of a 4-cluster loads nt / 2 weight rows (half of hi+lo) per K block
+  static int cs_env = -1;
+  if (cs_env < 0) cs_env = getenv("TISE_UMMA_CLUSTER") ? atoi(getenv("TISE_UMMA_CLUSTER")) : 0;
+  int cs = passes == 2 ? 4 : 2;
+  if (cs_env == 1 || cs_env == 2 || cs_env == 4) cs = cs_env;
+  if (passes == 1 && cs == 4) cs = 2;  // slice rows must stay a multiple of 8 (one swizzle atom)
+  while (cs > 1 && m_tiles < cs) cs >>= 1;
+  p.cs = cs;
   p.passes = passes;
   p.kb_bytes = p.a_bytes + passes * p.b_bytes;
   static int debug_env = -1;
@@ -629,12 +694,35 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(ctx, TISE_ERR_INVALID, "umma conv: tile does not fit shared memory");
   p.stages = stages;
-  const int grid = p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms;
+  const int num_super = cdiv(m_tiles, cs) * p.n_ntiles;
   // always request the full opt-in size: one CTA per SM, so the 512-column TMEM allocation never contends
-  if (a.out_f32)
-    conv_umma_kernel<true><<<grid, kNumThreads, smem_limit, st>>>(plan.tm_a, plan.tm_b, plan.tm_b2, p);
-  else
-    conv_umma_kernel<false><<<grid, kNumThreads, smem_limit, st>>>(plan.tm_a, plan.tm_b, plan.tm_b2, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ctx->num_sms / cs * cs));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = (size_t)smem_limit;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // the schedule is static (persistent CTAs), so the grid must not exceed the clusters that can be co-resident
+  static int max_clusters[5] = {0, 0, 0, 0, 0};
+  if (!max_clusters[cs]) {
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, conv_umma_kernel<false>, &cfg) != cudaSuccess || nc < 1) nc = ctx->num_sms / cs;
+    max_clusters[cs] = nc;
+  }
+  int clusters = max_clusters[cs];
+  if (clusters > ctx->num_sms / cs) clusters = ctx->num_sms / cs;
+  if (clusters > num_super) clusters = num_super;
+  cfg.gridDim = dim3((unsigned)(clusters * cs));
+  const CUtensorMap& tm_bs = plan.tm_bs;
+  cudaError_t le = a.out_f32 ? cudaLaunchKernelEx(&cfg, conv_umma_kernel<true>, plan.tm_a, plan.tm_b, plan.tm_b2, tm_bs, p)
+                             : cudaLaunchKernelEx(&cfg, conv_umma_kernel<false>, plan.tm_a, plan.tm_b, plan.tm_b2, tm_bs, p);
+  if (le != cudaSuccess) return fail(ctx, TISE_ERR_CUDA, "conv_umma_kernel launch failed: %s", cudaGetErrorString(le));
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;
 }

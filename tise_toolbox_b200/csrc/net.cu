@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "net.cuh"
@@ -36,10 +37,18 @@ static int dev_alloc(tise_ctx* ctx, std::vector<void*>* allocs, void** p, size_t
 // fp16's normal range, and 2^-e is folded into the epilogue scale (exact).
 // ---------------------------------------------------------------------------------------------
 int conv_chunk_of(int cin) {
-  if (cin % 64 == 0) return 64;
-  if (cin % 32 == 0) return 32;
-  if (cin == 48) return 64;  // one padded chunk beats three 16-deep ones (TMA issue rate)
-  return 16;
+  // TMA cost was measured to be per row (one pixel's / one output channel's chunk), ~2 cycles regardless of the
+  // row width, so narrower chunks only add rows: keep 64-channel chunks and let TMA zero-fill the remainder
+  // (the kernel supports kc = 32 and 16 -- SWIZZLE_64B / 32B operand tiles -- via TISE_UMMA_KC for experiments).
+  const char* e = getenv("TISE_UMMA_KC");
+  if (e && atoi(e) == 1) {
+    if (cin % 64 == 0) return 64;
+    if (cin % 32 == 0) return 32;
+    if (cin == 48) return 64;
+    return 16;
+  }
+  (void)cin;
+  return 64;
 }
 // Largest divisor of cout that is a multiple of 16 and at most 256.
 int conv_ntile_of(int cout) {
