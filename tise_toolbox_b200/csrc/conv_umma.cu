@@ -92,13 +92,14 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Spins on try_wait (which itself suspends the thread for a hardware-defined interval).  A pipeline
-// bug would otherwise hang the GPU; after ~2 s the kernel traps instead, which surfaces as a launch error.
+// Spins on try_wait (which itself suspends the thread for a hardware-defined interval).  A pipeline bug would
+// otherwise hang the GPU: after ~2^28 failed probes (seconds) the kernel traps instead, which surfaces as a
+// launch error.  (A clock read inside this loop costs ~80 cycles per producer/consumer hand-off, measured with
+// tools/mbar_bench.cu, so the bound is a probe count.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t probes = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (++probes == (1u << 28)) {
       printf("conv_umma_kernel: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, bar, parity);
       __trap();
@@ -298,43 +299,43 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int oy = rem / p.wo, ox = rem - oy * p.wo;
       const int wc = ox * p.stride - p.pad_w, hc = oy * p.stride - p.pad_h;  // base pixel (tap 0,0)
       const int brow = n_tile * 2 * p.nt;  // first hi row of this tile's weight block; the lo rows follow
+      // (tap r, sx; chunk ch) of the next K block; all lanes keep the counters, one elected lane issues the loads
+      int r = 0, sx = 0, ch = 0, kcol = 0;
       for (int kb0 = 0; kb0 < kb_per_tile; kb0 += p.group) {
         const int g = min(p.group, kb_per_tile - kb0);
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sbase = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
+        const uint32_t fb = full_bar(stage);
+        uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
         if (elect_one()) {
           if (kb_tx)
-            mbar_expect_tx(full_bar(stage), (uint32_t)g * kb_tx);
+            mbar_expect_tx(fb, (uint32_t)g * kb_tx);
           else
-            mbar_arrive(full_bar(stage));
-          int ch = kb0 % p.n_chunks;
-          const int tap = kb0 / p.n_chunks;
-          int r = tap / p.S, sx = tap - r * p.S;
-          for (int j = 0; j < g; ++j) {
-            const uint32_t sa = sbase + (uint32_t)j * (uint32_t)p.kb_bytes;
-            const int kcol = (r * p.S + sx) * p.cin_pad + ch * p.kc;
-            if (!(p.debug & 1))
-              tma_load_im2col(&tm_a, sa, full_bar(stage), ch * p.kc, wc, hc, img, (uint16_t)sx, (uint16_t)r);
+            mbar_arrive(fb);
+        }
+        for (int j = 0; j < g; ++j) {
+          if (elect_one()) {
+            if (!(p.debug & 1)) tma_load_im2col(&tm_a, sa, fb, ch * p.kc, wc, hc, img, (uint16_t)sx, (uint16_t)r);
             if (!(p.debug & 2)) {
               if (p.cs > 1) {
                 for (int i = 0; i < n_slices; ++i) {
                   const int sl = crank * n_slices + i;
-                  tma_load_2d_mcast(&tm_bs, sa + a_bytes + (uint32_t)sl * half_bytes, full_bar(stage), kcol,
-                                    brow + sl * half_rows, cmask);
+                  tma_load_2d_mcast(&tm_bs, sa + a_bytes + (uint32_t)sl * half_bytes, fb, kcol, brow + sl * half_rows, cmask);
                 }
               } else if (wide2) {
-                tma_load_2d(&tm_b2, sa + a_bytes, full_bar(stage), kcol, brow);  // hi and lo rows in one box
+                tma_load_2d(&tm_b2, sa + a_bytes, fb, kcol, brow);  // hi and lo rows in one box
               } else {
-                tma_load_2d(&tm_b, sa + a_bytes, full_bar(stage), kcol, brow);
-                if (p.passes == 2) tma_load_2d(&tm_b, sa + a_bytes + b_bytes, full_bar(stage), kcol, brow + p.nt);
+                tma_load_2d(&tm_b, sa + a_bytes, fb, kcol, brow);
+                if (p.passes == 2) tma_load_2d(&tm_b, sa + a_bytes + b_bytes, fb, kcol, brow + p.nt);
               }
             }
-            if (++ch == p.n_chunks) {
-              ch = 0;
-              if (++sx == p.S) {
-                sx = 0;
-                ++r;
-              }
+          }
+          sa += (uint32_t)p.kb_bytes;
+          kcol += p.kc;  // k = (r * S + sx) * cin_pad + ch * kc advances by kc per K block
+          if (++ch == p.n_chunks) {
+            ch = 0;
+            if (++sx == p.S) {
+              sx = 0;
+              ++r;
             }
           }
         }
@@ -357,30 +358,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccumCols);
+      int chunk = 0;
+      uint32_t first = 0;  // 0 for the very first MMA of the tile (overwrite), 1 afterwards (accumulate)
       for (int kb0 = 0; kb0 < kb_per_tile; kb0 += p.group) {
         const int g = min(p.group, kb_per_tile - kb0);
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t sbase = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
-        if (elect_one()) {
-          int chunk = kb0 % p.n_chunks;
-          for (int j = 0; j < g; ++j) {
-            const uint32_t sa = sbase + (uint32_t)j * (uint32_t)p.kb_bytes;
-            const uint64_t adesc = make_smem_desc(sa, dhi);
-            const uint64_t bhi = make_smem_desc(sa + a_bytes, dhi);
-            const uint64_t blo = make_smem_desc(sa + a_bytes + b_bytes, dhi);
-            const int ksteps = (p.debug & 4) ? 0 : ((chunk == p.n_chunks - 1) ? p.last_ksteps : p.ksteps);
+        // descriptors differ from K block to K block only in the 14-bit start-address field
+        uint64_t adesc = make_smem_desc(smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes, dhi);
+        for (int j = 0; j < g; ++j) {
+          const int ksteps = (p.debug & 4) ? 0 : ((chunk == p.n_chunks - 1) ? p.last_ksteps : p.ksteps);
+          if (elect_one()) {
+            const uint64_t bhi = adesc + (uint64_t)(a_bytes >> 4);
+            const uint64_t blo = bhi + (uint64_t)(b_bytes >> 4);
             for (int k = 0; k < ksteps; ++k) {
               // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (>>4) address field
-              umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), idesc, (kb0 | j | k) != 0 ? 1u : 0u);
-              if (p.passes == 2 && !wide2)
-                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc, 1u);
+              umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+              if (p.passes == 2 && !wide2) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc, 1u);
             }
-            if (++chunk == p.n_chunks) chunk = 0;
           }
+          first = 1u;
+          adesc += (uint64_t)(p.kb_bytes >> 4);
+          if (++chunk == p.n_chunks) chunk = 0;
+        }
+        if (elect_one()) {
           // frees the smem stage once these MMAs have read it -- in every CTA of the cluster, whose multicasts land here
-          if (p.cs > 1) umma_commit_mcast(empty_bar(stage), cmask); else umma_commit(empty_bar(stage));
-          if (kb0 + g >= kb_per_tile) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+          if (p.debug & 16) mbar_arrive(empty_bar(stage));  // timing experiment only (needs debug & 4)
+          else if (p.cs > 1) umma_commit_mcast(empty_bar(stage), cmask); else umma_commit(empty_bar(stage));
+          if (kb0 + g >= kb_per_tile) {  // accumulator complete -> epilogue
+            if (p.debug & 32) mbar_arrive(tfull_bar(as)); else umma_commit(tfull_bar(as));
+          }
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -719,6 +726,12 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   if (clusters > ctx->num_sms / cs) clusters = ctx->num_sms / cs;
   if (clusters > num_super) clusters = num_super;
   cfg.gridDim = dim3((unsigned)(clusters * cs));
+  static int verbose = -1;
+  if (verbose < 0) verbose = getenv("TISE_UMMA_VERBOSE") ? 1 : 0;
+  if (verbose)
+    fprintf(stderr, "conv_umma %dx%d cin%d cout%d k%dx%d: nt %d kc %d wide %d group %d stages %d stage_bytes %d cs %d grid %d tiles %d\n",
+            a.h, a.w, L.cin, L.cout, L.R, L.S, p.nt, p.kc, p.wide, p.group, p.stages, p.stage_bytes, cs, clusters * cs,
+            p.num_tiles);
   const CUtensorMap& tm_bs = plan.tm_bs;
   cudaError_t le = a.out_f32 ? cudaLaunchKernelEx(&cfg, conv_umma_kernel<true>, plan.tm_a, plan.tm_b, plan.tm_b2, tm_bs, p)
                              : cudaLaunchKernelEx(&cfg, conv_umma_kernel<false>, plan.tm_a, plan.tm_b, plan.tm_b2, tm_bs, p);
