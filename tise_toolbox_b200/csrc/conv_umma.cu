@@ -40,6 +40,7 @@ constexpr int kMaxStages = 8;
 constexpr int kAccumCols = 256;  // TMEM columns per accumulator stage
 constexpr int kNumThreads = 192;
 constexpr int kMaxNt = 256;
+constexpr int kMaxKb = 96;      // K blocks per tile: taps * ceil(cin / 64) (<= 63 in Inception-v3)
 constexpr int kMaxCout = 1344;  // widest (fused) layer: Mixed_7b 320 + 384 + 448 + 192
 constexpr int kEpiBufBytes = 128 * 64;  // staged output box: 128 pixels x 64 bytes (32 fp16 or 16 fp32 channels)
 
@@ -222,11 +223,17 @@ __device__ __forceinline__ uint32_t make_instr_desc(int n) {
 }
 
 // ----------------------------------------------------------------------------- kernel
-template <bool kF32>
+template <bool kF32, bool kCluster, bool kDebug>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_b2, const __grid_constant__ CUtensorMap tm_bs,
                  const UmmaParams p) {
+  // The producer and MMA warps are single instruction streams in which every dependent instruction costs its full
+  // latency (~10 cycles, ~25 for a constant-bank load), so their loops must be short: a private copy of the
+  // parameters keeps them in registers (the "memory" clobbers of the PTX wrappers would otherwise force a reload
+  // from the constant bank on every use), and the timing-ablation branches exist only in the kDebug instantiation.
+  const int dbg = kDebug ? p.debug : 0;
+  const int pcs = kCluster ? p.cs : 1;  // compile-time 1 in the non-cluster instantiation
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   // layout: [stages x group x (A | B_hi | B_lo)] [2 staged output boxes] [scale cout | shift cout] [barriers] [tmem slot]
@@ -239,6 +246,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   auto tfull_bar = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4);
+  // per-K-block table {channel offset, tap s | tap r << 16, weight column, MMA K steps}: built once so that the
+  // producer / MMA loops need no counters, divisions or branches per K block
+  uint4* kbtab = reinterpret_cast<uint4*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -248,7 +258,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), (uint32_t)p.cs);  // every CTA of the cluster must have consumed the multicast weights
+      mbar_init(empty_bar(s), (uint32_t)(kCluster ? p.cs : 1));  // every CTA of the cluster must have consumed the multicast weights
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -257,6 +267,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  for (int kb = threadIdx.x; kb < p.R * p.S * p.n_chunks; kb += blockDim.x) {
+    const int ch = kb % p.n_chunks, tap = kb / p.n_chunks;
+    const int r = tap / p.S, sx = tap - r * p.S;
+    kbtab[kb] = make_uint4((uint32_t)(ch * p.kc), (uint32_t)sx | ((uint32_t)r << 16), (uint32_t)(kb * p.kc),
+                           (uint32_t)((kDebug && (p.debug & 4)) ? 0 : (ch == p.n_chunks - 1 ? p.last_ksteps : p.ksteps)));
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
                  : "memory");
@@ -264,17 +280,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cs > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast can reach them
+  if (kCluster) cluster_sync_all();  // peers' barriers are initialised before any multicast can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const int crank = p.cs > 1 ? (int)cluster_ctarank() : 0;
-  const int cluster_id = blockIdx.x / p.cs, num_clusters = gridDim.x / p.cs;
-  const int num_super = ((p.m_tiles + p.cs - 1) / p.cs) * p.n_ntiles;  // (group of cs M tiles, N tile) work items
-  const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
+  const int crank = kCluster ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / pcs, num_clusters = gridDim.x / pcs;
+  const int num_super = ((p.m_tiles + pcs - 1) / pcs) * p.n_ntiles;  // (group of cs M tiles, N tile) work items
+  const uint16_t cmask = (uint16_t)((1u << pcs) - 1u);
 
   const int kb_per_tile = p.R * p.S * p.n_chunks;
   const uint32_t a_bytes = (uint32_t)p.a_bytes, b_bytes = (uint32_t)p.b_bytes;
-  const uint32_t kb_tx = ((p.debug & 1) ? 0u : a_bytes) + ((p.debug & 2) ? 0u : (uint32_t)p.passes * b_bytes);
+  const uint32_t kb_tx = ((dbg & 1) ? 0u : a_bytes) + ((dbg & 2) ? 0u : (uint32_t)p.passes * b_bytes);
   const bool wide2 = p.wide && p.passes == 2;
 
   // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the mbarriers and compute the
@@ -283,66 +299,59 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   // uniform-datapath instruction in an election loop (~700 cycles per K block, measured).
   if (warp == 0) {
     // ===================================================================== TMA producer
-    int stage = 0;
-    uint32_t phase = 0;
+    const int group = p.group, n_stages = p.stages, nt = p.nt;
+    const uint32_t stage_bytes = (uint32_t)p.stage_bytes, kb_bytes = (uint32_t)p.kb_bytes;
+    const bool two_loads = p.passes == 2 && !wide2;
     // cluster mode: the passes * nt weight rows of a K block are cut into slices of nt / 2 rows; this CTA loads
     // n_slices of them and multicasts each to every CTA of the cluster
     const int half_rows = p.nt / 2;
-    const int n_slices = 2 * p.passes / p.cs;
+    const int n_slices = 2 * p.passes / pcs;
     const uint32_t half_bytes = (uint32_t)(half_rows * p.kc * 2);
+    int stage = 0;
+    uint32_t phase = 0;
     for (int st = cluster_id; st < num_super; st += num_clusters) {
       const int m_group = st / p.n_ntiles, n_tile = st - m_group * p.n_ntiles;
-      const int m_tile = m_group * p.cs + crank;  // may be past the end in the last group: loads zero-fill, nothing is stored
+      const int m_tile = m_group * pcs + crank;  // may be past the end in the last group: loads zero-fill, nothing is stored
       const long long m0 = (long long)m_tile * kBlockM;
       const int img = (int)(m0 / p.ho_wo);
       const int rem = (int)(m0 - (long long)img * p.ho_wo);
       const int oy = rem / p.wo, ox = rem - oy * p.wo;
       const int wc = ox * p.stride - p.pad_w, hc = oy * p.stride - p.pad_h;  // base pixel (tap 0,0)
-      const int brow = n_tile * 2 * p.nt;  // first hi row of this tile's weight block; the lo rows follow
-      // (tap r, sx; chunk ch) of the next K block; all lanes keep the counters, one elected lane issues the loads
-      int r = 0, sx = 0, ch = 0, kcol = 0;
-      for (int kb0 = 0; kb0 < kb_per_tile; kb0 += p.group) {
-        const int g = min(p.group, kb_per_tile - kb0);
-        mbar_wait(empty_bar(stage), phase ^ 1u);
+      const int brow = n_tile * 2 * nt;  // first hi row of this tile's weight block; the lo rows follow
+      int jg = 0;
+      uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+      for (int kb = 0; kb < kb_per_tile; ++kb) {
+        if (jg == 0) mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint4 e = kbtab[kb];
         const uint32_t fb = full_bar(stage);
-        uint32_t sa = smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes;
         if (elect_one()) {
-          if (kb_tx)
-            mbar_expect_tx(fb, (uint32_t)g * kb_tx);
-          else
-            mbar_arrive(fb);
-        }
-        for (int j = 0; j < g; ++j) {
-          if (elect_one()) {
-            if (!(p.debug & 1)) tma_load_im2col(&tm_a, sa, fb, ch * p.kc, wc, hc, img, (uint16_t)sx, (uint16_t)r);
-            if (!(p.debug & 2)) {
-              if (p.cs > 1) {
-                for (int i = 0; i < n_slices; ++i) {
-                  const int sl = crank * n_slices + i;
-                  tma_load_2d_mcast(&tm_bs, sa + a_bytes + (uint32_t)sl * half_bytes, fb, kcol, brow + sl * half_rows, cmask);
-                }
-              } else if (wide2) {
-                tma_load_2d(&tm_b2, sa + a_bytes, fb, kcol, brow);  // hi and lo rows in one box
-              } else {
-                tma_load_2d(&tm_b, sa + a_bytes, fb, kcol, brow);
-                if (p.passes == 2) tma_load_2d(&tm_b, sa + a_bytes + b_bytes, fb, kcol, brow + p.nt);
+          if (jg == 0) {
+            const uint32_t g = (uint32_t)min(group, kb_per_tile - kb);
+            if (kb_tx) mbar_expect_tx(fb, g * kb_tx); else mbar_arrive(fb);
+          }
+          if (!(dbg & 1)) tma_load_im2col(&tm_a, sa, fb, (int)e.x, wc, hc, img, (uint16_t)(e.y & 0xffffu), (uint16_t)(e.y >> 16));
+          if (!(dbg & 2)) {
+            if (kCluster) {
+              for (int i = 0; i < n_slices; ++i) {
+                const int sl = crank * n_slices + i;
+                tma_load_2d_mcast(&tm_bs, sa + a_bytes + (uint32_t)sl * half_bytes, fb, (int)e.z, brow + sl * half_rows, cmask);
               }
-            }
-          }
-          sa += (uint32_t)p.kb_bytes;
-          kcol += p.kc;  // k = (r * S + sx) * cin_pad + ch * kc advances by kc per K block
-          if (++ch == p.n_chunks) {
-            ch = 0;
-            if (++sx == p.S) {
-              sx = 0;
-              ++r;
+            } else if (!two_loads) {
+              tma_load_2d(wide2 ? &tm_b2 : &tm_b, sa + a_bytes, fb, (int)e.z, brow);  // wide: hi and lo rows in one box
+            } else {
+              tma_load_2d(&tm_b, sa + a_bytes, fb, (int)e.z, brow);
+              tma_load_2d(&tm_b, sa + a_bytes + b_bytes, fb, (int)e.z, brow + nt);
             }
           }
         }
-        __syncwarp();
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1u;
+        sa += kb_bytes;
+        if (++jg == group || kb == kb_per_tile - 1) {
+          jg = 0;
+          if (++stage == n_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          sa = smem_base + (uint32_t)stage * stage_bytes;
         }
       }
     }
@@ -350,6 +359,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ===================================================================== MMA issuer
     const uint32_t idesc = make_instr_desc(wide2 ? 2 * p.nt : p.nt);
     const uint64_t dhi = smem_desc_hi(p.swz_type, p.sbo);
+    const int group = p.group, n_stages = p.stages;
+    const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+    const uint64_t kb_desc_step = (uint64_t)(p.kb_bytes >> 4), bhi_off = (uint64_t)(a_bytes >> 4),
+                   blo_off = (uint64_t)((a_bytes + b_bytes) >> 4);
+    const bool two_mma = p.passes == 2 && !wide2;
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -358,41 +372,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccumCols);
-      int chunk = 0;
-      uint32_t first = 0;  // 0 for the very first MMA of the tile (overwrite), 1 afterwards (accumulate)
-      for (int kb0 = 0; kb0 < kb_per_tile; kb0 += p.group) {
-        const int g = min(p.group, kb_per_tile - kb0);
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
-        // descriptors differ from K block to K block only in the 14-bit start-address field
-        uint64_t adesc = make_smem_desc(smem_base + (uint32_t)stage * (uint32_t)p.stage_bytes, dhi);
-        for (int j = 0; j < g; ++j) {
-          const int ksteps = (p.debug & 4) ? 0 : ((chunk == p.n_chunks - 1) ? p.last_ksteps : p.ksteps);
-          if (elect_one()) {
-            const uint64_t bhi = adesc + (uint64_t)(a_bytes >> 4);
-            const uint64_t blo = bhi + (uint64_t)(b_bytes >> 4);
-            for (int k = 0; k < ksteps; ++k) {
-              // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (>>4) address field
-              umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
-              if (p.passes == 2 && !wide2) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc, 1u);
+      int jg = 0;
+      // descriptors differ from K block to K block only in the 14-bit start-address field
+      uint64_t adesc = make_smem_desc(smem_base + (uint32_t)stage * stage_bytes, dhi);
+      for (int kb = 0; kb < kb_per_tile; ++kb) {
+        if (jg == 0) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+        }
+        const int ksteps = (int)kbtab[kb].w;
+        const bool last_in_group = (jg + 1 == group) || (kb == kb_per_tile - 1);
+        if (elect_one()) {
+          const uint64_t bhi = adesc + bhi_off, blo = adesc + blo_off;
+          for (int k = 0; k < ksteps; ++k) {
+            // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (>>4) address field
+            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), idesc, (uint32_t)(kb | k));
+            if (two_mma) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc, 1u);
+          }
+          if (last_in_group) {
+            // frees the smem stage once these MMAs have read it -- in every CTA of the cluster, whose multicasts land here
+            if (dbg & 16) mbar_arrive(empty_bar(stage));  // timing experiment only (needs debug & 4)
+            else if (kCluster) umma_commit_mcast(empty_bar(stage), cmask); else umma_commit(empty_bar(stage));
+            if (kb == kb_per_tile - 1) {  // accumulator complete -> epilogue
+              if (dbg & 32) mbar_arrive(tfull_bar(as)); else umma_commit(tfull_bar(as));
             }
           }
-          first = 1u;
-          adesc += (uint64_t)(p.kb_bytes >> 4);
-          if (++chunk == p.n_chunks) chunk = 0;
         }
-        if (elect_one()) {
-          // frees the smem stage once these MMAs have read it -- in every CTA of the cluster, whose multicasts land here
-          if (p.debug & 16) mbar_arrive(empty_bar(stage));  // timing experiment only (needs debug & 4)
-          else if (p.cs > 1) umma_commit_mcast(empty_bar(stage), cmask); else umma_commit(empty_bar(stage));
-          if (kb0 + g >= kb_per_tile) {  // accumulator complete -> epilogue
-            if (p.debug & 32) mbar_arrive(tfull_bar(as)); else umma_commit(tfull_bar(as));
+        adesc += kb_desc_step;
+        if (last_in_group) {
+          jg = 0;
+          if (++stage == n_stages) {
+            stage = 0;
+            phase ^= 1u;
           }
-        }
-        __syncwarp();
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1u;
+          adesc = make_smem_desc(smem_base + (uint32_t)stage * stage_bytes, dhi);
+        } else {
+          ++jg;
         }
       }
       if (++as == 2) {
@@ -425,17 +440,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint32_t box_it = 0;
     for (int st = cluster_id; st < num_super; st += num_clusters) {
       const int m_group = st / p.n_ntiles, n_tile = st - m_group * p.n_ntiles;
-      const long long m0 = (long long)(m_group * p.cs + crank) * kBlockM;
+      const long long m0 = (long long)(m_group * pcs + crank) * kBlockM;
       const int co0 = n_tile * p.nt;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccumCols);
-      if (p.debug & 8) {
+      if (dbg & 8) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
       }
-      for (int c0 = 0; c0 < ((p.debug & 8) ? 0 : p.nt); c0 += W, ++box_it) {
+      for (int c0 = 0; c0 < ((dbg & 8) ? 0 : p.nt); c0 += W, ++box_it) {
         const uint32_t buf = epi_base + (box_it & 1u) * kEpiBufBytes;
         float f[W];
         {
@@ -528,7 +543,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (p.cs > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or signal its barriers
+  if (kCluster) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or signal its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -561,6 +576,7 @@ int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPl
   int rc = load_driver_entry_points(ctx);
   if (rc) return rc;
   if (L.cout > kMaxCout) return fail(ctx, TISE_ERR_INVALID, "umma conv: unsupported cout %d", L.cout);
+  if (L.R * L.S * (L.cin_pad / L.kc) > kMaxKb) return fail(ctx, TISE_ERR_INVALID, "umma conv: too many K blocks");
   if (a.in_stride % 8 || ((uintptr_t)a.in & 15))
     return fail(ctx, TISE_ERR_INVALID, "umma conv: input view is not 16-byte aligned");
   if (a.n_segs < 1 || a.n_segs > kMaxSegs) return fail(ctx, TISE_ERR_INVALID, "umma conv: %d segments", a.n_segs);
@@ -667,7 +683,7 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   // cluster size: with two passes every CTA of a 4-cluster loads nt / 2 weight rows (half of hi+lo) per K block
   static int cs_env = -1;
   if (cs_env < 0) cs_env = getenv("TISE_UMMA_CLUSTER") ? atoi(getenv("TISE_UMMA_CLUSTER")) : 0;
-  int cs = passes == 2 ? 4 : 2;
+  int cs = 1;  // clusters (2, 4) are available through TISE_UMMA_CLUSTER; measured slower so far (profiles/)
   if (cs_env == 1 || cs_env == 2 || cs_env == 4) cs = cs_env;
   if (passes == 1 && cs == 4) cs = 2;  // slice rows must stay a multiple of 8 (one swizzle atom)
   while (cs > 1 && m_tiles < cs) cs >>= 1;
@@ -681,11 +697,15 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   static int configured_smem = 0;
   const int smem_limit = ctx->smem_optin > 0 ? ctx->smem_optin : 232448;
   if (configured_smem != smem_limit) {
-    TISE_CUDA(ctx, cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
-    TISE_CUDA(ctx, cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
+    const void* kernels[8] = {(const void*)conv_umma_kernel<false, false, false>, (const void*)conv_umma_kernel<true, false, false>,
+                              (const void*)conv_umma_kernel<false, true, false>,  (const void*)conv_umma_kernel<true, true, false>,
+                              (const void*)conv_umma_kernel<false, false, true>,  (const void*)conv_umma_kernel<true, false, true>,
+                              (const void*)conv_umma_kernel<false, true, true>,   (const void*)conv_umma_kernel<true, true, true>};
+    for (int i = 0; i < 8; ++i)
+      TISE_CUDA(ctx, cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
     configured_smem = smem_limit;
   }
-  const int reserve = 1024 /*alignment*/ + 2 * kEpiBufBytes + 2 * kMaxCout * 4 + 8 * (2 * kMaxStages + 4) + 16;
+  const int reserve = 1024 /*alignment*/ + 2 * kEpiBufBytes + 2 * kMaxCout * 4 + 8 * (2 * kMaxStages + 4) + 16 + 16 * kMaxKb;
   const int budget = smem_limit - reserve;
   // The TMA -> MMA -> tcgen05.commit -> TMA round trip of a stage is ~2000 cycles (measured), so what matters is
   // the amount of work in flight: fill the budget with up to kMaxStages stages of `group` K blocks each.
@@ -719,7 +739,7 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   static int max_clusters[5] = {0, 0, 0, 0, 0};
   if (!max_clusters[cs]) {
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, conv_umma_kernel<false>, &cfg) != cudaSuccess || nc < 1) nc = ctx->num_sms / cs;
+    if (cudaOccupancyMaxActiveClusters(&nc, conv_umma_kernel<false, true, false>, &cfg) != cudaSuccess || nc < 1) nc = ctx->num_sms / cs;
     max_clusters[cs] = nc;
   }
   int clusters = max_clusters[cs];
@@ -733,8 +753,21 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
             a.h, a.w, L.cin, L.cout, L.R, L.S, p.nt, p.kc, p.wide, p.group, p.stages, p.stage_bytes, cs, clusters * cs,
             p.num_tiles);
   const CUtensorMap& tm_bs = plan.tm_bs;
-  cudaError_t le = a.out_f32 ? cudaLaunchKernelEx(&cfg, conv_umma_kernel<true>, plan.tm_a, plan.tm_b, plan.tm_b2, tm_bs, p)
-                             : cudaLaunchKernelEx(&cfg, conv_umma_kernel<false>, plan.tm_a, plan.tm_b, plan.tm_b2, tm_bs, p);
+  cudaError_t le;
+#define TISE_LAUNCH_UMMA(F32, CL, DBG) \
+  le = cudaLaunchKernelEx(&cfg, conv_umma_kernel<F32, CL, DBG>, plan.tm_a, plan.tm_b, plan.tm_b2, tm_bs, p)
+  const int variant = (a.out_f32 ? 1 : 0) | (cs > 1 ? 2 : 0) | (p.debug ? 4 : 0);
+  switch (variant) {
+    case 0: TISE_LAUNCH_UMMA(false, false, false); break;
+    case 1: TISE_LAUNCH_UMMA(true, false, false); break;
+    case 2: TISE_LAUNCH_UMMA(false, true, false); break;
+    case 3: TISE_LAUNCH_UMMA(true, true, false); break;
+    case 4: TISE_LAUNCH_UMMA(false, false, true); break;
+    case 5: TISE_LAUNCH_UMMA(true, false, true); break;
+    case 6: TISE_LAUNCH_UMMA(false, true, true); break;
+    default: TISE_LAUNCH_UMMA(true, true, true); break;
+  }
+#undef TISE_LAUNCH_UMMA
   if (le != cudaSuccess) return fail(ctx, TISE_ERR_CUDA, "conv_umma_kernel launch failed: %s", cudaGetErrorString(le));
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;
