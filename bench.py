@@ -256,6 +256,7 @@ def main():
     eng.profile(True)
     for s in range(2):
         job2.step(batch_of(s))
+    torch.cuda.synchronize()
     prof = eng.profile_read()
     eng.profile(False)
     conv_ms, conv_launches, conv_flops = prof["conv"]

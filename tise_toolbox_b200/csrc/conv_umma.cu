@@ -707,12 +707,13 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   }
   const int reserve = 1024 /*alignment*/ + 2 * kEpiBufBytes + 2 * kMaxCout * 4 + 8 * (2 * kMaxStages + 4) + 16 + 16 * kMaxKb;
   const int budget = smem_limit - reserve;
-  // The TMA -> MMA -> tcgen05.commit -> TMA round trip of a stage is ~2000 cycles (measured), so what matters is
-  // the amount of work in flight: fill the budget with up to kMaxStages stages of `group` K blocks each.
+  // K blocks per pipeline stage.  The producer and MMA warps are single instruction streams (~10 cycles per dependent
+  // instruction, measured), so a K block with little tensor work (small nt) cannot hide its own barrier wait /
+  // expect_tx / commit: two K blocks share a stage when one holds < ~600 tensor cycles and 3 stages still fit.
   const int kb_per_tile = L.R * L.S * p.n_chunks;
-  int group = (budget / p.kb_bytes + kMaxStages - 1) / kMaxStages;
+  const int kb_cycles = p.ksteps * passes * p.nt / 2;  // tcgen05 floor: M=128 x N x K=16 takes N / 2 cycles
+  int group = (kb_cycles < 600 && 2 * p.kb_bytes * 3 <= budget) ? 2 : 1;
   if (group > kb_per_tile) group = kb_per_tile;
-  if (group < 1) group = 1;
   const char* genv = getenv("TISE_UMMA_GROUP");
   if (genv && atoi(genv) > 0 && atoi(genv) * p.kb_bytes * 2 <= budget) group = atoi(genv) < kb_per_tile ? atoi(genv) : kb_per_tile;
   p.group = group;

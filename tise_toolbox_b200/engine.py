@@ -130,12 +130,12 @@ class Engine:
         self._check(self.lib.tise_profile_enable(self.ctx, int(bool(on))))
 
     def profile_read(self):
-        """{kind: (ms, launches, algorithmic flops)} for kinds stem / conv / maxpool / avgpool / gap."""
+        """{kind: (ms, launches, algorithmic flops)} for kinds stem / conv / maxpool / avgpool / gap / avgpool_bn."""
         ms = (C.c_double * 8)()
         ln = (C.c_longlong * 8)()
         fl = (C.c_double * 8)()
         self._check(self.lib.tise_profile_read(self.ctx, ms, ln, fl))
-        names = ["stem", "conv", "maxpool", "avgpool", "gap"]
+        names = ["stem", "conv", "maxpool", "avgpool", "gap", "avgpool_bn"]
         return {n: (ms[i], int(ln[i]), fl[i]) for i, n in enumerate(names)}
 
     # ------------------------------------------------------------------ buffers
