@@ -55,7 +55,10 @@ def test_get_activations_matches_reference_golden(model, golden):
           for s in sets]
     v = fid_score.calculate_frechet_distance(st[0][0], st[0][1], st[1][0], st[1][1])
     assert isinstance(v, np.float64)
-    assert abs(v - golden["fid_2x16"]["value"]) <= 1e-3 * golden["fid_2x16"]["value"]
+    # same statistics through the oracle's scipy sqrtm: separates feature error from the Frechet kernel
+    v_scipy = float(restate.calculate_frechet_distance(st[0][0], st[0][1], st[1][0], st[1][1]))
+    g = golden["fid_2x16"]["value"]
+    assert abs(v - g) <= 1e-3 * g, "FID %.6f (scipy on the same stats %.6f) vs reference %.6f" % (v, v_scipy, g)
 
 
 def _d192():

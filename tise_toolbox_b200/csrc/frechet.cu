@@ -19,7 +19,7 @@
 namespace tise {
 
 // scalars[] slots
-enum { FR_DIFF2 = 0, FR_TR1, FR_TR2, FR_TAU, FR_TRSQRT, FR_NEGMAX, FR_NSLOTS = 16 };
+enum { FR_DIFF2 = 0, FR_TR1, FR_TR2, FR_TAU, FR_TRSQRT, FR_NEGMAX, FR_BADPIV, FR_NSLOTS = 16 };
 
 // ---------------------------------------------------------------------------- small helpers
 __device__ __forceinline__ double warp_sum(double v) {
@@ -63,17 +63,18 @@ __global__ void fr_scalars_kernel(const double* mu1, const double* s1, const dou
     scal[FR_TR2] = c;
     scal[FR_TRSQRT] = 0.0;
     scal[FR_NEGMAX] = 0.0;
+    scal[FR_BADPIV] = 0.0;
   }
 }
 
-// dst = src + (add + rel * max(tr/d, 0)) I
+// dst = src + (add + rel * max(tr, 0)) I
 __global__ void fr_copy_shift_kernel(const double* src, double* dst, int d, double add, double rel, const double* scal,
                                      int tr_slot) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)d * d) return;
   const int r = (int)(i / d), c = (int)(i % d);
   double v = src[i];
-  if (r == c) v += add + rel * fmax(scal[tr_slot] / d, 0.0);
+  if (r == c) v += add + rel * fmax(scal[tr_slot], 0.0);
   dst[i] = v;
 }
 
@@ -81,15 +82,22 @@ __global__ void fr_copy_shift_kernel(const double* src, double* dst, int d, doub
 constexpr int CNB = 32;
 
 // factor the nb x nb diagonal block at (k, k) in shared memory; non-positive pivots are clamped
-__global__ void __launch_bounds__(CNB* CNB) chol_diag_kernel(double* A, int d, int k, int nb, double floor_piv) {
+__global__ void __launch_bounds__(CNB* CNB) chol_diag_kernel(double* A, int d, int k, int nb, double rel,
+                                                             double* scal) {
   __shared__ double s[CNB][CNB + 1];
   const int i = threadIdx.y, j = threadIdx.x;
   if (i < nb && j < nb) s[i][j] = A[(size_t)(k + i) * d + k + j];
   __syncthreads();
   for (int c = 0; c < nb; ++c) {
     if (i == c && j == c) {
+      // the jitter delta = rel * tr(s1) should dominate the rounding noise of the Schur complement; a pivot below
+      // delta / 4 means it did not: clamp (keeps everything finite) and report, the caller retries with 100 x delta
+      const double delta = rel * fmax(scal[FR_TR1], 1e-300);
       double p = s[c][c];
-      if (!(p > floor_piv)) p = floor_piv;
+      if (!(p > 0.25 * delta)) {
+        p = 0.25 * delta;
+        scal[FR_BADPIV] = 1.0;
+      }
       s[c][c] = sqrt(p);
     }
     __syncthreads();
@@ -415,7 +423,7 @@ static FrWs fr_layout(int d) {
 }
 
 static int frechet_once(tise_ctx* ctx, const double* mu1, const double* s1, const double* mu2, const double* s2, int d,
-                        double eps_add, char* ws, cudaStream_t st, double* h_scal) {
+                        double eps_add, double delta_rel, char* ws, cudaStream_t st, double* h_scal) {
   const FrWs w = fr_layout(d);
   double* L = (double*)(ws + w.off_L);
   double* S2 = (double*)(ws + w.off_S2);
@@ -430,7 +438,7 @@ static int frechet_once(tise_ctx* ctx, const double* mu1, const double* s1, cons
 
   fr_scalars_kernel<<<1, 1024, 0, st>>>(mu1, s1, mu2, s2, d, scal);
   TISE_LAUNCH_CHECK(ctx);
-  fr_copy_shift_kernel<<<nel_blocks, 256, 0, st>>>(s1, L, d, eps_add, 1e-11, scal, FR_TR1);
+  fr_copy_shift_kernel<<<nel_blocks, 256, 0, st>>>(s1, L, d, eps_add, delta_rel, scal, FR_TR1);
   TISE_LAUNCH_CHECK(ctx);
   fr_copy_shift_kernel<<<nel_blocks, 256, 0, st>>>(s2, S2, d, eps_add, 0.0, scal, FR_TR2);
   TISE_LAUNCH_CHECK(ctx);
@@ -438,7 +446,7 @@ static int frechet_once(tise_ctx* ctx, const double* mu1, const double* s1, cons
   // 1. Cholesky
   for (int k = 0; k < d; k += CNB) {
     const int nb = d - k < CNB ? d - k : CNB;
-    chol_diag_kernel<<<1, dim3(CNB, CNB), 0, st>>>(L, d, k, nb, 1e-300);
+    chol_diag_kernel<<<1, dim3(CNB, CNB), 0, st>>>(L, d, k, nb, delta_rel, scal);
     TISE_LAUNCH_CHECK(ctx);
     const int rest = d - k - nb;
     if (rest > 0) {
@@ -508,15 +516,21 @@ extern "C" int tise_frechet(tise_ctx* ctx, const double* d_mu1, const double* d_
   }
   double scal[FR_NSLOTS];
   int flags = 0;
-  int rc = frechet_once(ctx, d_mu1, d_sigma1, d_mu2, d_sigma2, d, 0.0, (char*)d_ws, st, scal);
-  if (rc) return rc;
-  double fid = scal[FR_DIFF2] + scal[FR_TR1] + scal[FR_TR2] - 2.0 * scal[FR_TRSQRT];
-  if (!isfinite(fid)) {
+  double fid = 0.0;
+  // jitter delta = delta_rel * tr(s1): start tiny (bias of FID(X, X) ~ d * delta) and grow only if a Cholesky pivot
+  // drowned in rounding noise (heavily rank-deficient s1, e.g. 16 images in 2048 dimensions)
+  double eps_add = 0.0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    for (double delta_rel = 1e-14; delta_rel <= 1e-7; delta_rel *= 100.0) {
+      int rc = frechet_once(ctx, d_mu1, d_sigma1, d_mu2, d_sigma2, d, eps_add, delta_rel, (char*)d_ws, st, scal);
+      if (rc) return rc;
+      if (scal[FR_BADPIV] == 0.0) break;
+    }
+    fid = scal[FR_DIFF2] + scal[FR_TR1] + scal[FR_TR2] - 2.0 * scal[FR_TRSQRT];
+    if (isfinite(fid)) break;
     // fid_score.py:156-160: singular product -> add eps to the diagonal of both covariances and redo
     flags |= 1;
-    rc = frechet_once(ctx, d_mu1, d_sigma1, d_mu2, d_sigma2, d, eps, (char*)d_ws, st, scal);
-    if (rc) return rc;
-    fid = scal[FR_DIFF2] + scal[FR_TR1] + scal[FR_TR2] - 2.0 * scal[FR_TRSQRT];
+    eps_add = eps;
   }
   // fid_score.py:163-166: an imaginary part above 1e-3 is an error; here that is sqrt(-lambda_min) of M
   if (scal[FR_NEGMAX] > 0.0 && sqrt(scal[FR_NEGMAX]) > 1e-3) flags |= 2;
