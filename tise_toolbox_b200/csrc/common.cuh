@@ -127,13 +127,33 @@ int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPl
 int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const UmmaPlan& plan, int passes,
                      cudaStream_t st);
 
+// conv_flat.cu: stride-1 convolutions with 32 / 64 input channels evaluated on the flattened (padded) input grid
+struct FlatArgs {
+  const __half* in = nullptr;  // [n][hp][wp][cin], the consumer's padding already materialised as zeros
+  __half* out = nullptr;       // [n][hp][wp][cout] on the same grid
+  int n = 0, hp = 0, wp = 0;   // physical grid
+  int ho = 0, wo = 0;          // valid outputs (top-left aligned): y < ho && x < wo; the rest is written as 0
+  int out_shift = 0;           // output position = input position + out_shift (e.g. wp + 1 to centre for a pad-1 consumer)
+  int relu = 1;
+};
+struct FlatPlan {
+  alignas(64) CUtensorMap tm_a;
+  alignas(64) CUtensorMap tm_w;
+  bool valid = false;
+};
+bool conv_flat_supported(const ConvLayer& L);
+int build_flat_plan(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, FlatPlan* plan);
+int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const FlatPlan& plan, cudaStream_t st);
+
 // stem.cu : Conv2d_1a_3x3 (3->32, 3x3, stride 2) fused with the uint8 LUT / float input
 int launch_stem(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, const float* d_w /*[27][32]*/,
                 const float* d_scale, const float* d_shift, __half* d_out, cudaStream_t st);
 
 // pool.cu
+// in_rows / in_pitch: physical rows per image and pixels per row of the input (>= h, w: flat-conv outputs keep the
+// padded grid); 0 = dense
 int launch_maxpool3s2(tise_ctx* ctx, const __half* in, int n, int h, int w, int c, int in_stride, __half* out,
-                      int out_stride, cudaStream_t st);
+                      int out_stride, cudaStream_t st, int in_rows = 0, int in_pitch = 0);
 int launch_avgpool3s1p1(tise_ctx* ctx, const __half* in, int n, int h, int w, int c, int in_stride, __half* out,
                         int out_stride, cudaStream_t st);
 // avg_pool2d(3, 1, 1) of a raw (pre-BN) fp16 tensor followed by scale/shift + ReLU into a channel slice

@@ -1,0 +1,359 @@
+// "Flat" tcgen05 convolution for stride-1 layers with few channels (Conv2d_2a_3x3, Conv2d_2b_3x3 of the stem).
+//
+// conv_umma_kernel feeds the tensor cores one (filter tap, 64-channel chunk) at a time through TMA im2col loads;
+// with 32 input channels and 32/64 output channels a K block holds ~100 tensor cycles of work but costs ~500
+// cycles of producer / MMA-issue instructions (single instruction streams), so those layers ran at 10-18 %
+// tensor-pipe utilisation (profiles/).  Here the convolution is evaluated on the *flattened, padded input grid*:
+//
+//     out[v] = sum_{r,s} in[v + r * Wp + s] . W[r,s]        v = (n * Hp + y) * Wp + x
+//
+// so every filter tap is the SAME run of pixels shifted by r * Wp + s rows.  Per 128-pixel tile the producer
+// issues R plain 2D TMA loads (one run of 128 + S - 1 pixels per filter row) into ONE pipeline stage, the MMA
+// warp issues all R * S * (C / 16) MMAs of the tile against shifted views of those runs (the shared-memory
+// descriptor's start address moves by whole pixel rows), and the weights of all taps stay resident in shared
+// memory for the lifetime of the CTA.  Outputs that fall outside the valid region (x >= Wo or y >= Ho: the
+// wrap-around columns / rows of the padded grid) are written as zeros, so the output tensor is itself a correctly
+// zero-padded input grid for the next flat layer (written at a constant flat offset `out_shift`).
+//
+// Numerics are those of conv_umma_kernel: fp16 activations x (hi | lo) fp16 weights as one N = 2 * cout MMA,
+// fp32 TMEM accumulation, hi and lo halves summed in the epilogue, folded-BN scale/shift + ReLU in fp32.
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "umma_ptx.cuh"
+
+namespace tise {
+
+constexpr int kFlatThreads = 192;
+constexpr int kFlatMaxStages = 8;
+constexpr int kFlatEpiBuf = 128 * 64;
+
+struct FlatParams {
+  const float* scale;
+  const float* shift;
+  __half* out;
+  long long total;      // virtual output positions: n * Hp * Wp
+  long long out_total;  // positions of the output tensor (stores beyond are dropped)
+  int out_stride;       // elements per output pixel (= cout)
+  int wp, hpwp;         // grid pitch and positions per image
+  int ho, wo;           // valid outputs: y < ho && x < wo
+  int out_shift;        // output position = v + out_shift
+  int R, S, ksteps;     // filter taps, K = 16 steps per tap (cin / 16)
+  int row_bytes;        // cin * 2: 64 (SWIZZLE_64B) or 128 (SWIZZLE_128B)
+  int swz_type, sbo;
+  int nt;               // cout (<= 128); MMA N = 2 * nt
+  int run_rows, run_bytes;  // pixels per run (128 + S - 1) and its shared-memory footprint
+  int wtile_bytes;          // one tap's weights: 2 * nt rows
+  int stages, stage_bytes, num_tiles, relu;
+  int base_offset_mode;  // 0: descriptor base_offset field = 0, 1: (start address >> 7) & 7
+};
+
+__global__ void __launch_bounds__(kFlatThreads, 1)
+conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const FlatParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int taps = p.R * p.S;
+  // layout: [weights taps x wtile][stages x R runs][2 staged output boxes][scale | shift][barriers][tmem slot]
+  const uint32_t w_base = smem_base;
+  const uint32_t st_base = (w_base + (uint32_t)(taps * p.wtile_bytes) + 1023u) & ~1023u;
+  const uint32_t epi_base = st_base + (uint32_t)p.stages * (uint32_t)p.stage_bytes;
+  const uint32_t ss_base = epi_base + 2u * kFlatEpiBuf;
+  const uint32_t bar_base = ss_base + 2u * 128u * 4u;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(kFlatMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kFlatMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kFlatMaxStages + 2 + s); };
+  const uint32_t wfull_bar = bar_base + 8u * (2 * kFlatMaxStages + 4);
+  const uint32_t tmem_slot = wfull_bar + 8u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    mbar_init(wfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    const int R = p.R, wp = p.wp, n_stages = p.stages;
+    const uint32_t run_bytes = (uint32_t)p.run_bytes, stage_bytes = (uint32_t)p.stage_bytes;
+    const uint32_t tx = (uint32_t)(p.R * p.run_rows * p.row_bytes);
+    if (elect_one()) {  // all weights, once
+      mbar_expect_tx(wfull_bar, (uint32_t)(taps * p.wtile_bytes));
+      for (int t = 0; t < taps; ++t) tma_load_2d(&tm_w, w_base + (uint32_t)(t * p.wtile_bytes), wfull_bar, t * (p.ksteps * 16), 0);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const long long v0 = (long long)tile * kBlockM;
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t sa = st_base + (uint32_t)stage * stage_bytes;
+      const uint32_t fb = full_bar(stage);
+      if (elect_one()) {
+        mbar_expect_tx(fb, tx);
+        for (int r = 0; r < R; ++r) tma_load_2d(&tm_a, sa + (uint32_t)r * run_bytes, fb, 0, (int)(v0 + (long long)r * wp));
+      }
+      if (++stage == n_stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    const uint32_t idesc = make_instr_desc(2 * p.nt);
+    const uint64_t dhi = smem_desc_hi(p.swz_type, p.sbo);
+    const int R = p.R, S = p.S, ksteps = p.ksteps, n_stages = p.stages, bom = p.base_offset_mode;
+    const uint32_t run_bytes = (uint32_t)p.run_bytes, stage_bytes = (uint32_t)p.stage_bytes, row_bytes = (uint32_t)p.row_bytes,
+                   wtile_bytes = (uint32_t)p.wtile_bytes;
+    mbar_wait(wfull_bar, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      mbar_wait(full_bar(stage), phase);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+      const uint32_t sa = st_base + (uint32_t)stage * stage_bytes;
+      if (elect_one()) {
+        uint32_t first = 0;
+        uint32_t wt = w_base;
+        for (int r = 0; r < R; ++r) {
+          for (int s = 0; s < S; ++s) {
+            // the tap's A operand is the run of filter row r, shifted by s pixel rows
+            const uint32_t astart = sa + (uint32_t)r * run_bytes + (uint32_t)s * row_bytes;
+            uint64_t adesc = make_smem_desc(astart, dhi);
+            if (bom) adesc |= (uint64_t)((astart >> 7) & 7u) << 49;
+            const uint64_t bdesc = make_smem_desc(wt, dhi);
+            for (int k = 0; k < ksteps; ++k) {
+              umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first);
+              first = 1u;
+            }
+            wt += wtile_bytes;
+          }
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(as));
+      }
+      __syncwarp();
+      if (++stage == n_stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int etid = threadIdx.x - 64;
+    float* s_scale = reinterpret_cast<float*>(smem_raw + (ss_base - smem_u32(smem_raw)));
+    float* s_shift = s_scale + 128;
+    for (int c = etid; c < p.nt; c += 128) {
+      s_scale[c] = __ldg(p.scale + c);
+      s_shift[c] = __ldg(p.shift + c);
+    }
+    epi_bar(2);
+    const uint32_t wr_off = (uint32_t)row * 64u;
+    const uint32_t wr_swz = (uint32_t)((row >> 1) & 3);
+    const int st_chunk = etid & 3, st_row0 = etid >> 2;
+    const int nt = p.nt, wp = p.wp, hpwp = p.hpwp, ho = p.ho, wo = p.wo;
+    const bool relu = p.relu != 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    uint32_t box_it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const long long v0 = (long long)tile * kBlockM;
+      // is this thread's output position a real output or a wrap-around cell of the padded grid (written as 0)?
+      const long long v = v0 + row;
+      const int rem = (int)(v % hpwp);
+      const int y = rem / wp, x = rem - y * wp;
+      const bool valid = v < p.total && y < ho && x < wo;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 256);
+      for (int c0 = 0; c0 < nt; c0 += 32, ++box_it) {
+        const uint32_t buf = epi_base + (box_it & 1u) * kFlatEpiBuf;
+        float f[32];
+        {
+          uint32_t a[32], b[32];
+          tmem_ld32(taddr + (uint32_t)c0, a);
+          tmem_ld32(taddr + (uint32_t)(nt + c0), b);  // W_lo products
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
+        }
+        if (c0 + 32 >= nt) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * q);
+          const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + 4 * q);
+          float* yv = f + 4 * q;
+          yv[0] = fmaf(yv[0], sc.x, sh.x);
+          yv[1] = fmaf(yv[1], sc.y, sh.y);
+          yv[2] = fmaf(yv[2], sc.z, sh.z);
+          yv[3] = fmaf(yv[3], sc.w, sh.w);
+          if (relu) {
+            yv[0] = fmaxf(yv[0], 0.f);
+            yv[1] = fmaxf(yv[1], 0.f);
+            yv[2] = fmaxf(yv[2], 0.f);
+            yv[3] = fmaxf(yv[3], 0.f);
+          }
+          if (!valid) yv[0] = yv[1] = yv[2] = yv[3] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(buf + wr_off + (((uint32_t)j ^ wr_swz) << 4), pack_h2(f[8 * j], f[8 * j + 1]),
+                       pack_h2(f[8 * j + 2], f[8 * j + 3]), pack_h2(f[8 * j + 4], f[8 * j + 5]),
+                       pack_h2(f[8 * j + 6], f[8 * j + 7]));
+        epi_bar(1);
+        const int ccol = c0 + st_chunk * 8;
+        if (ccol < nt) {
+          char* obase = reinterpret_cast<char*>(p.out) + (size_t)ccol * 2;
+          const size_t pitch = (size_t)p.out_stride * 2;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = st_row0 + 32 * i;
+            const long long mo = v0 + r + p.out_shift;
+            if (mo < p.out_total && v0 + r < p.total) {
+              const uint4 val = ld_shared_v4(buf + (uint32_t)r * 64u + (((uint32_t)st_chunk ^ (uint32_t)((r >> 1) & 3)) << 4));
+              *reinterpret_cast<uint4*>(obase + (size_t)mo * pitch) = val;
+            }
+          }
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+static PFN_cuTensorMapEncodeTiled_v12000 g_flat_encode = nullptr;
+
+bool conv_flat_supported(const ConvLayer& L) {
+  return L.stride == 1 && (L.cin == 32 || L.cin == 64) && L.cout <= 128 && L.cout % 32 == 0 && L.kc == L.cin &&
+         L.nt == L.cout && L.S <= 7 && L.R <= 7;
+}
+
+int build_flat_plan(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, FlatPlan* plan) {
+  if (!conv_flat_supported(L)) return fail(ctx, TISE_ERR_INVALID, "flat conv: unsupported layer");
+  if (!g_flat_encode) {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    TISE_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(ctx, TISE_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    g_flat_encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  }
+  const CUtensorMapSwizzle swz = L.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const long long total = (long long)a.n * a.hp * a.wp;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)L.cin, (cuuint64_t)total};
+    cuuint64_t strides[1] = {(cuuint64_t)L.cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)L.kc, (cuuint32_t)(kBlockM + L.S - 1)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_flat_encode(&plan->tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)a.in, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, TISE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for flat input", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)L.ktot, (cuuint64_t)2 * L.cout};
+    cuuint64_t strides[1] = {(cuuint64_t)L.ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)L.kc, (cuuint32_t)(2 * L.nt)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_flat_encode(&plan->tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)L.d_w, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, TISE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for flat weights", (int)r);
+  }
+  plan->valid = true;
+  return TISE_OK;
+}
+
+int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const FlatPlan& plan, cudaStream_t st) {
+  if (!plan.valid) return fail(ctx, TISE_ERR_STATE, "flat conv: plan not built");
+  FlatParams p;
+  p.scale = L.d_scale;
+  p.shift = L.d_shift;
+  p.out = a.out;
+  p.total = (long long)a.n * a.hp * a.wp;
+  p.out_total = p.total;
+  p.out_stride = L.cout;
+  p.wp = a.wp;
+  p.hpwp = a.hp * a.wp;
+  p.ho = a.ho;
+  p.wo = a.wo;
+  p.out_shift = a.out_shift;
+  p.R = L.R;
+  p.S = L.S;
+  p.ksteps = L.cin / 16;
+  p.row_bytes = L.cin * 2;
+  p.swz_type = L.kc == 64 ? 2 : 4;
+  p.sbo = 8 * p.row_bytes;
+  p.nt = L.cout;
+  p.run_rows = kBlockM + L.S - 1;
+  p.run_bytes = (int)align_up((size_t)p.run_rows * p.row_bytes, 1024);
+  p.wtile_bytes = 2 * L.nt * p.row_bytes;
+  p.stage_bytes = L.R * p.run_bytes;
+  p.num_tiles = cdiv(p.total, kBlockM);
+  p.relu = a.relu;
+  static int bom = -1;
+  if (bom < 0) bom = getenv("TISE_FLAT_BASE_OFFSET") ? atoi(getenv("TISE_FLAT_BASE_OFFSET")) : 1;
+  p.base_offset_mode = bom;
+
+  static int configured = 0;
+  const int smem_limit = ctx->smem_optin > 0 ? ctx->smem_optin : 232448;
+  if (configured != smem_limit) {
+    TISE_CUDA(ctx, cudaFuncSetAttribute(conv_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
+    configured = smem_limit;
+  }
+  const int fixed = 1024 + (int)align_up((size_t)L.R * L.S * p.wtile_bytes, 1024) + 2 * kFlatEpiBuf + 2 * 128 * 4 +
+                    8 * (2 * kFlatMaxStages + 6) + 16;
+  int stages = (smem_limit - fixed) / p.stage_bytes;
+  if (stages > kFlatMaxStages) stages = kFlatMaxStages;
+  if (stages < 2) return fail(ctx, TISE_ERR_INVALID, "flat conv: does not fit shared memory");
+  p.stages = stages;
+  const int grid = p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms;
+  conv_flat_kernel<<<grid, kFlatThreads, smem_limit, st>>>(plan.tm_a, plan.tm_w, p);
+  TISE_LAUNCH_CHECK(ctx);
+  return TISE_OK;
+}
+
+}  // namespace tise

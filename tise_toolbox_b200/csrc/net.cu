@@ -58,8 +58,8 @@ int conv_ntile_of(int cout) {
 }
 
 int pack_conv_layer(tise_ctx* ctx, ConvLayer* L, const float* w, const float* scale, const float* shift,
-                    std::vector<void*>* allocs) {
-  L->kc = conv_chunk_of(L->cin);
+                    std::vector<void*>* allocs, int force_kc) {
+  L->kc = force_kc ? force_kc : conv_chunk_of(L->cin);
   L->cin_pad = (L->cin + L->kc - 1) / L->kc * L->kc;
   L->ktot = L->R * L->S * L->cin_pad;
   L->nt = conv_ntile_of(L->cout);
@@ -137,6 +137,7 @@ struct Builder {
   Plan* plan;  // may be null (declare-only walk)
   int n;
   char* ws;
+  bool flat_stem = true;  // tcgen05 path; the SIMT cross-check path keeps dense 147 x 147 tensors
   std::vector<Buf> bufs;
   size_t per_image = 0;
   int rc = TISE_OK;
@@ -163,7 +164,7 @@ struct Builder {
 
   // Creates (once) the packed layer holding the members' output channels back to back.
   const ConvLayer* layer(const std::string& key, const std::vector<Member>& ms, int cin, int R, int S, int stride, int ph,
-                         int pw) {
+                         int pw, int force_kc = 0) {
     auto it = net->convs.find(key);
     if (it != net->convs.end()) return &it->second;
     const int taps = R * S;
@@ -203,7 +204,7 @@ struct Builder {
     L.stride = stride;
     L.pad_h = ph;
     L.pad_w = pw;
-    if ((rc = pack_conv_layer(ctx, &L, w.data(), scale.data(), shift.data(), &net->device_allocs))) return nullptr;
+    if ((rc = pack_conv_layer(ctx, &L, w.data(), scale.data(), shift.data(), &net->device_allocs, force_kc))) return nullptr;
     return &(net->convs[key] = L);
   }
 
@@ -243,7 +244,30 @@ struct Builder {
   void conv(const std::string& name, View in, View out, int R = 1, int S = 1, int stride = 1, int ph = 0, int pw = 0) {
     conv_multi(name, in, {Member{name, out, false}}, R, S, stride, ph, pw);
   }
-  void pool(StepKind kind, View in, View out) {
+  // flat convolution `name` from buffer `in` to buffer `out` (same physical grid); valid outputs ho x wo
+  void flat(const std::string& name, int in, int out, int ho, int wo, int out_shift) {
+    if (rc || !plan) return;
+    const Buf& bi = bufs[in];
+    Step z;  // the cells in front of the first shifted output are never written: keep them zero
+    z.kind = STEP_ZERO;
+    z.out = ptr(all(out));
+    z.zero_bytes = (size_t)out_shift * bufs[out].c * 2;
+    if (z.zero_bytes) plan->steps.push_back(z);
+    Step s;
+    s.kind = STEP_FLATCONV;
+    s.layer = &net->convs[name];
+    s.flat.in = (const __half*)ptr(all(in));
+    s.flat.out = (__half*)ptr(all(out));
+    s.flat.n = n;
+    s.flat.hp = bi.h;
+    s.flat.wp = bi.w;
+    s.flat.ho = ho;
+    s.flat.wo = wo;
+    s.flat.out_shift = out_shift;
+    s.flat.relu = 1;
+    plan->steps.push_back(s);
+  }
+  void pool(StepKind kind, View in, View out, int logical_h = 0, int logical_w = 0) {
     if (rc || !plan) return;
     const Buf& bi = bufs[in.buf];
     const Buf& bo = bufs[out.buf];
@@ -252,8 +276,10 @@ struct Builder {
     s.in = ptr(in);
     s.out = ptr(out);
     s.n = n;
-    s.h = bi.h;
-    s.w = bi.w;
+    s.h = logical_h ? logical_h : bi.h;
+    s.w = logical_w ? logical_w : bi.w;
+    s.in_rows = bi.h;
+    s.in_pitch = bi.w;
     s.c = in.c;
     s.in_stride = bi.c;
     s.out_stride = bo.c;
@@ -394,10 +420,23 @@ struct Builder {
       s.n = n;
       plan->steps.push_back(s);
     }
-    const int c2 = buf(147, 147, 32), c3 = buf(147, 147, 64), p1 = buf(73, 73, 64);
-    conv("Conv2d_2a_3x3", all(c1), all(c2), 3, 3, 1, 0, 0);
-    conv("Conv2d_2b_3x3", all(c2), all(c3), 3, 3, 1, 1, 1);
-    pool(STEP_MAXPOOL, all(c3), all(p1));
+    // Conv2d_2a / 2b have 32 input channels: packed with 32-channel K chunks and, on the tcgen05 path, evaluated by
+    // the flat kernel on the 149 x 149 grid (2a's output is written one row + one pixel further, which makes it the
+    // zero-padded input of the pad-1 convolution 2b; 2b's output keeps the 149-pixel pitch for the max pool)
+    layer("Conv2d_2a_3x3", {Member{"Conv2d_2a_3x3", View{0, 0, 32}, false}}, 32, 3, 3, 1, 0, 0, 32);
+    layer("Conv2d_2b_3x3", {Member{"Conv2d_2b_3x3", View{0, 0, 64}, false}}, 32, 3, 3, 1, 1, 1, 32);
+    const int p1 = buf(73, 73, 64);
+    if (flat_stem) {
+      const int c2 = buf(149, 149, 32), c3 = buf(149, 149, 64);
+      flat("Conv2d_2a_3x3", c1, c2, 147, 147, 149 + 1);
+      flat("Conv2d_2b_3x3", c2, c3, 147, 147, 0);
+      pool(STEP_MAXPOOL, all(c3), all(p1), 147, 147);
+    } else {
+      const int c2 = buf(147, 147, 32), c3 = buf(147, 147, 64);
+      conv("Conv2d_2a_3x3", all(c1), all(c2), 3, 3, 1, 0, 0);
+      conv("Conv2d_2b_3x3", all(c2), all(c3), 3, 3, 1, 1, 1);
+      pool(STEP_MAXPOOL, all(c3), all(p1));
+    }
     if (tap == TISE_TAP_64) return gap(all(p1));
     // block 1
     const int c4 = buf(73, 73, 80), c5 = buf(71, 71, 192), p2 = buf(35, 35, 192);
@@ -488,8 +527,11 @@ void net_free(tise_ctx* ctx) {
 
 static int get_plan(tise_ctx* ctx, void* ws, int n, int tap, Plan** out) {
   Net* net = ctx->net;
+  static int flat_env = -1;
+  if (flat_env < 0) flat_env = getenv("TISE_FLAT_STEM") ? atoi(getenv("TISE_FLAT_STEM")) : 1;
+  const bool flat_stem = ctx->conv_impl == TISE_CONV_UMMA && ctx->passes == 2 && flat_env != 0;
   for (auto& p : net->plans)
-    if (p->ws == ws && p->n == n && p->tap == tap) {
+    if (p->ws == ws && p->n == n && p->tap == tap && p->impl == (flat_stem ? 1 : 0)) {
       *out = p.get();
       return TISE_OK;
     }
@@ -497,7 +539,9 @@ static int get_plan(tise_ctx* ctx, void* ws, int n, int tap, Plan** out) {
   plan->ws = ws;
   plan->n = n;
   plan->tap = tap;
+  plan->impl = flat_stem ? 1 : 0;
   Builder b{ctx, net, plan.get(), n, (char*)ws};
+  b.flat_stem = flat_stem;
   b.walk(tap);
   if (b.rc) return b.rc;
   if (net->plans.size() >= 16) net->plans.erase(net->plans.begin());
@@ -523,9 +567,13 @@ int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, i
   int rc = get_plan(ctx, d_ws, n, tap, &plan);
   if (rc) return rc;
   for (Step& s : plan->steps) {
-    tise_ctx::ProfRec rec{(int)s.kind, nullptr, nullptr, 0.0, {0}};
+    tise_ctx::ProfRec rec{s.kind == STEP_FLATCONV ? (int)STEP_CONV : (int)s.kind, nullptr, nullptr, 0.0, {0}};
     if (ctx->profiling) {
-      if (s.kind == STEP_CONV)
+      if (s.kind == STEP_FLATCONV) {
+        snprintf(rec.tag, sizeof(rec.tag), "conv n%d %dx%d cin%d cout%d k%dx%d s1 flat", s.flat.n, s.flat.hp, s.flat.wp,
+                 s.layer->cin, s.layer->cout, s.layer->R, s.layer->S);
+        rec.flops = 2.0 * (double)s.flat.n * s.flat.ho * s.flat.wo * s.layer->cout * s.layer->R * s.layer->S * s.layer->cin;
+      } else if (s.kind == STEP_CONV)
         snprintf(rec.tag, sizeof(rec.tag), "conv n%d %dx%d cin%d cout%d k%dx%d s%d", s.conv.n, s.conv.h, s.conv.w,
                  s.layer->cin, s.layer->cout, s.layer->R, s.layer->S, s.layer->stride);
       else
@@ -551,8 +599,17 @@ int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, i
         break;
       case STEP_MAXPOOL:
         rc = launch_maxpool3s2(ctx, (const __half*)s.in, s.n, s.h, s.w, s.c, s.in_stride, (__half*)s.out, s.out_stride,
-                               st);
+                               st, s.in_rows, s.in_pitch);
         break;
+      case STEP_FLATCONV:
+        if (!s.flatplan.valid && (rc = build_flat_plan(ctx, *s.layer, s.flat, &s.flatplan))) break;
+        rc = launch_conv_flat(ctx, *s.layer, s.flat, s.flatplan, st);
+        break;
+      case STEP_ZERO: {
+        cudaError_t e = cudaMemsetAsync(s.out, 0, s.zero_bytes, st);
+        if (e != cudaSuccess) rc = fail(ctx, TISE_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+        break;
+      }
       case STEP_AVGPOOL:
         rc = launch_avgpool3s1p1(ctx, (const __half*)s.in, s.n, s.h, s.w, s.c, s.in_stride, (__half*)s.out,
                                  s.out_stride, st);

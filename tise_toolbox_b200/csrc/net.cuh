@@ -7,7 +7,7 @@
 
 namespace tise {
 
-enum StepKind { STEP_STEM = 0, STEP_CONV, STEP_MAXPOOL, STEP_AVGPOOL, STEP_GAP, STEP_AVGPOOL_BN };
+enum StepKind { STEP_STEM = 0, STEP_CONV, STEP_MAXPOOL, STEP_AVGPOOL, STEP_GAP, STEP_AVGPOOL_BN, STEP_FLATCONV, STEP_ZERO };
 
 struct Step {
   StepKind kind;
@@ -18,6 +18,10 @@ struct Step {
   const void* in = nullptr;
   void* out = nullptr;
   int n = 0, h = 0, w = 0, c = 0, in_stride = 0, out_stride = 0, in_f32 = 0, out_f32 = 0;
+  FlatArgs flat;    // STEP_FLATCONV
+  FlatPlan flatplan;
+  int in_rows = 0, in_pitch = 0;  // STEP_MAXPOOL: physical input grid if not dense
+  size_t zero_bytes = 0;          // STEP_ZERO: cudaMemsetAsync(out, 0, zero_bytes)
   const float* pool_scale = nullptr;  // STEP_AVGPOOL_BN
   const float* pool_shift = nullptr;
 };
@@ -26,6 +30,7 @@ struct Plan {
   void* ws = nullptr;
   int n = 0;
   int tap = 3;
+  int impl = 0;
   std::vector<Step> steps;
   float* feat_dst = nullptr;  // patched per call (GAP output)
 };
@@ -55,6 +60,6 @@ void net_free(tise_ctx* ctx);
 int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, int tap, float* d_feat, void* d_ws,
                 size_t ws_bytes, cudaStream_t st);
 int pack_conv_layer(tise_ctx* ctx, ConvLayer* L, const float* w /*[cout][cin][R][S]*/, const float* scale,
-                    const float* shift, std::vector<void*>* allocs);
+                    const float* shift, std::vector<void*>* allocs, int force_kc = 0);
 
 }  // namespace tise

@@ -7,6 +7,7 @@ namespace tise {
 
 __global__ void maxpool3s2_kernel(const __half* __restrict__ in, int n, int h, int w, int c8, int in_stride,
                                   __half* __restrict__ out, int out_stride, int ho, int wo) {
+  // h, w here are the PHYSICAL rows per image / pixels per row of the input
   const long long total = (long long)n * ho * wo * c8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -149,11 +150,11 @@ static int grid_for(long long total, int threads, int num_sms) {
 }
 
 int launch_maxpool3s2(tise_ctx* ctx, const __half* in, int n, int h, int w, int c, int in_stride, __half* out,
-                      int out_stride, cudaStream_t st) {
+                      int out_stride, cudaStream_t st, int in_rows, int in_pitch) {
   const int ho = (h - 3) / 2 + 1, wo = (w - 3) / 2 + 1;
   const long long total = (long long)n * ho * wo * (c / 8);
-  maxpool3s2_kernel<<<grid_for(total, 256, ctx->num_sms), 256, 0, st>>>(in, n, h, w, c / 8, in_stride, out,
-                                                                       out_stride, ho, wo);
+  maxpool3s2_kernel<<<grid_for(total, 256, ctx->num_sms), 256, 0, st>>>(in, n, in_rows ? in_rows : h, in_pitch ? in_pitch : w,
+                                                                       c / 8, in_stride, out, out_stride, ho, wo);
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;
 }
