@@ -46,9 +46,12 @@ struct FlatParams {
   int run_rows, run_bytes;  // pixels per run (128 + S - 1) and its shared-memory footprint
   int wtile_bytes;          // one tap's weights: 2 * nt rows
   int stages, stage_bytes, num_tiles, relu;
-  int base_offset_mode;  // 0: descriptor base_offset field = 0, 1: (start address >> 7) & 7
 };
 
+// TR, TS, TK: compile-time filter size and K steps (0: taken from the parameters at run time).  The MMA warp is a single
+// instruction stream at ~10 cycles per dependent instruction, so for the 3x3x32-channel stem layers its loop is fully
+// unrolled with all descriptor offsets folded into constants: one add + one tcgen05.mma per K step.
+template <int TR, int TS, int TK>
 __global__ void __launch_bounds__(kFlatThreads, 1)
 conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const FlatParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -121,9 +124,13 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ===================================================================== MMA issuer
     const uint32_t idesc = make_instr_desc(2 * p.nt);
     const uint64_t dhi = smem_desc_hi(p.swz_type, p.sbo);
-    const int R = p.R, S = p.S, ksteps = p.ksteps, n_stages = p.stages, bom = p.base_offset_mode;
+    const int R = TR ? TR : p.R, S = TS ? TS : p.S, ksteps = TK ? TK : p.ksteps, n_stages = p.stages;
     const uint32_t run_bytes = (uint32_t)p.run_bytes, stage_bytes = (uint32_t)p.stage_bytes, row_bytes = (uint32_t)p.row_bytes,
                    wtile_bytes = (uint32_t)p.wtile_bytes;
+    // Descriptor start-address fields (>> 4).  The swizzle of both TMA and tcgen05 is a function of the absolute
+    // shared-memory address bits, so a view shifted by whole pixel rows needs nothing but the new start address (the
+    // descriptor's base-offset field stays 0; setting it to (addr >> 7) & 7 gives wrong results -- measured).
+    const uint64_t wdesc0 = make_smem_desc(w_base, dhi);
     mbar_wait(wfull_bar, 0);
     int stage = 0;
     uint32_t phase = 0;
@@ -134,23 +141,31 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_wait(full_bar(stage), phase);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
-      const uint32_t sa = st_base + (uint32_t)stage * stage_bytes;
+      const uint64_t adesc0 = make_smem_desc(st_base + (uint32_t)stage * stage_bytes, dhi);
       if (elect_one()) {
-        uint32_t first = 0;
-        uint32_t wt = w_base;
-        for (int r = 0; r < R; ++r) {
-          for (int s = 0; s < S; ++s) {
-            // the tap's A operand is the run of filter row r, shifted by s pixel rows
-            const uint32_t astart = sa + (uint32_t)r * run_bytes + (uint32_t)s * row_bytes;
-            uint64_t adesc = make_smem_desc(astart, dhi);
-            if (bom) adesc |= (uint64_t)((astart >> 7) & 7u) << 49;
-            const uint64_t bdesc = make_smem_desc(wt, dhi);
-            for (int k = 0; k < ksteps; ++k) {
-              umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first);
-              first = 1u;
+        if (TR && TS && TK) {
+#pragma unroll
+          for (int r = 0; r < TR; ++r)
+#pragma unroll
+            for (int s2 = 0; s2 < TS; ++s2)
+#pragma unroll
+              for (int k = 0; k < TK; ++k) {
+                const uint64_t ad = adesc0 + (uint64_t)(((uint32_t)r * run_bytes + (uint32_t)s2 * row_bytes) >> 4) + (uint64_t)(2 * k);
+                const uint64_t bd = wdesc0 + (uint64_t)(((uint32_t)(r * TS + s2) * wtile_bytes) >> 4) + (uint64_t)(2 * k);
+                umma_f16(d_tmem, ad, bd, idesc, (r | s2 | k) ? 1u : 0u);
+              }
+        } else {
+          uint32_t first = 0;
+          uint64_t bd = wdesc0;
+          for (int r = 0; r < R; ++r)
+            for (int s2 = 0; s2 < S; ++s2) {
+              const uint64_t ad = adesc0 + (uint64_t)(((uint32_t)r * run_bytes + (uint32_t)s2 * row_bytes) >> 4);
+              for (int k = 0; k < ksteps; ++k) {
+                umma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, first);
+                first = 1u;
+              }
+              bd += (uint64_t)(wtile_bytes >> 4);
             }
-            wt += wtile_bytes;
-          }
         }
         umma_commit(empty_bar(stage));
         umma_commit(tfull_bar(as));
@@ -334,14 +349,12 @@ int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const
   p.stage_bytes = L.R * p.run_bytes;
   p.num_tiles = cdiv(p.total, kBlockM);
   p.relu = a.relu;
-  static int bom = -1;
-  if (bom < 0) bom = getenv("TISE_FLAT_BASE_OFFSET") ? atoi(getenv("TISE_FLAT_BASE_OFFSET")) : 1;
-  p.base_offset_mode = bom;
 
   static int configured = 0;
   const int smem_limit = ctx->smem_optin > 0 ? ctx->smem_optin : 232448;
   if (configured != smem_limit) {
-    TISE_CUDA(ctx, cudaFuncSetAttribute(conv_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
+    TISE_CUDA(ctx, cudaFuncSetAttribute(conv_flat_kernel<3, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
+    TISE_CUDA(ctx, cudaFuncSetAttribute(conv_flat_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
     configured = smem_limit;
   }
   const int fixed = 1024 + (int)align_up((size_t)L.R * L.S * p.wtile_bytes, 1024) + 2 * kFlatEpiBuf + 2 * 128 * 4 +
@@ -351,7 +364,10 @@ int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const
   if (stages < 2) return fail(ctx, TISE_ERR_INVALID, "flat conv: does not fit shared memory");
   p.stages = stages;
   const int grid = p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms;
-  conv_flat_kernel<<<grid, kFlatThreads, smem_limit, st>>>(plan.tm_a, plan.tm_w, p);
+  if (L.R == 3 && L.S == 3 && p.ksteps == 2)
+    conv_flat_kernel<3, 3, 2><<<grid, kFlatThreads, smem_limit, st>>>(plan.tm_a, plan.tm_w, p);
+  else
+    conv_flat_kernel<0, 0, 0><<<grid, kFlatThreads, smem_limit, st>>>(plan.tm_a, plan.tm_w, p);
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;
 }
