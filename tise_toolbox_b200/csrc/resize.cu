@@ -8,6 +8,7 @@
 // output byte -- are identical to Pillow's.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -123,6 +124,74 @@ __global__ void resize_v_kernel(const uint8_t* __restrict__ tmp, const ImgDesc* 
   dst[j] = clip8(acc);
 }
 
+// Fused variant: one CTA = (image, strip of kStripRows output rows).  The input rows the strip depends on are staged in
+// shared memory, resampled horizontally into a uint8 shared-memory temporary (Pillow rounds to uint8 between the
+// passes) and vertically into the output strip, which is one contiguous byte range of the NHWC output.  HBM traffic is
+// the algorithmic minimum (read the image once, write the 299 x 299 result once); used whenever the strip's input
+// rows fit in shared memory (always for up-scaling; the two-kernel path above remains for big down-scales).
+constexpr int kStripRows = 13;  // 299 = 23 * 13
+constexpr int kFusedSmem = 96 * 1024;
+__global__ void __launch_bounds__(256) resize_fused_kernel(const uint8_t* __restrict__ imgs, const ImgDesc* __restrict__ descs,
+                                                           const int* __restrict__ tabs, int kmax,
+                                                           uint8_t* __restrict__ out) {
+  extern __shared__ uint8_t sm[];
+  const ImgDesc d = descs[blockIdx.y];
+  const int r0 = blockIdx.x * kStripRows;
+  const int* bounds_y = tabs + (size_t)d.tab_y * kOutSize * (2 + kmax);
+  const int* kk_y = bounds_y + kOutSize * 2;
+  const int* bounds_x = tabs + (size_t)d.tab_x * kOutSize * (2 + kmax);
+  const int* kk_x = bounds_x + kOutSize * 2;
+  const bool vpass = d.h != kOutSize, hpass = d.w != kOutSize;
+  // input rows needed by this strip
+  int y_lo = r0, y_hi = r0 + kStripRows;
+  if (vpass) {
+    y_lo = bounds_y[r0 * 2];
+    y_hi = bounds_y[(r0 + kStripRows - 1) * 2] + bounds_y[(r0 + kStripRows - 1) * 2 + 1];
+  }
+  const int n_in = y_hi - y_lo;
+  const int in_row = d.w * 3, out_row = kOutSize * 3;
+  uint8_t* s_tmp = sm;                                   // [n_in][897]   horizontally resampled rows
+  uint8_t* s_in = sm + (((size_t)n_in * out_row + 15) & ~(size_t)15);  // [n_in][w * 3]  raw input rows
+  const uint8_t* src = imgs + d.src_off + (size_t)y_lo * in_row;
+  const int in_bytes = n_in * in_row;
+  if (hpass) {
+    if ((((uintptr_t)src | (uintptr_t)in_bytes) & 15) == 0) {
+      for (int i = threadIdx.x; i < in_bytes / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_in)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    } else {
+      for (int i = threadIdx.x; i < in_bytes; i += blockDim.x) s_in[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_in * out_row; i += blockDim.x) {
+      const int y = i / out_row, j = i - y * out_row;
+      const int xx = j / 3, c = j - xx * 3;
+      const int xmin = bounds_x[xx * 2], cnt = bounds_x[xx * 2 + 1];
+      const int* k = kk_x + xx * kmax;
+      const uint8_t* row = s_in + y * in_row + xmin * 3 + c;
+      int acc = 1 << (kPrecisionBits - 1);
+      for (int x = 0; x < cnt; ++x) acc += (int)row[x * 3] * k[x];
+      s_tmp[i] = clip8(acc);
+    }
+  } else {  // Pillow skips the horizontal pass: the rows are already 897 bytes wide
+    for (int i = threadIdx.x; i < in_bytes; i += blockDim.x) s_tmp[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  uint8_t* dst = out + ((size_t)blockIdx.y * kOutSize + r0) * out_row;
+  for (int i = threadIdx.x; i < kStripRows * out_row; i += blockDim.x) {
+    const int yy = i / out_row, j = i - yy * out_row;
+    if (!vpass) {
+      dst[i] = s_tmp[i];
+      continue;
+    }
+    const int ymin = bounds_y[(r0 + yy) * 2], cnt = bounds_y[(r0 + yy) * 2 + 1];
+    const int* k = kk_y + (r0 + yy) * kmax;
+    const uint8_t* col = s_tmp + (ymin - y_lo) * out_row + j;
+    int acc = 1 << (kPrecisionBits - 1);
+    for (int y = 0; y < cnt; ++y) acc += (int)col[y * out_row] * k[y];
+    dst[i] = clip8(acc);
+  }
+}
+
 // Workspace layout: [descs n][sizes 2n ints][tables (2n) * 299 * (2 + kmax) ints][tmp n * max_h * 897]
 struct ResizeWs {
   size_t off_desc, off_sizes, off_tabs, off_tmp, total;
@@ -207,6 +276,28 @@ extern "C" int tise_resize_u8(tise_ctx* ctx, const uint8_t* d_imgs, const int64_
 
   resize_coeffs_kernel<<<(unsigned)sizes.size(), 320, 0, st>>>(d_sizes, kmax, d_tabs);
   TISE_LAUNCH_CHECK(ctx);
+  // fused single-kernel path if every strip's input rows (+ the uint8 temporary) fit in shared memory
+  {
+    const double vscale = max_h > kOutSize ? (double)max_h / kOutSize : 1.0;
+    const int n_in_max = (int)(kStripRows * ((double)max_h / kOutSize) + 2.0 * vscale + 3.0);
+    const size_t need = (((size_t)n_in_max * kOutSize * 3 + 15) & ~(size_t)15) + (size_t)n_in_max * max_w * 3 + 16;
+    static int fused_env = -1;
+    if (fused_env < 0) fused_env = getenv("TISE_RESIZE_FUSED") ? atoi(getenv("TISE_RESIZE_FUSED")) : 1;
+    if (fused_env && need <= (size_t)kFusedSmem) {
+      static bool configured = false;
+      if (!configured) {
+        TISE_CUDA(ctx, cudaFuncSetAttribute(resize_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
+        configured = true;
+      }
+      for (int i0 = 0; i0 < n; i0 += 32768) {
+        const int cnt = n - i0 < 32768 ? n - i0 : 32768;
+        resize_fused_kernel<<<dim3(kOutSize / kStripRows, cnt), 256, need, st>>>(
+            d_imgs, d_descs + i0, d_tabs, kmax, d_out + (size_t)i0 * kOutSize * kOutSize * 3);
+        TISE_LAUNCH_CHECK(ctx);
+      }
+      return TISE_OK;
+    }
+  }
   const dim3 blk(256);
   const unsigned gx = (kOutSize * 3 + 255) / 256;
   // gridDim.z is limited to 65535: chunk the batch

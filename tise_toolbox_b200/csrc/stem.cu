@@ -27,68 +27,89 @@ __global__ void __launch_bounds__(128) stem_kernel(const uint8_t* __restrict__ u
   }
   __syncthreads();
 
-  const long long total = (long long)n * kStemOut * kStemOut;
-  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total;
-       m += (long long)gridDim.x * blockDim.x) {
-    const int img = (int)(m / (kStemOut * kStemOut));
-    const int rem = (int)(m - (long long)img * kStemOut * kStemOut);
-    const int oy = rem / kStemOut, ox = rem - oy * kStemOut;
+  // Two horizontally adjacent output pixels per thread: every weight fetched from shared memory (one LDS.128 per
+  // 4 output channels) feeds 8 FMAs instead of 4 -- with one pixel per thread the kernel was bound by the 243
+  // shared-memory loads per 864 FMAs, not by the FMA pipe.
+  constexpr int kPairs = (kStemOut + 1) / 2;  // 75 pixel pairs per output row (the last one is a single pixel)
+  const long long total = (long long)n * kStemOut * kPairs;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(t / (kStemOut * kPairs));
+    const int rem = (int)(t - (long long)img * kStemOut * kPairs);
+    const int oy = rem / kPairs, ox = (rem - oy * kPairs) * 2;
+    const bool two = ox + 1 < kStemOut;
 
-    float x[27];  // k = (r * 3 + s) * 3 + c
+    // input window: 3 rows x 5 columns x 3 channels (columns 2*ox .. 2*ox+4); x[r][col*3 + c]
+    float x[3][15];
     if (kU8) {
       const uint8_t* base = u8 + ((size_t)img * kOutSize + 2 * oy) * kOutSize * 3 + 2 * ox * 3;
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int j = 0; j < 9; ++j) {  // j = s * 3 + c, 9 contiguous bytes of the row
-          const int v = __ldg(base + (size_t)r * kOutSize * 3 + j);
-          x[r * 9 + j] = s_lut[(j % 3) * 256 + v];
+        for (int j = 0; j < 15; ++j) {
+          const bool ok = j < 9 || two;  // columns 3, 4 exist only if the second pixel does
+          const int v = ok ? (int)__ldg(base + (size_t)r * kOutSize * 3 + j) : 0;
+          x[r][j] = s_lut[(j % 3) * 256 + v];
         }
     } else {
       const float* base = f32 + (size_t)img * 3 * kOutSize * kOutSize;
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int s = 0; s < 3; ++s)
+        for (int col = 0; col < 5; ++col)
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
-            x[(r * 3 + s) * 3 + c] = __ldg(base + ((size_t)c * kOutSize + 2 * oy + r) * kOutSize + 2 * ox + s);
+          for (int c = 0; c < 3; ++c) {
+            const bool ok = col < 3 || two;
+            x[r][col * 3 + c] = ok ? __ldg(base + ((size_t)c * kOutSize + 2 * oy + r) * kOutSize + 2 * ox + col) : 0.f;
+          }
     }
 
-    float acc[kStemC];
+    float acc0[kStemC], acc1[kStemC];
 #pragma unroll
-    for (int co = 0; co < kStemC; ++co) acc[co] = 0.f;
+    for (int co = 0; co < kStemC; ++co) acc0[co] = acc1[co] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
-      const float4* wr = reinterpret_cast<const float4*>(s_w + k * kStemC);
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int q = 0; q < kStemC / 4; ++q) {
-        const float4 wv = wr[q];
-        acc[4 * q + 0] = fmaf(x[k], wv.x, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(x[k], wv.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(x[k], wv.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(x[k], wv.w, acc[4 * q + 3]);
+      for (int sc = 0; sc < 9; ++sc) {  // sc = s * 3 + c; weights k = (r * 3 + s) * 3 + c = r * 9 + sc
+        const float4* wr = reinterpret_cast<const float4*>(s_w + (r * 9 + sc) * kStemC);
+        const float a = x[r][sc], b = x[r][sc + 6];  // second pixel: two columns (6 values) to the right
+#pragma unroll
+        for (int q = 0; q < kStemC / 4; ++q) {
+          const float4 wv = wr[q];
+          acc0[4 * q + 0] = fmaf(a, wv.x, acc0[4 * q + 0]);
+          acc0[4 * q + 1] = fmaf(a, wv.y, acc0[4 * q + 1]);
+          acc0[4 * q + 2] = fmaf(a, wv.z, acc0[4 * q + 2]);
+          acc0[4 * q + 3] = fmaf(a, wv.w, acc0[4 * q + 3]);
+          acc1[4 * q + 0] = fmaf(b, wv.x, acc1[4 * q + 0]);
+          acc1[4 * q + 1] = fmaf(b, wv.y, acc1[4 * q + 1]);
+          acc1[4 * q + 2] = fmaf(b, wv.z, acc1[4 * q + 2]);
+          acc1[4 * q + 3] = fmaf(b, wv.w, acc1[4 * q + 3]);
+        }
       }
-    }
-    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m * kStemC);
+    const size_t m = ((size_t)img * kStemOut + oy) * kStemOut + ox;
 #pragma unroll
-    for (int q = 0; q < kStemC / 8; ++q) {
-      __half2 h[4];
+    for (int px = 0; px < 2; ++px) {
+      if (px == 1 && !two) break;
+      const float* acc = px ? acc1 : acc0;
+      uint4* dst = reinterpret_cast<uint4*>(out + (m + px) * kStemC);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int co = 8 * q + 2 * j;
-        float a = fmaxf(fmaf(acc[co], s_scale[co], s_shift[co]), 0.f);
-        float b = fmaxf(fmaf(acc[co + 1], s_scale[co + 1], s_shift[co + 1]), 0.f);
-        h[j] = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));
+      for (int q = 0; q < kStemC / 8; ++q) {
+        __half2 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int co = 8 * q + 2 * j;
+          const float ya = fmaxf(fmaf(acc[co], s_scale[co], s_shift[co]), 0.f);
+          const float yb = fmaxf(fmaf(acc[co + 1], s_scale[co + 1], s_shift[co + 1]), 0.f);
+          h[j] = __floats2half2_rn(fminf(ya, 65504.f), fminf(yb, 65504.f));
+        }
+        dst[q] = *reinterpret_cast<uint4*>(h);
       }
-      dst[q] = *reinterpret_cast<uint4*>(h);
     }
   }
 }
 
 int launch_stem(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, const float* d_w,
                 const float* d_scale, const float* d_shift, __half* d_out, cudaStream_t st) {
-  const long long total = (long long)n * kStemOut * kStemOut;
+  const long long total = (long long)n * kStemOut * ((kStemOut + 1) / 2);
   const int blocks = (int)((total + 127) / 128 < (long long)ctx->num_sms * 16 ? (total + 127) / 128
                                                                               : (long long)ctx->num_sms * 16);
   if (d_u8)
