@@ -54,31 +54,48 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md 'clocks line')."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md 'clocks line'): one streaming
+    nvidia-smi process (-lms 100); only lines that arrive between mark_start() and mark_stop() are summarised."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.t0, self.t1 = index, [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        if not self.proc:
+            return
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.strip().split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_stop(self):
+        self.t1 = time.perf_counter()
+
+    def close(self):
+        if self.proc:
+            self.proc.terminate()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if len(r) >= 7 and self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30) + 0.15]
+        if not rows:  # very short timed region: fall back to everything seen while the job ran
+            rows = [r for t, r in self.rows if len(r) >= 7]
+        num = lambda v: float(v) if v.replace(".", "", 1).isdigit() else None
+        sm = [num(r[0]) for r in rows if num(r[0]) is not None]
+        mx = [num(r[1]) for r in rows if num(r[1]) is not None]
+        pw = [num(r[2]) for r in rows if num(r[2]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
@@ -200,6 +217,8 @@ def main():
     if sampler:
         sampler.start()
     barrier()
+    if sampler:
+        sampler.mark_start()
     l0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -209,9 +228,9 @@ def main():
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     launches = eng.launches - l0
-    barrier()
     if sampler:
-        sampler.stop_flag = True
+        sampler.mark_stop()
+    barrier()
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
@@ -223,23 +242,26 @@ def main():
     torch.cuda.synchronize()
     finish_ms = 1e3 * (time.perf_counter() - t0)
 
-    # ---- end-to-end: same step through the public API from pinned host memory, result read back every step
+    # ---- end-to-end: the same step through the public API (RealismJob.step_from_host) from pinned host memory: every
+    # step's uint8 batch crosses PCIe (copy stream, double-buffered staging) and the step's result -- the running IS
+    # partial sums -- is read back to the host before the next step is issued
     host = torch.empty((min(args.pool, 2 * B), 256, 256, 3), dtype=torch.uint8).pin_memory()
     host.copy_(pool[:host.shape[0]].cpu())
-    staging = torch.empty((B, 256, 256, 3), dtype=torch.uint8, device=dev)
     job2 = RealismJob(eng, n_total=world * B * (K + W), start=lo, is_variant="bird", splits=10, input_variant="bird")
     d2h = torch.empty(job2.parts.f.numel(), dtype=torch.float64).pin_memory()
 
-    def e2e_step(s):
+    def host_batch(s):
         o = (s * B) % max(1, host.shape[0] - B + 1)
-        job2.step_from_host(host[o:o + B], staging)
-        d2h.copy_(job2.parts.f, non_blocking=True)  # the step's running IS partial sums -> host
+        return host[o:o + B]
+
+    def e2e_step(s):
+        job2.step_from_host(host_batch(s), host_batch(s + 1))
+        d2h.copy_(job2.parts.f, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     for s in range(min(W, 2)):
         e2e_step(s)
     barrier()
-    t0 = time.perf_counter()
     e0.record()
     for s in range(K):
         e2e_step(s)
@@ -250,6 +272,8 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * B * K / (float(e2e_ms.item()) / 1e3)
+    if sampler:
+        sampler.close()
 
     # ---- roofline of the dominant kernel (conv_umma_kernel): CUDA events around every launch, 2 extra steps
     pk = peaks()
@@ -262,7 +286,7 @@ def main():
     conv_ms, conv_launches, conv_flops = prof["conv"]
     trunk_ms = sum(v[0] for v in prof.values())
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel", "achieved": achieved, "peak": pk["tflops"],
+    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel + conv_flat_kernel (tcgen05 convolutions, 93 launches per micro-batch)", "achieved": achieved, "peak": pk["tflops"],
                 "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["source"],
                 "launches_per_step": conv_launches // 2, "avg_launch_us": 1e3 * conv_ms / max(1, conv_launches),
                 "algorithmic_gflop_per_image": conv_flops / (2 * B) / 1e9,

@@ -68,10 +68,41 @@ class RealismJob:
         self.pos += int(feat.shape[0])
         return feat
 
-    def step_from_host(self, pinned: torch.Tensor, staging: torch.Tensor) -> torch.Tensor:
-        """End-to-end step: async H2D copy of a pinned uint8 batch into ``staging``, then ``step``."""
-        staging[:pinned.shape[0]].copy_(pinned, non_blocking=True)
-        return self.step(staging[:pinned.shape[0]])
+    def step_from_host(self, pinned: torch.Tensor, next_pinned: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """End-to-end step from pinned host memory.  The H2D copy runs on a private copy stream into one of two
+        staging buffers; passing the following batch as ``next_pinned`` lets its copy overlap this step's compute."""
+        dev = self.e.device
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staging = [None, None]
+            self._slot_done = [None, None]  # event after the last step that read each staging buffer
+            self._pending = {}
+            self._slot = 0
+
+        def start_copy(src, slot):
+            buf = self._staging[slot]
+            if buf is None or buf.shape != src.shape:
+                buf = self._staging[slot] = torch.empty(src.shape, dtype=torch.uint8, device=dev)
+            if self._slot_done[slot] is not None:  # only the last reader of THIS buffer has to be finished
+                self._copy_stream.wait_event(self._slot_done[slot])
+            with torch.cuda.stream(self._copy_stream):
+                buf.copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            self._pending[src.data_ptr()] = (slot, ev)
+
+        key = pinned.data_ptr()
+        if key not in self._pending:
+            start_copy(pinned, self._slot)
+        slot, ev = self._pending.pop(key)
+        torch.cuda.current_stream(dev).wait_event(ev)
+        out = self.step(self._staging[slot])
+        self._slot_done[slot] = torch.cuda.Event()
+        self._slot_done[slot].record(torch.cuda.current_stream(dev))
+        self._slot = 1 - slot
+        if next_pinned is not None and next_pinned.data_ptr() not in self._pending:
+            start_copy(next_pinned, self._slot)
+        return out
 
     def finish(self, group=None) -> Dict[str, object]:
         """All-reduce (if ``group`` / torch.distributed is initialised) and finalise on every rank."""
