@@ -33,7 +33,7 @@ def parse():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--batch", type=int, default=1024, help="images per rank per step")
-    p.add_argument("--micro-batch", type=int, default=256)
+    p.add_argument("--micro-batch", type=int, default=512)
     p.add_argument("--pool", type=int, default=2048, help="distinct synthetic images resident per rank")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--passes", type=int, default=2)
@@ -286,12 +286,25 @@ def main():
     conv_ms, conv_launches, conv_flops = prof["conv"]
     trunk_ms = sum(v[0] for v in prof.values())
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel + conv_flat_kernel (tcgen05 convolutions, 93 launches per micro-batch)", "achieved": achieved, "peak": pk["tflops"],
-                "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["source"],
+    traffic, traffic_src = None, None
+    ncu_path = os.path.join(ROOT, "profiles", "ncu_conv_r01.json")
+    if os.path.exists(ncu_path) and args.micro_batch == 512:  # the ncu capture was taken at micro-batch 512
+        with open(ncu_path) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+        traffic_src = ("profiles/ncu_conv_r01.json: dram__bytes_read.sum + dram__bytes_write.sum averaged over the 66 "
+                       "tcgen05 conv launches of one 512-image micro-batch")
+    n_mb = 2 * ((B + args.micro_batch - 1) // args.micro_batch)  # micro-batches in the 2 profiled steps
+    roofline = {"bound": "tensor",
+                "kernel": "conv_umma_kernel + conv_flat_kernel (the tcgen05 convolutions: %d launches per micro-batch)"
+                          % (conv_launches // max(1, n_mb)),
+                "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["source"],
+                "flops_per_launch": conv_flops / max(1, conv_launches),
                 "launches_per_step": conv_launches // 2, "avg_launch_us": 1e3 * conv_ms / max(1, conv_launches),
                 "algorithmic_gflop_per_image": conv_flops / (2 * B) / 1e9,
                 "share_of_trunk_time": conv_ms / trunk_ms if trunk_ms else None,
                 "other_kernels_ms_per_step": {k: v[0] / 2 for k, v in prof.items() if k != "conv"},
+                "note": "two MMA passes (W_hi, W_lo) per algorithmic FLOP: frac <= 0.5 x tensor-pipe utilisation",
                 "how": "cudaEvent pairs on the launch stream around each launch, summed over 2 steps after the timed region"}
 
     line = {"metric": "FID/IS* images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
