@@ -107,6 +107,27 @@ def test_conv_umma_single_pass(engine):
     _conv_case(engine, 0, 2, 17, 17, 768, 192, 1, 1, 1, 0, 0, passes=1)
 
 
+# Batches large enough that the tcgen05 engine pairs two M tiles per work item (conv_umma.cu: msub = 2).
+PAIRED_SHAPES = [
+    (40, 35, 35, 64, 96, 3, 3, 1, 1, 1),     # nt 96: two MMAs per K step and tile; odd number of M tiles
+    (40, 35, 35, 48, 64, 5, 5, 1, 2, 2),     # nt 64: hi | lo planes in one MMA; 3-step chunks
+    (150, 17, 17, 128, 128, 1, 7, 1, 0, 3),  # nt 128: accumulators fill the 256-column TMEM stage
+    (150, 17, 17, 160, 192, 7, 1, 1, 3, 0),  # two N tiles, short last chunk
+    (20, 73, 73, 80, 192, 3, 3, 1, 0, 0),
+    (300, 8, 8, 448, 384, 3, 3, 1, 1, 1),    # three N tiles of 128
+    (64, 35, 35, 288, 240, 1, 1, 1, 0, 0),   # nt 240 stays unpaired
+]
+
+
+@pytest.mark.parametrize("shape", PAIRED_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_umma_paired_tiles(engine, shape):
+    _conv_case(engine, 0, *shape)
+
+
+def test_conv_umma_paired_tiles_single_pass(engine):
+    _conv_case(engine, 0, 40, 35, 35, 64, 96, 3, 3, 1, 1, 1, passes=1)
+
+
 # ----------------------------------------------------------------------------- statistics kernels
 def test_logits(engine, state_dict):
     g = torch.Generator().manual_seed(1)

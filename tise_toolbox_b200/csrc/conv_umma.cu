@@ -59,14 +59,120 @@ struct UmmaParams {
   int a_bytes, b_bytes;    // bytes of the A tile (128 x kc) and of one B plane (nt x kc) of a K block
   int swz_type, sbo;       // UMMA descriptor layout type and stride between 8-row groups for this kc
   int wide;                // hi | lo planes side by side form ONE MMA of N = 2 nt (nt <= 128, 2 passes)
+  int onebox;              // hi | lo rows of a tile arrive as ONE TMA box of 2 nt rows (nt <= 128, 2 passes)
   int nt, n_ntiles, num_tiles;
   int passes, stages, stage_bytes;
   int group, kb_bytes;  // K blocks per pipeline stage, bytes of one K block (A + B planes)
   int cs;               // CTAs per cluster (1, 2, 4): they work on cs consecutive M tiles of the same N tile and
                         // each loads 1/cs of the weight rows, multicast to all (TMA cost is per row)
   int m_tiles;
+  int msub;             // M tiles (1, 2) per work item: they share every weight load and barrier round trip (cs == 1 only)
+  int acc_cols;         // TMEM columns of one M tile's accumulator: 2 nt (wide) or nt
+  unsigned long long* dbg_out;  // debug & 64: per-CTA cycle counters of the three roles (see launch_conv_umma)
   int debug;            // timing ablations (TISE_UMMA_DEBUG): 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip epilogue
 };
+
+// ----------------------------------------------------------------------------- MMA issue loop
+struct MmaLoopArgs {
+  uint32_t idesc, desc_hi, desc_lo0;
+  uint32_t stage_step, kb_step;     // descriptor address-field steps (bytes >> 4) between stages / K blocks
+  uint32_t b_off, bplane, a1_off;   // W_hi tile, W_lo plane and second A tile relative to the first A tile
+  uint32_t acc_cols;
+  int group, n_stages, kb_per_tile;
+  bool uniform_ks;
+  int ks_const;
+  uint32_t bar_base, tmem_base;
+  int first, count, step;           // work items first, first + step, ... < count
+  uint16_t cmask;
+  int dbg;
+  unsigned long long* dbg_out;
+};
+
+// mbarrier wait whose duration is added to `acc` in the instrumented (debug & 64) runs of the kDebug instantiation
+template <bool kDebug>
+__device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, int dbg, unsigned long long& acc) {
+  if (kDebug && (dbg & 64)) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += (unsigned long long)(clock64() - t0);
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+
+// kTwoMma: W_lo is a second MMA into the same accumulator (otherwise hi | lo form one MMA of N = 2 nt, or 1 pass).
+// kTwoM: two M tiles per work item.  All 32 lanes run the loop; one elected lane issues (see the kernel).
+template <bool kCluster, bool kDebug, bool kTwoMma, bool kTwoM>
+__device__ __forceinline__ void mma_loop(const MmaLoopArgs& a, const uint4* kbtab) {
+  const uint32_t full0 = a.bar_base, empty0 = a.bar_base + 8u * kMaxStages, tfull0 = a.bar_base + 8u * (2 * kMaxStages),
+                 tempty0 = a.bar_base + 8u * (2 * kMaxStages + 2);
+  const uint32_t hi = a.desc_hi, idesc = a.idesc;
+  int stage = 0;
+  uint32_t phase = 0;
+  int as = 0;
+  uint32_t aphase = 0;
+  unsigned long long w_full = 0, w_tempty = 0;
+  const long long t_begin = kDebug ? clock64() : 0;
+  for (int st = a.first; st < a.count; st += a.step) {
+    timed_wait<kDebug>(tempty0 + 8u * (uint32_t)as, aphase ^ 1u, a.dbg, w_tempty);  // epilogue has drained this accumulator
+    tc_fence_after();
+    const uint32_t d0 = a.tmem_base + (uint32_t)(as * kAccumCols), d1 = d0 + a.acc_cols;
+    int jg = 0;
+    // descriptors differ from K block to K block only in the 14-bit start-address field (low word)
+    uint32_t alo = a.desc_lo0 + (uint32_t)stage * a.stage_step;
+    for (int kb = 0; kb < a.kb_per_tile; ++kb) {
+      if (jg == 0) {
+        timed_wait<kDebug>(full0 + 8u * (uint32_t)stage, phase, a.dbg, w_full);
+        tc_fence_after();
+      }
+      const int ksteps = a.uniform_ks ? a.ks_const : (int)kbtab[kb].w;
+      const bool last_in_group = (jg + 1 == a.group) || (kb == a.kb_per_tile - 1);
+      if (elect_one()) {
+        const uint32_t blo = alo + a.b_off;
+        // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (>> 4) address field
+#pragma unroll 4
+        for (int k = 0; k < ksteps; ++k) {
+          const uint32_t acc = (uint32_t)(kb | k);
+          umma_f16_lh(d0, alo + 2u * k, blo + 2u * k, hi, idesc, acc);
+          if (kTwoMma) umma_f16_lh(d0, alo + 2u * k, blo + a.bplane + 2u * k, hi, idesc, 1u);
+          if (kTwoM) {  // second M tile against the same weights
+            umma_f16_lh(d1, alo + a.a1_off + 2u * k, blo + 2u * k, hi, idesc, acc);
+            if (kTwoMma) umma_f16_lh(d1, alo + a.a1_off + 2u * k, blo + a.bplane + 2u * k, hi, idesc, 1u);
+          }
+        }
+        if (last_in_group) {
+          // frees the smem stage once these MMAs have read it -- in every CTA of the cluster, whose multicasts land here
+          const uint32_t eb = empty0 + 8u * (uint32_t)stage;
+          if (kDebug && (a.dbg & 16)) mbar_arrive(eb);  // timing experiment only (needs debug & 4)
+          else if (kCluster) umma_commit_mcast(eb, a.cmask); else umma_commit(eb);
+          if (kb == a.kb_per_tile - 1) {  // accumulator complete -> epilogue
+            if (kDebug && (a.dbg & 32)) mbar_arrive(tfull0 + 8u * (uint32_t)as); else umma_commit(tfull0 + 8u * (uint32_t)as);
+          }
+        }
+      }
+      alo += a.kb_step;
+      if (last_in_group) {
+        jg = 0;
+        if (++stage == a.n_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        alo = a.desc_lo0 + (uint32_t)stage * a.stage_step;
+      } else {
+        ++jg;
+      }
+    }
+    if (++as == 2) {
+      as = 0;
+      aphase ^= 1u;
+    }
+  }
+  if (kDebug && (a.dbg & 64) && (threadIdx.x & 31) == 0) {
+    a.dbg_out[blockIdx.x * 8 + 2] = (unsigned long long)(clock64() - t_begin);
+    a.dbg_out[blockIdx.x * 8 + 3] = w_full;
+    a.dbg_out[blockIdx.x * 8 + 4] = w_tempty;
+  }
+}
 
 // ----------------------------------------------------------------------------- kernel
 template <bool kF32, bool kCluster, bool kDebug>
@@ -80,6 +186,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   // from the constant bank on every use), and the timing-ablation branches exist only in the kDebug instantiation.
   const int dbg = kDebug ? p.debug : 0;
   const int pcs = kCluster ? p.cs : 1;  // compile-time 1 in the non-cluster instantiation
+  const int msub = kCluster ? 1 : p.msub;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   // layout: [stages x group x (A | B_hi | B_lo)] [2 staged output boxes] [scale cout | shift cout] [barriers] [tmem slot]
@@ -131,12 +238,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int crank = kCluster ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / pcs, num_clusters = gridDim.x / pcs;
-  const int num_super = ((p.m_tiles + pcs - 1) / pcs) * p.n_ntiles;  // (group of cs M tiles, N tile) work items
+  const int mg = pcs * msub;                                       // M tiles per work item
+  const int num_super = ((p.m_tiles + mg - 1) / mg) * p.n_ntiles;  // (group of M tiles, N tile) work items
   const uint16_t cmask = (uint16_t)((1u << pcs) - 1u);
 
   const int kb_per_tile = p.R * p.S * p.n_chunks;
   const uint32_t a_bytes = (uint32_t)p.a_bytes, b_bytes = (uint32_t)p.b_bytes;
-  const uint32_t kb_tx = ((dbg & 1) ? 0u : a_bytes) + ((dbg & 2) ? 0u : (uint32_t)p.passes * b_bytes);
+  const uint32_t a_tot = (uint32_t)msub * a_bytes;  // the A tiles of a K block lie side by side, then the weight planes
+  const uint32_t kb_tx = ((dbg & 1) ? 0u : a_tot) + ((dbg & 2) ? 0u : (uint32_t)p.passes * b_bytes);
   const bool wide2 = p.wide && p.passes == 2;
 
   // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the mbarriers and compute the
@@ -147,7 +256,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ===================================================================== TMA producer
     const int group = p.group, n_stages = p.stages, nt = p.nt;
     const uint32_t stage_bytes = (uint32_t)p.stage_bytes, kb_bytes = (uint32_t)p.kb_bytes;
-    const bool two_loads = p.passes == 2 && !wide2;
+    const bool two_loads = p.passes == 2 && !p.onebox;
     // cluster mode: the passes * nt weight rows of a K block are cut into slices of nt / 2 rows; this CTA loads
     // n_slices of them and multicasts each to every CTA of the cluster
     const int half_rows = p.nt / 2;
@@ -155,19 +264,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t half_bytes = (uint32_t)(half_rows * p.kc * 2);
     int stage = 0;
     uint32_t phase = 0;
+    unsigned long long w_empty = 0, n_kb = 0;
+    const long long t_begin = kDebug ? clock64() : 0;
     for (int st = cluster_id; st < num_super; st += num_clusters) {
       const int m_group = st / p.n_ntiles, n_tile = st - m_group * p.n_ntiles;
-      const int m_tile = m_group * pcs + crank;  // may be past the end in the last group: loads zero-fill, nothing is stored
-      const long long m0 = (long long)m_tile * kBlockM;
-      const int img = (int)(m0 / p.ho_wo);
-      const int rem = (int)(m0 - (long long)img * p.ho_wo);
-      const int oy = rem / p.wo, ox = rem - oy * p.wo;
-      const int wc = ox * p.stride - p.pad_w, hc = oy * p.stride - p.pad_h;  // base pixel (tap 0,0)
+      const int m_tile = (m_group * pcs + crank) * msub;  // may be past the end in the last group: loads zero-fill, nothing is stored
+      int img[2], wc[2], hc[2];  // base pixel (tap 0,0) of each M tile
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const long long m0 = (long long)(m_tile + sub) * kBlockM;
+        img[sub] = (int)(m0 / p.ho_wo);
+        const int rem = (int)(m0 - (long long)img[sub] * p.ho_wo);
+        const int oy = rem / p.wo, ox = rem - oy * p.wo;
+        wc[sub] = ox * p.stride - p.pad_w;
+        hc[sub] = oy * p.stride - p.pad_h;
+      }
       const int brow = n_tile * 2 * nt;  // first hi row of this tile's weight block; the lo rows follow
       int jg = 0;
       uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
       for (int kb = 0; kb < kb_per_tile; ++kb) {
-        if (jg == 0) mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (jg == 0) timed_wait<kDebug>(empty_bar(stage), phase ^ 1u, dbg, w_empty);
+        if (kDebug) ++n_kb;
         const uint4 e = kbtab[kb];
         const uint32_t fb = full_bar(stage);
         if (elect_one()) {
@@ -175,18 +292,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint32_t g = (uint32_t)min(group, kb_per_tile - kb);
             if (kb_tx) mbar_expect_tx(fb, g * kb_tx); else mbar_arrive(fb);
           }
-          if (!(dbg & 1)) tma_load_im2col(&tm_a, sa, fb, (int)e.x, wc, hc, img, (uint16_t)(e.y & 0xffffu), (uint16_t)(e.y >> 16));
+          if (!(dbg & 1)) {
+            tma_load_im2col(&tm_a, sa, fb, (int)e.x, wc[0], hc[0], img[0], (uint16_t)(e.y & 0xffffu), (uint16_t)(e.y >> 16));
+            if (msub == 2)
+              tma_load_im2col(&tm_a, sa + a_bytes, fb, (int)e.x, wc[1], hc[1], img[1], (uint16_t)(e.y & 0xffffu), (uint16_t)(e.y >> 16));
+          }
           if (!(dbg & 2)) {
             if (kCluster) {
               for (int i = 0; i < n_slices; ++i) {
                 const int sl = crank * n_slices + i;
-                tma_load_2d_mcast(&tm_bs, sa + a_bytes + (uint32_t)sl * half_bytes, fb, (int)e.z, brow + sl * half_rows, cmask);
+                tma_load_2d_mcast(&tm_bs, sa + a_tot + (uint32_t)sl * half_bytes, fb, (int)e.z, brow + sl * half_rows, cmask);
               }
             } else if (!two_loads) {
-              tma_load_2d(wide2 ? &tm_b2 : &tm_b, sa + a_bytes, fb, (int)e.z, brow);  // wide: hi and lo rows in one box
+              tma_load_2d(p.onebox ? &tm_b2 : &tm_b, sa + a_tot, fb, (int)e.z, brow);  // onebox: hi and lo rows together
             } else {
-              tma_load_2d(&tm_b, sa + a_bytes, fb, (int)e.z, brow);
-              tma_load_2d(&tm_b, sa + a_bytes + b_bytes, fb, (int)e.z, brow + nt);
+              tma_load_2d(&tm_b, sa + a_tot, fb, (int)e.z, brow);
+              tma_load_2d(&tm_b, sa + a_tot + b_bytes, fb, (int)e.z, brow + nt);
             }
           }
         }
@@ -201,65 +322,46 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
       }
     }
+    if (kDebug && (dbg & 64) && lane == 0) {
+      p.dbg_out[blockIdx.x * 8 + 0] = (unsigned long long)(clock64() - t_begin);
+      p.dbg_out[blockIdx.x * 8 + 1] = w_empty;
+      p.dbg_out[blockIdx.x * 8 + 7] = n_kb;
+    }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    const uint32_t idesc = make_instr_desc(wide2 ? 2 * p.nt : p.nt);
-    const uint64_t dhi = smem_desc_hi(p.swz_type, p.sbo);
-    const int group = p.group, n_stages = p.stages;
-    const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
-    const uint64_t kb_desc_step = (uint64_t)(p.kb_bytes >> 4), bhi_off = (uint64_t)(a_bytes >> 4),
-                   blo_off = (uint64_t)((a_bytes + b_bytes) >> 4);
     const bool two_mma = p.passes == 2 && !wide2;
-    int stage = 0;
-    uint32_t phase = 0;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int st = cluster_id; st < num_super; st += num_clusters) {
-      mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccumCols);
-      int jg = 0;
-      // descriptors differ from K block to K block only in the 14-bit start-address field
-      uint64_t adesc = make_smem_desc(smem_base + (uint32_t)stage * stage_bytes, dhi);
-      for (int kb = 0; kb < kb_per_tile; ++kb) {
-        if (jg == 0) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-        }
-        const int ksteps = (int)kbtab[kb].w;
-        const bool last_in_group = (jg + 1 == group) || (kb == kb_per_tile - 1);
-        if (elect_one()) {
-          const uint64_t bhi = adesc + bhi_off, blo = adesc + blo_off;
-          for (int k = 0; k < ksteps; ++k) {
-            // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (>>4) address field
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), idesc, (uint32_t)(kb | k));
-            if (two_mma) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc, 1u);
-          }
-          if (last_in_group) {
-            // frees the smem stage once these MMAs have read it -- in every CTA of the cluster, whose multicasts land here
-            if (dbg & 16) mbar_arrive(empty_bar(stage));  // timing experiment only (needs debug & 4)
-            else if (kCluster) umma_commit_mcast(empty_bar(stage), cmask); else umma_commit(empty_bar(stage));
-            if (kb == kb_per_tile - 1) {  // accumulator complete -> epilogue
-              if (dbg & 32) mbar_arrive(tfull_bar(as)); else umma_commit(tfull_bar(as));
-            }
-          }
-        }
-        adesc += kb_desc_step;
-        if (last_in_group) {
-          jg = 0;
-          if (++stage == n_stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
-          adesc = make_smem_desc(smem_base + (uint32_t)stage * stage_bytes, dhi);
-        } else {
-          ++jg;
-        }
-      }
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1u;
-      }
+    MmaLoopArgs ma;
+    ma.idesc = make_instr_desc(wide2 ? 2 * p.nt : p.nt);
+    const uint64_t dhi = smem_desc_hi(p.swz_type, p.sbo);
+    ma.desc_hi = (uint32_t)(dhi >> 32);
+    ma.desc_lo0 = (uint32_t)make_smem_desc(smem_base, dhi);  // low word of the descriptor of stage 0, K block 0
+    ma.stage_step = (uint32_t)p.stage_bytes >> 4;
+    ma.kb_step = (uint32_t)p.kb_bytes >> 4;
+    ma.b_off = a_tot >> 4;
+    ma.bplane = b_bytes >> 4;
+    ma.a1_off = a_bytes >> 4;
+    ma.acc_cols = (uint32_t)p.acc_cols;
+    ma.group = p.group;
+    ma.n_stages = p.stages;
+    ma.kb_per_tile = kb_per_tile;
+    // K steps per block: constant unless the channel count leaves a short last chunk (then read from the table)
+    ma.uniform_ks = p.n_chunks == 1 || p.last_ksteps == p.ksteps;
+    ma.ks_const = ((kDebug && (p.debug & 4)) ? 0 : (p.n_chunks == 1 ? p.last_ksteps : p.ksteps));
+    ma.bar_base = bar_base;
+    ma.tmem_base = tmem_base;
+    ma.first = cluster_id;
+    ma.count = num_super;
+    ma.step = num_clusters;
+    ma.cmask = cmask;
+    ma.dbg = dbg;
+    ma.dbg_out = p.dbg_out;
+    // one instantiation per (W_lo as a second MMA, second M tile): the loop body is straight-line code
+    if (two_mma) {
+      if (msub == 2) mma_loop<kCluster, kDebug, true, true>(ma, kbtab);
+      else mma_loop<kCluster, kDebug, true, false>(ma, kbtab);
+    } else {
+      if (msub == 2) mma_loop<kCluster, kDebug, false, true>(ma, kbtab);
+      else mma_loop<kCluster, kDebug, false, false>(ma, kbtab);
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
@@ -284,18 +386,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     int as = 0;
     uint32_t aphase = 0;
     uint32_t box_it = 0;
+    unsigned long long w_tfull = 0;
+    const long long t_begin = kDebug ? clock64() : 0;
     for (int st = cluster_id; st < num_super; st += num_clusters) {
       const int m_group = st / p.n_ntiles, n_tile = st - m_group * p.n_ntiles;
-      const long long m0 = (long long)(m_group * pcs + crank) * kBlockM;
       const int co0 = n_tile * p.nt;
-      mbar_wait(tfull_bar(as), aphase);
+      timed_wait<kDebug>(tfull_bar(as), aphase, dbg, w_tfull);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccumCols);
       if (dbg & 8) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
       }
+      for (int sub = 0; sub < msub; ++sub) {
+      const long long m0 = (long long)((m_group * pcs + crank) * msub + sub) * kBlockM;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccumCols + sub * p.acc_cols);
       for (int c0 = 0; c0 < ((dbg & 8) ? 0 : p.nt); c0 += W, ++box_it) {
         const uint32_t buf = epi_base + (box_it & 1u) * kEpiBufBytes;
         float f[W];
@@ -320,7 +425,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int j = 0; j < W; ++j) f[j] += __uint_as_float(v[j]);
           }
         }
-        if (c0 + W >= p.nt) {  // accumulator fully read: hand it back to the MMA warp before the stores
+        if (c0 + W >= p.nt && sub == msub - 1) {  // accumulators fully read: hand them back to the MMA warp before the stores
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -380,10 +485,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
         }
       }
+      }
       if (++as == 2) {
         as = 0;
         aphase ^= 1u;
       }
+    }
+    if (kDebug && (dbg & 64) && threadIdx.x == 64) {
+      p.dbg_out[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - t_begin);
+      p.dbg_out[blockIdx.x * 8 + 6] = w_tfull;
     }
   }
 
@@ -522,7 +632,6 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   p.b_bytes = L.nt * L.kc * 2;
   p.swz_type = L.kc == 64 ? 2 : (L.kc == 32 ? 4 : 6);
   p.sbo = 8 * L.kc * 2;
-  p.wide = 2 * L.nt <= 256 ? 1 : 0;
   const int m_tiles = cdiv(p.M, kBlockM);
   p.m_tiles = m_tiles;
   p.num_tiles = m_tiles * p.n_ntiles;
@@ -535,10 +644,31 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   while (cs > 1 && m_tiles < cs) cs >>= 1;
   p.cs = cs;
   p.passes = passes;
-  p.kb_bytes = p.a_bytes + passes * p.b_bytes;
+  // Two M tiles (256 output pixels) per work item share every weight load, barrier round trip and commit: the
+  // TMA fill rate out of L2 (~60-85 B/clk/SM measured), not the tensor pipe, bounds M = 128 tiles, whose weight
+  // bytes (2 planes) outweigh the activation bytes.  Needs both accumulators of a stage in 256 TMEM columns.
+  static int msub_env = -1;
+  if (msub_env < 0) msub_env = getenv("TISE_UMMA_MSUB") ? atoi(getenv("TISE_UMMA_MSUB")) : 0;
+  int msub = 1;
+  if (cs == 1 && 2 * p.nt <= kAccumCols && cdiv(m_tiles, 2) * p.n_ntiles >= ctx->num_sms) msub = 2;  // enough work items for every SM
+  if (msub_env == 1) msub = 1;
+  p.msub = msub;
+  p.onebox = (passes == 2 && 2 * p.nt <= 256) ? 1 : 0;
+  // one MMA of N = 2 nt per K step where even two M tiles leave TMEM room for it; decided by nt alone, so that the
+  // summation order -- and with it every output bit -- does not depend on the batch size
+  p.wide = (p.onebox && 4 * p.nt <= kAccumCols) ? 1 : 0;
+  p.acc_cols = p.wide ? 2 * p.nt : p.nt;
+  p.kb_bytes = msub * p.a_bytes + passes * p.b_bytes;
   static int debug_env = -1;
   if (debug_env < 0) debug_env = getenv("TISE_UMMA_DEBUG") ? atoi(getenv("TISE_UMMA_DEBUG")) : 0;
   p.debug = debug_env;
+  p.dbg_out = nullptr;
+  static unsigned long long* d_dbg = nullptr;
+  if (p.debug & 64) {  // role cycle counters: one synchronous report per launch on stderr
+    if (!d_dbg) TISE_CUDA(ctx, cudaMalloc(&d_dbg, 1024 * 8 * sizeof(unsigned long long)));
+    TISE_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, 1024 * 8 * sizeof(unsigned long long), st));
+    p.dbg_out = d_dbg;
+  }
 
   static int configured_smem = 0;
   const int smem_limit = ctx->smem_optin > 0 ? ctx->smem_optin : 232448;
@@ -557,7 +687,7 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   // instruction, measured), so a K block with little tensor work (small nt) cannot hide its own barrier wait /
   // expect_tx / commit: two K blocks share a stage when one holds < ~600 tensor cycles and 3 stages still fit.
   const int kb_per_tile = L.R * L.S * p.n_chunks;
-  const int kb_cycles = p.ksteps * passes * p.nt / 2;  // tcgen05 floor: M=128 x N x K=16 takes N / 2 cycles
+  const int kb_cycles = msub * p.ksteps * passes * p.nt / 2;  // tcgen05 floor: M=128 x N x K=16 takes N / 2 cycles
   int group = (kb_cycles < 600 && 2 * p.kb_bytes * 3 <= budget) ? 2 : 1;
   if (group > kb_per_tile) group = kb_per_tile;
   const char* genv = getenv("TISE_UMMA_GROUP");
@@ -568,7 +698,7 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(ctx, TISE_ERR_INVALID, "umma conv: tile does not fit shared memory");
   p.stages = stages;
-  const int num_super = cdiv(m_tiles, cs) * p.n_ntiles;
+  const int num_super = cdiv(m_tiles, cs * msub) * p.n_ntiles;
   // always request the full opt-in size: one CTA per SM, so the 512-column TMEM allocation never contends
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(ctx->num_sms / cs * cs));
@@ -596,8 +726,8 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   static int verbose = -1;
   if (verbose < 0) verbose = getenv("TISE_UMMA_VERBOSE") ? 1 : 0;
   if (verbose)
-    fprintf(stderr, "conv_umma %dx%d cin%d cout%d k%dx%d: nt %d kc %d wide %d group %d stages %d stage_bytes %d cs %d grid %d tiles %d\n",
-            a.h, a.w, L.cin, L.cout, L.R, L.S, p.nt, p.kc, p.wide, p.group, p.stages, p.stage_bytes, cs, clusters * cs,
+    fprintf(stderr, "conv_umma %dx%d cin%d cout%d k%dx%d: nt %d kc %d wide %d msub %d group %d stages %d stage_bytes %d cs %d grid %d tiles %d\n",
+            a.h, a.w, L.cin, L.cout, L.R, L.S, p.nt, p.kc, p.wide, p.msub, p.group, p.stages, p.stage_bytes, cs, clusters * cs,
             p.num_tiles);
   const CUtensorMap& tm_bs = plan.tm_bs;
   cudaError_t le;
@@ -616,6 +746,21 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   }
 #undef TISE_LAUNCH_UMMA
   if (le != cudaSuccess) return fail(ctx, TISE_ERR_CUDA, "conv_umma_kernel launch failed: %s", cudaGetErrorString(le));
+  if (p.debug & 64) {
+    static unsigned long long h[1024 * 8];
+    TISE_CUDA(ctx, cudaStreamSynchronize(st));
+    TISE_CUDA(ctx, cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    double sum[8] = {0};
+    const int nb = clusters * cs;
+    for (int b = 0; b < nb; ++b)
+      for (int j = 0; j < 8; ++j) sum[j] += (double)h[b * 8 + j];
+    const double kb = sum[7] > 0 ? sum[7] : 1;
+    fprintf(stderr,
+            "umma_roles %dx%d cin%d cout%d k%dx%d s%d nt%d msub%d: kb/cta %.0f | cycles per K block: producer %.0f (wait empty %.0f) "
+            "mma %.0f (wait full %.0f, wait tmem %.0f) epilogue %.0f (wait accum %.0f)\n",
+            a.h, a.w, L.cin, L.cout, L.R, L.S, L.stride, p.nt, p.msub, sum[7] / nb, sum[0] / kb, sum[1] / kb, sum[2] / kb,
+            sum[3] / kb, sum[4] / kb, sum[5] / kb, sum[6] / kb);
+  }
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;
 }

@@ -51,10 +51,25 @@ int conv_chunk_of(int cin) {
   return 64;
 }
 // Largest divisor of cout that is a multiple of 16 and at most 256.
+// N tile of a layer: the divisor of cout (multiple of 16, <= 256) that needs the fewest shared-memory fill bytes per
+// tensor-pipe cycle.  One K block of a work item of msub M tiles loads msub x 16 KiB of activations and 2 planes x
+// nt x 128 B of weights for msub x 4 nt cycles of MMAs; tiles of nt <= 128 can pair two M tiles (their accumulators
+// fit one 256-column TMEM stage), which halves the weight bytes per output.  See conv_umma.cu.
 int conv_ntile_of(int cout) {
-  for (int nt = 256; nt >= 16; nt -= 16)
-    if (cout % nt == 0) return nt;
-  return 0;
+  static int pair = -1;
+  if (pair < 0) pair = (getenv("TISE_UMMA_MSUB") && atoi(getenv("TISE_UMMA_MSUB")) == 1) ? 0 : 1;
+  int best = 0;
+  double best_cost = 1e30;
+  for (int nt = 256; nt >= 16; nt -= 16) {
+    if (cout % nt) continue;
+    const int msub = (pair && nt <= 128) ? 2 : 1;
+    const double cost = (msub * 16384.0 + 256.0 * nt) / (msub * 4.0 * nt);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = nt;
+    }
+  }
+  return best;
 }
 
 int pack_conv_layer(tise_ctx* ctx, ConvLayer* L, const float* w, const float* scale, const float* shift,

@@ -3,6 +3,8 @@
 // tensor cores (0.34 % of the trunk's MACs), so this is a direct fp32 convolution on the CUDA
 // cores; it reads the resized uint8 image (or the caller's float CHW batch) and writes the fp16
 // NHWC tensor the tcgen05 layers consume.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tise {
@@ -10,7 +12,9 @@ namespace tise {
 constexpr int kStemOut = 149;
 constexpr int kStemC = 32;
 
-template <bool kU8>
+// kCh = output channels per thread: 32, or 16 (two neighbouring threads share a pixel pair; fewer registers, more
+// resident warps to hide the input-load latency).
+template <bool kU8, int kCh>
 __global__ void __launch_bounds__(128) stem_kernel(const uint8_t* __restrict__ u8, const float* __restrict__ f32,
                                                    const float* __restrict__ lut, const float* __restrict__ w,
                                                    const float* __restrict__ scale, const float* __restrict__ shift,
@@ -31,8 +35,11 @@ __global__ void __launch_bounds__(128) stem_kernel(const uint8_t* __restrict__ u
   // 4 output channels) feeds 8 FMAs instead of 4 -- with one pixel per thread the kernel was bound by the 243
   // shared-memory loads per 864 FMAs, not by the FMA pipe.
   constexpr int kPairs = (kStemOut + 1) / 2;  // 75 pixel pairs per output row (the last one is a single pixel)
-  const long long total = (long long)n * kStemOut * kPairs;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+  constexpr int kSplit = kStemC / kCh;
+  const long long total = (long long)n * kStemOut * kPairs * kSplit;
+  for (long long tt = (long long)blockIdx.x * blockDim.x + threadIdx.x; tt < total; tt += (long long)gridDim.x * blockDim.x) {
+    const long long t = tt / kSplit;
+    const int coff = (int)(tt - t * kSplit) * kCh;  // first output channel of this thread
     const int img = (int)(t / (kStemOut * kPairs));
     const int rem = (int)(t - (long long)img * kStemOut * kPairs);
     const int oy = rem / kPairs, ox = (rem - oy * kPairs) * 2;
@@ -63,17 +70,17 @@ __global__ void __launch_bounds__(128) stem_kernel(const uint8_t* __restrict__ u
           }
     }
 
-    float acc0[kStemC], acc1[kStemC];
+    float acc0[kCh], acc1[kCh];
 #pragma unroll
-    for (int co = 0; co < kStemC; ++co) acc0[co] = acc1[co] = 0.f;
+    for (int co = 0; co < kCh; ++co) acc0[co] = acc1[co] = 0.f;
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int sc = 0; sc < 9; ++sc) {  // sc = s * 3 + c; weights k = (r * 3 + s) * 3 + c = r * 9 + sc
-        const float4* wr = reinterpret_cast<const float4*>(s_w + (r * 9 + sc) * kStemC);
+        const float4* wr = reinterpret_cast<const float4*>(s_w + (r * 9 + sc) * kStemC + coff);
         const float a = x[r][sc], b = x[r][sc + 6];  // second pixel: two columns (6 values) to the right
 #pragma unroll
-        for (int q = 0; q < kStemC / 4; ++q) {
+        for (int q = 0; q < kCh / 4; ++q) {
           const float4 wv = wr[q];
           acc0[4 * q + 0] = fmaf(a, wv.x, acc0[4 * q + 0]);
           acc0[4 * q + 1] = fmaf(a, wv.y, acc0[4 * q + 1]);
@@ -90,15 +97,15 @@ __global__ void __launch_bounds__(128) stem_kernel(const uint8_t* __restrict__ u
     for (int px = 0; px < 2; ++px) {
       if (px == 1 && !two) break;
       const float* acc = px ? acc1 : acc0;
-      uint4* dst = reinterpret_cast<uint4*>(out + (m + px) * kStemC);
+      uint4* dst = reinterpret_cast<uint4*>(out + (m + px) * kStemC + coff);
 #pragma unroll
-      for (int q = 0; q < kStemC / 8; ++q) {
+      for (int q = 0; q < kCh / 8; ++q) {
         __half2 h[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int co = 8 * q + 2 * j;
-          const float ya = fmaxf(fmaf(acc[co], s_scale[co], s_shift[co]), 0.f);
-          const float yb = fmaxf(fmaf(acc[co + 1], s_scale[co + 1], s_shift[co + 1]), 0.f);
+          const float ya = fmaxf(fmaf(acc[co], s_scale[coff + co], s_shift[coff + co]), 0.f);
+          const float yb = fmaxf(fmaf(acc[co + 1], s_scale[coff + co + 1], s_shift[coff + co + 1]), 0.f);
           h[j] = __floats2half2_rn(fminf(ya, 65504.f), fminf(yb, 65504.f));
         }
         dst[q] = *reinterpret_cast<uint4*>(h);
@@ -109,13 +116,18 @@ __global__ void __launch_bounds__(128) stem_kernel(const uint8_t* __restrict__ u
 
 int launch_stem(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, const float* d_w,
                 const float* d_scale, const float* d_shift, __half* d_out, cudaStream_t st) {
-  const long long total = (long long)n * kStemOut * ((kStemOut + 1) / 2);
-  const int blocks = (int)((total + 127) / 128 < (long long)ctx->num_sms * 16 ? (total + 127) / 128
-                                                                              : (long long)ctx->num_sms * 16);
-  if (d_u8)
-    stem_kernel<true><<<blocks, 128, 0, st>>>(d_u8, nullptr, ctx->d_lut, d_w, d_scale, d_shift, d_out, n);
-  else
-    stem_kernel<false><<<blocks, 128, 0, st>>>(nullptr, d_f32, nullptr, d_w, d_scale, d_shift, d_out, n);
+  static int split = -1;
+  if (split < 0) split = getenv("TISE_STEM_SPLIT") ? atoi(getenv("TISE_STEM_SPLIT")) : 1;
+  const long long total = (long long)n * kStemOut * ((kStemOut + 1) / 2) * (split ? 2 : 1);
+  const long long want = (total + 127) / 128, cap = (long long)ctx->num_sms * 32;
+  const int blocks = (int)(want < cap ? want : cap);
+  if (d_u8) {
+    if (split) stem_kernel<true, 16><<<blocks, 128, 0, st>>>(d_u8, nullptr, ctx->d_lut, d_w, d_scale, d_shift, d_out, n);
+    else stem_kernel<true, 32><<<blocks, 128, 0, st>>>(d_u8, nullptr, ctx->d_lut, d_w, d_scale, d_shift, d_out, n);
+  } else {
+    if (split) stem_kernel<false, 16><<<blocks, 128, 0, st>>>(nullptr, d_f32, nullptr, d_w, d_scale, d_shift, d_out, n);
+    else stem_kernel<false, 32><<<blocks, 128, 0, st>>>(nullptr, d_f32, nullptr, d_w, d_scale, d_shift, d_out, n);
+  }
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;
 }

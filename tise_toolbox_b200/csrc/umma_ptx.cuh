@@ -109,6 +109,22 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same instruction with the descriptors given as (low word, shared high word): K-step / plane / tile offsets only
+// ever change the 14-bit start-address field, so the issuing warp does 32-bit adds instead of 64-bit carry chains.
+__device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

@@ -54,10 +54,18 @@ def fid(a, b):
 def install(net, mode):
     """mode: 'f32' | 'f16a' (fp16 activations, hi+lo fp16 weights) | 'bf16x3' | 'f16' | 'bf16'."""
     first = net.Conv2d_1a_3x3.conv
+    stem = {id(net.Conv2d_2a_3x3.conv), id(net.Conv2d_2b_3x3.conv), id(net.Conv2d_3b_1x1.conv), id(net.Conv2d_4a_3x3.conv)}
     for mod in net.modules():
         if isinstance(mod, torch.nn.Conv2d) and mod is not first:
             w = mod.weight.data
-            if mode == "f16a":
+            if mode in ("f16stem", "f16nostem"):  # single fp16 pass only in (f16stem) / except in (f16nostem) the stem convs
+                single = (id(mod) in stem) == (mode == "f16stem")
+                if single:
+                    mod.weight.data = w.half().float()
+                else:
+                    hi = w.half().float(); lo = (w - hi).half().float(); mod.weight.data = hi + lo
+                mod.register_forward_pre_hook(lambda m, inp: (inp[0].half().float(),))
+            elif mode == "f16a":
                 hi = w.half().float(); lo = (w - hi).half().float(); mod.weight.data = hi + lo
                 mod.register_forward_pre_hook(lambda m, inp: (inp[0].half().float(),))
             elif mode == "f16":
