@@ -63,8 +63,8 @@ struct UmmaParams {
   int nt, n_ntiles, num_tiles;
   int passes, stages, stage_bytes;
   int group, kb_bytes;  // K blocks per pipeline stage, bytes of one K block (A + B planes)
-  int cs;               // CTAs per cluster (1, 2, 4): they work on cs consecutive M tiles of the same N tile and
-                        // each loads 1/cs of the weight rows, multicast to all (TMA cost is per row)
+  int cs;               // CTAs per cluster: 1, or 2 = CTA pair (cta_group::2 MMAs of M = 256 over two consecutive M tiles;
+                        // each CTA stages its own activation rows and half of the weight rows)
   int m_tiles;
   int msub;             // M tiles (1, 2) per work item: they share every weight load and barrier round trip (cs == 1 only)
   int acc_cols;         // TMEM columns of one M tile's accumulator: 2 nt (wide) or nt
@@ -83,7 +83,6 @@ struct MmaLoopArgs {
   int ks_const;
   uint32_t bar_base, tmem_base;
   int first, count, step;           // work items first, first + step, ... < count
-  uint16_t cmask;
   int dbg;
   unsigned long long* dbg_out;
 };
@@ -101,8 +100,15 @@ __device__ __forceinline__ void timed_wait(uint32_t bar, uint32_t parity, int db
 }
 
 // kTwoMma: W_lo is a second MMA into the same accumulator (otherwise hi | lo form one MMA of N = 2 nt, or 1 pass).
-// kTwoM: two M tiles per work item.  All 32 lanes run the loop; one elected lane issues (see the kernel).
-template <bool kCluster, bool kDebug, bool kTwoMma, bool kTwoM>
+// kTwoM: two M tiles per work item.  kPair: cta_group::2 MMAs issued by the leader CTA of a pair.
+// All 32 lanes run the loop; one elected lane issues (see the kernel).
+template <bool kPair>
+__device__ __forceinline__ void issue_mma(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  if (kPair) umma_f16_lh_pair(d, a_lo, b_lo, hi, idesc, acc);
+  else umma_f16_lh(d, a_lo, b_lo, hi, idesc, acc);
+}
+
+template <bool kPair, bool kDebug, bool kTwoMma, bool kTwoM>
 __device__ __forceinline__ void mma_loop(const MmaLoopArgs& a, const uint4* kbtab) {
   const uint32_t full0 = a.bar_base, empty0 = a.bar_base + 8u * kMaxStages, tfull0 = a.bar_base + 8u * (2 * kMaxStages),
                  tempty0 = a.bar_base + 8u * (2 * kMaxStages + 2);
@@ -133,20 +139,22 @@ __device__ __forceinline__ void mma_loop(const MmaLoopArgs& a, const uint4* kbta
 #pragma unroll 4
         for (int k = 0; k < ksteps; ++k) {
           const uint32_t acc = (uint32_t)(kb | k);
-          umma_f16_lh(d0, alo + 2u * k, blo + 2u * k, hi, idesc, acc);
-          if (kTwoMma) umma_f16_lh(d0, alo + 2u * k, blo + a.bplane + 2u * k, hi, idesc, 1u);
+          issue_mma<kPair>(d0, alo + 2u * k, blo + 2u * k, hi, idesc, acc);
+          if (kTwoMma) issue_mma<kPair>(d0, alo + 2u * k, blo + a.bplane + 2u * k, hi, idesc, 1u);
           if (kTwoM) {  // second M tile against the same weights
-            umma_f16_lh(d1, alo + a.a1_off + 2u * k, blo + 2u * k, hi, idesc, acc);
-            if (kTwoMma) umma_f16_lh(d1, alo + a.a1_off + 2u * k, blo + a.bplane + 2u * k, hi, idesc, 1u);
+            issue_mma<kPair>(d1, alo + a.a1_off + 2u * k, blo + 2u * k, hi, idesc, acc);
+            if (kTwoMma) issue_mma<kPair>(d1, alo + a.a1_off + 2u * k, blo + a.bplane + 2u * k, hi, idesc, 1u);
           }
         }
         if (last_in_group) {
-          // frees the smem stage once these MMAs have read it -- in every CTA of the cluster, whose multicasts land here
+          // frees the smem stage once these MMAs have read it (pair: in both CTAs, each has its own producer)
           const uint32_t eb = empty0 + 8u * (uint32_t)stage;
-          if (kDebug && (a.dbg & 16)) mbar_arrive(eb);  // timing experiment only (needs debug & 4)
-          else if (kCluster) umma_commit_mcast(eb, a.cmask); else umma_commit(eb);
-          if (kb == a.kb_per_tile - 1) {  // accumulator complete -> epilogue
-            if (kDebug && (a.dbg & 32)) mbar_arrive(tfull0 + 8u * (uint32_t)as); else umma_commit(tfull0 + 8u * (uint32_t)as);
+          if (kDebug && !kPair && (a.dbg & 16)) mbar_arrive(eb);  // timing experiment only (needs debug & 4)
+          else if (kPair) umma_commit_pair(eb); else umma_commit(eb);
+          if (kb == a.kb_per_tile - 1) {  // accumulator complete -> epilogue (pair: of both CTAs)
+            const uint32_t tb = tfull0 + 8u * (uint32_t)as;
+            if (kDebug && !kPair && (a.dbg & 32)) mbar_arrive(tb);
+            else if (kPair) umma_commit_pair(tb); else umma_commit(tb);
           }
         }
       }
@@ -175,7 +183,7 @@ __device__ __forceinline__ void mma_loop(const MmaLoopArgs& a, const uint4* kbta
 }
 
 // ----------------------------------------------------------------------------- kernel
-template <bool kF32, bool kCluster, bool kDebug>
+template <bool kF32, bool kPair, bool kDebug>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_b2, const __grid_constant__ CUtensorMap tm_bs,
@@ -185,8 +193,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   // parameters keeps them in registers (the "memory" clobbers of the PTX wrappers would otherwise force a reload
   // from the constant bank on every use), and the timing-ablation branches exist only in the kDebug instantiation.
   const int dbg = kDebug ? p.debug : 0;
-  const int pcs = kCluster ? p.cs : 1;  // compile-time 1 in the non-cluster instantiation
-  const int msub = kCluster ? 1 : p.msub;
+  constexpr int pcs = kPair ? 2 : 1;  // CTAs per work item
+  const int msub = kPair ? 1 : p.msub;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   // layout: [stages x group x (A | B_hi | B_lo)] [2 staged output boxes] [scale cout | shift cout] [barriers] [tmem slot]
@@ -211,11 +219,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), (uint32_t)(kCluster ? p.cs : 1));  // every CTA of the cluster must have consumed the multicast weights
+      mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), kPair ? 8 : 4);  // one arrive per epilogue warp (pair: of both CTAs, on the leader's barrier)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -227,25 +235,32 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                            (uint32_t)((kDebug && (p.debug & 4)) ? 0 : (ch == p.n_chunks - 1 ? p.last_ksteps : p.ksteps)));
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {  // both CTAs of the pair issue it, with the same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (kCluster) cluster_sync_all();  // peers' barriers are initialised before any multicast can reach them
+  if (kPair) cluster_sync_all();  // the peer's barriers are initialised before any load or commit can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const int crank = kCluster ? (int)cluster_ctarank() : 0;
+  const int crank = kPair ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / pcs, num_clusters = gridDim.x / pcs;
   const int mg = pcs * msub;                                       // M tiles per work item
   const int num_super = ((p.m_tiles + mg - 1) / mg) * p.n_ntiles;  // (group of M tiles, N tile) work items
-  const uint16_t cmask = (uint16_t)((1u << pcs) - 1u);
 
   const int kb_per_tile = p.R * p.S * p.n_chunks;
   const uint32_t a_bytes = (uint32_t)p.a_bytes, b_bytes = (uint32_t)p.b_bytes;
   const uint32_t a_tot = (uint32_t)msub * a_bytes;  // the A tiles of a K block lie side by side, then the weight planes
-  const uint32_t kb_tx = ((dbg & 1) ? 0u : a_tot) + ((dbg & 2) ? 0u : (uint32_t)p.passes * b_bytes);
+  // pair: each CTA stages half of the rows of every weight plane
+  const uint32_t half_bytes = (uint32_t)(p.nt / 2 * p.kc * 2);
+  const uint32_t kb_tx = ((dbg & 1) ? 0u : a_tot) + ((dbg & 2) ? 0u : (uint32_t)p.passes * (kPair ? half_bytes : b_bytes));
   const bool wide2 = p.wide && p.passes == 2;
 
   // Producer and MMA warps run their loops warp-uniformly (all 32 lanes wait on the mbarriers and compute the
@@ -257,11 +272,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int group = p.group, n_stages = p.stages, nt = p.nt;
     const uint32_t stage_bytes = (uint32_t)p.stage_bytes, kb_bytes = (uint32_t)p.kb_bytes;
     const bool two_loads = p.passes == 2 && !p.onebox;
-    // cluster mode: the passes * nt weight rows of a K block are cut into slices of nt / 2 rows; this CTA loads
-    // n_slices of them and multicasts each to every CTA of the cluster
     const int half_rows = p.nt / 2;
-    const int n_slices = 2 * p.passes / pcs;
-    const uint32_t half_bytes = (uint32_t)(half_rows * p.kc * 2);
+    // pair: every load of both CTAs completes on the leader's full barrier, which alone carries the expect_tx
+    const uint32_t full_base = kPair ? mapa_u32(bar_base, 0) : bar_base;
     int stage = 0;
     uint32_t phase = 0;
     unsigned long long w_empty = 0, n_kb = 0;
@@ -286,22 +299,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (jg == 0) timed_wait<kDebug>(empty_bar(stage), phase ^ 1u, dbg, w_empty);
         if (kDebug) ++n_kb;
         const uint4 e = kbtab[kb];
-        const uint32_t fb = full_bar(stage);
+        const uint32_t fb = full_base + 8u * (uint32_t)stage;
         if (elect_one()) {
-          if (jg == 0) {
+          if (jg == 0 && crank == 0) {
             const uint32_t g = (uint32_t)min(group, kb_per_tile - kb);
-            if (kb_tx) mbar_expect_tx(fb, g * kb_tx); else mbar_arrive(fb);
+            if (kb_tx) mbar_expect_tx(full_bar(stage), g * kb_tx * (uint32_t)pcs); else mbar_arrive(full_bar(stage));
           }
           if (!(dbg & 1)) {
-            tma_load_im2col(&tm_a, sa, fb, (int)e.x, wc[0], hc[0], img[0], (uint16_t)(e.y & 0xffffu), (uint16_t)(e.y >> 16));
-            if (msub == 2)
-              tma_load_im2col(&tm_a, sa + a_bytes, fb, (int)e.x, wc[1], hc[1], img[1], (uint16_t)(e.y & 0xffffu), (uint16_t)(e.y >> 16));
+            if (kPair) {
+              tma_load_im2col_pair(&tm_a, sa, fb, (int)e.x, wc[0], hc[0], img[0], (uint16_t)(e.y & 0xffffu), (uint16_t)(e.y >> 16));
+            } else {
+              tma_load_im2col(&tm_a, sa, fb, (int)e.x, wc[0], hc[0], img[0], (uint16_t)(e.y & 0xffffu), (uint16_t)(e.y >> 16));
+              if (msub == 2)
+                tma_load_im2col(&tm_a, sa + a_bytes, fb, (int)e.x, wc[1], hc[1], img[1], (uint16_t)(e.y & 0xffffu), (uint16_t)(e.y >> 16));
+            }
           }
           if (!(dbg & 2)) {
-            if (kCluster) {
-              for (int i = 0; i < n_slices; ++i) {
-                const int sl = crank * n_slices + i;
-                tma_load_2d_mcast(&tm_bs, sa + a_tot + (uint32_t)sl * half_bytes, fb, (int)e.z, brow + sl * half_rows, cmask);
+            if (kPair) {
+              if (wide2) {  // N = 2 nt: the leader holds the W_hi rows, its peer the W_lo rows
+                tma_load_2d_pair(&tm_b, sa + a_bytes, fb, (int)e.z, brow + crank * nt);
+              } else {      // N = nt per pass: rows [0, nt / 2) of each plane in the leader, the rest in its peer
+                tma_load_2d_pair(&tm_bs, sa + a_bytes, fb, (int)e.z, brow + crank * half_rows);
+                if (p.passes == 2) tma_load_2d_pair(&tm_bs, sa + a_bytes + half_bytes, fb, (int)e.z, brow + nt + crank * half_rows);
               }
             } else if (!two_loads) {
               tma_load_2d(p.onebox ? &tm_b2 : &tm_b, sa + a_tot, fb, (int)e.z, brow);  // onebox: hi and lo rows together
@@ -327,18 +346,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       p.dbg_out[blockIdx.x * 8 + 1] = w_empty;
       p.dbg_out[blockIdx.x * 8 + 7] = n_kb;
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+  } else if (warp == 1 && crank == 0) {
+    // ===================================================================== MMA issuer (pair: the leader CTA only)
     const bool two_mma = p.passes == 2 && !wide2;
     MmaLoopArgs ma;
-    ma.idesc = make_instr_desc(wide2 ? 2 * p.nt : p.nt);
+    ma.idesc = make_instr_desc(wide2 ? 2 * p.nt : p.nt, kPair ? 256 : 128);
     const uint64_t dhi = smem_desc_hi(p.swz_type, p.sbo);
     ma.desc_hi = (uint32_t)(dhi >> 32);
     ma.desc_lo0 = (uint32_t)make_smem_desc(smem_base, dhi);  // low word of the descriptor of stage 0, K block 0
     ma.stage_step = (uint32_t)p.stage_bytes >> 4;
     ma.kb_step = (uint32_t)p.kb_bytes >> 4;
     ma.b_off = a_tot >> 4;
-    ma.bplane = b_bytes >> 4;
+    ma.bplane = (kPair ? half_bytes : b_bytes) >> 4;
     ma.a1_off = a_bytes >> 4;
     ma.acc_cols = (uint32_t)p.acc_cols;
     ma.group = p.group;
@@ -352,18 +371,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     ma.first = cluster_id;
     ma.count = num_super;
     ma.step = num_clusters;
-    ma.cmask = cmask;
     ma.dbg = dbg;
     ma.dbg_out = p.dbg_out;
     // one instantiation per (W_lo as a second MMA, second M tile): the loop body is straight-line code
     if (two_mma) {
-      if (msub == 2) mma_loop<kCluster, kDebug, true, true>(ma, kbtab);
-      else mma_loop<kCluster, kDebug, true, false>(ma, kbtab);
+      if (!kPair && msub == 2) mma_loop<kPair, kDebug, true, true>(ma, kbtab);
+      else mma_loop<kPair, kDebug, true, false>(ma, kbtab);
     } else {
-      if (msub == 2) mma_loop<kCluster, kDebug, false, true>(ma, kbtab);
-      else mma_loop<kCluster, kDebug, false, false>(ma, kbtab);
+      if (!kPair && msub == 2) mma_loop<kPair, kDebug, false, true>(ma, kbtab);
+      else mma_loop<kPair, kDebug, false, false>(ma, kbtab);
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================================================================== epilogue (warps 2..5)
     constexpr int W = kF32 ? 16 : 32;  // channels per staged box (64-byte rows)
     constexpr int CPC = kF32 ? 4 : 8;  // channels per 16-byte chunk
@@ -378,6 +396,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       s_shift[c] = __ldg(p.shift + c);
     }
     epi_bar(2);
+    // hands an accumulator stage back to the MMA warp -- which, in a pair, lives in the leader CTA
+    const uint32_t tempty_leader = kPair ? mapa_u32(tempty_bar(0), 0) : 0u;
+    auto release_accum = [&](int s) {
+      if (kPair && crank != 0) mbar_arrive_cluster(tempty_leader + 8u * (uint32_t)s);
+      else mbar_arrive(tempty_bar(s));
+    };
     // staged box: row r at r * 64 bytes, its 16-byte chunk j stored at slot j ^ ((r >> 1) & 3): conflict-free both
     // for the row-per-thread writes and for the 4-lanes-per-row reads of the store phase
     const uint32_t wr_off = (uint32_t)row * 64u;
@@ -396,7 +420,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       if (dbg & 8) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) release_accum(as);
       }
       for (int sub = 0; sub < msub; ++sub) {
       const long long m0 = (long long)((m_group * pcs + crank) * msub + sub) * kBlockM;
@@ -428,7 +452,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (c0 + W >= p.nt && sub == msub - 1) {  // accumulators fully read: hand them back to the MMA warp before the stores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(as));
+          if (lane == 0) release_accum(as);
         }
         // scale / shift / ReLU (the ReLU flag can change every 16 channels: segment boundaries)
 #pragma unroll
@@ -499,10 +523,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (kCluster) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or signal its barriers
+  if (kPair) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers or read its operands
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -526,6 +551,13 @@ static int load_driver_entry_points(tise_ctx* ctx) {
 
 static CUtensorMapSwizzle swizzle_of(int kc) {
   return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// CTA-pair (cta_group::2) execution is the default; TISE_UMMA_PAIR=0 selects the single-CTA form of the kernel.
+bool umma_pair_mode() {
+  static int pair = -1;
+  if (pair < 0) pair = (getenv("TISE_UMMA_PAIR") && atoi(getenv("TISE_UMMA_PAIR")) == 0) ? 0 : 1;
+  return pair != 0;
 }
 
 int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPlan* plan) {
@@ -635,13 +667,10 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   const int m_tiles = cdiv(p.M, kBlockM);
   p.m_tiles = m_tiles;
   p.num_tiles = m_tiles * p.n_ntiles;
-  // cluster size: with two passes every CTA of a 4-cluster loads nt / 2 weight rows (half of hi+lo) per K block
-  static int cs_env = -1;
-  if (cs_env < 0) cs_env = getenv("TISE_UMMA_CLUSTER") ? atoi(getenv("TISE_UMMA_CLUSTER")) : 0;
-  int cs = 1;  // clusters (2, 4) are available through TISE_UMMA_CLUSTER; measured slower so far (profiles/)
-  if (cs_env == 1 || cs_env == 2 || cs_env == 4) cs = cs_env;
-  if (passes == 1 && cs == 4) cs = 2;  // slice rows must stay a multiple of 8 (one swizzle atom)
-  while (cs > 1 && m_tiles < cs) cs >>= 1;
+  // CTA pairs (cta_group::2): one MMA of M = 256 spans two SMs, each staging its own 128 activation rows and HALF of
+  // the weight rows.  Shared-memory traffic (TMA fills + operand reads, 128 B/clk/SM) is what bounds the single-CTA
+  // form of this kernel (measured: profiles/); the pair halves the weight share of both.
+  const int cs = umma_pair_mode() ? 2 : 1;
   p.cs = cs;
   p.passes = passes;
   // Two M tiles (256 output pixels) per work item share every weight load, barrier round trip and commit: the
@@ -654,11 +683,12 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   if (msub_env == 1) msub = 1;
   p.msub = msub;
   p.onebox = (passes == 2 && 2 * p.nt <= 256) ? 1 : 0;
-  // one MMA of N = 2 nt per K step where even two M tiles leave TMEM room for it; decided by nt alone, so that the
-  // summation order -- and with it every output bit -- does not depend on the batch size
-  p.wide = (p.onebox && 4 * p.nt <= kAccumCols) ? 1 : 0;
+  // one MMA of N = 2 nt per K step where TMEM has room for it (pair: nt <= 128; single CTA: nt <= 64, so that two M
+  // tiles fit); decided by nt alone, so that the summation order -- and with it every output bit -- does not depend
+  // on the batch size
+  p.wide = (p.onebox && (cs == 2 ? 2 : 4) * p.nt <= kAccumCols) ? 1 : 0;
   p.acc_cols = p.wide ? 2 * p.nt : p.nt;
-  p.kb_bytes = msub * p.a_bytes + passes * p.b_bytes;
+  p.kb_bytes = cs == 2 ? p.a_bytes + passes * (p.nt / 2) * L.kc * 2 : msub * p.a_bytes + passes * p.b_bytes;
   static int debug_env = -1;
   if (debug_env < 0) debug_env = getenv("TISE_UMMA_DEBUG") ? atoi(getenv("TISE_UMMA_DEBUG")) : 0;
   p.debug = debug_env;
@@ -687,7 +717,7 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   // instruction, measured), so a K block with little tensor work (small nt) cannot hide its own barrier wait /
   // expect_tx / commit: two K blocks share a stage when one holds < ~600 tensor cycles and 3 stages still fit.
   const int kb_per_tile = L.R * L.S * p.n_chunks;
-  const int kb_cycles = msub * p.ksteps * passes * p.nt / 2;  // tcgen05 floor: M=128 x N x K=16 takes N / 2 cycles
+  const int kb_cycles = msub * p.ksteps * passes * p.nt / 2;  // tcgen05 floor: M=128 (per SM) x N x K=16 takes N / 2 cycles
   int group = (kb_cycles < 600 && 2 * p.kb_bytes * 3 <= budget) ? 2 : 1;
   if (group > kb_per_tile) group = kb_per_tile;
   const char* genv = getenv("TISE_UMMA_GROUP");

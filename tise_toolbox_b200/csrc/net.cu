@@ -51,18 +51,24 @@ int conv_chunk_of(int cin) {
   return 64;
 }
 // Largest divisor of cout that is a multiple of 16 and at most 256.
-// N tile of a layer: the divisor of cout (multiple of 16, <= 256) that needs the fewest shared-memory fill bytes per
-// tensor-pipe cycle.  One K block of a work item of msub M tiles loads msub x 16 KiB of activations and 2 planes x
-// nt x 128 B of weights for msub x 4 nt cycles of MMAs; tiles of nt <= 128 can pair two M tiles (their accumulators
-// fit one 256-column TMEM stage), which halves the weight bytes per output.  See conv_umma.cu.
+// N tile of a layer: a divisor of cout, multiple of 16, <= 256 (one tcgen05.mma).
+// * CTA pairs (default): the largest one -- per K block a CTA stages 16 KiB of activations plus nt x 128 B of weights
+//   and re-reads them once per K step, so shared-memory bytes per tensor-pipe cycle fall monotonically with nt.
+// * single-CTA form (TISE_UMMA_PAIR=0): the divisor that needs the fewest fill bytes per cycle when tiles of
+//   nt <= 128 pair two M tiles per work item (conv_umma.cu).
 int conv_ntile_of(int cout) {
-  static int pair = -1;
-  if (pair < 0) pair = (getenv("TISE_UMMA_MSUB") && atoi(getenv("TISE_UMMA_MSUB")) == 1) ? 0 : 1;
+  if (umma_pair_mode()) {
+    for (int nt = 256; nt >= 16; nt -= 16)
+      if (cout % nt == 0) return nt;
+    return 0;
+  }
+  static int pair_m = -1;
+  if (pair_m < 0) pair_m = (getenv("TISE_UMMA_MSUB") && atoi(getenv("TISE_UMMA_MSUB")) == 1) ? 0 : 1;
   int best = 0;
   double best_cost = 1e30;
   for (int nt = 256; nt >= 16; nt -= 16) {
     if (cout % nt) continue;
-    const int msub = (pair && nt <= 128) ? 2 : 1;
+    const int msub = (pair_m && nt <= 128) ? 2 : 1;
     const double cost = (msub * 16384.0 + 256.0 * nt) / (msub * 4.0 * nt);
     if (cost < best_cost - 1e-9) {
       best_cost = cost;

@@ -54,17 +54,36 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mcast(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1,
-                                                  uint16_t mask) {
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on one TPC run ONE MMA of M = 256; each holds its 128 rows of A and
+// half of the B rows in its own shared memory, and its 128 accumulator rows in its own TMEM.  The TMA loads of both
+// CTAs complete on the LEADER's (cluster rank 0) mbarrier, which .cta_group::2 permits; the leader issues the MMAs
+// and its commits arrive on the barriers of both CTAs (multicast).
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {  // same location in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t dst, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, "
-      "%5}], [%2], %3;" ::"r"(dst),
-      "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(dst),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(mask)
+__device__ __forceinline__ void tma_load_im2col_pair(const CUtensorMap* map, uint32_t dst, uint32_t leader_bar, int c, int w,
+                                                     int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(map), "r"(leader_bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
                : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -125,6 +144,20 @@ __device__ __forceinline__ void umma_f16_lh(uint32_t tmem_d, uint32_t a_lo, uint
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16_lh_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -175,8 +208,8 @@ __device__ __forceinline__ uint64_t smem_desc_hi(int swz_type, int sbo) {
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = f16 (0), both K-major,
 // N >> 3 in [17,23), M >> 4 in [24,29).
-__device__ __forceinline__ uint32_t make_instr_desc(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+__device__ __forceinline__ uint32_t make_instr_desc(int n, int m = kBlockM) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 
