@@ -25,7 +25,7 @@
 
 namespace tise {
 
-constexpr int kFlatThreads = 192;
+constexpr int kFlatThreads = 320;  // producer warp, MMA warp, 2 epilogue groups of 4 warps (one per accumulator stage)
 constexpr int kFlatMaxStages = 8;
 constexpr int kFlatEpiBuf = 128 * 64;
 
@@ -61,7 +61,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t w_base = smem_base;
   const uint32_t st_base = (w_base + (uint32_t)(taps * p.wtile_bytes) + 1023u) & ~1023u;
   const uint32_t epi_base = st_base + (uint32_t)p.stages * (uint32_t)p.stage_bytes;
-  const uint32_t ss_base = epi_base + 2u * kFlatEpiBuf;
+  const uint32_t ss_base = epi_base + 4u * kFlatEpiBuf;
   const uint32_t bar_base = ss_base + 2u * 128u * 4u;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(kFlatMaxStages + s); };
@@ -181,26 +181,29 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 2..5 and 6..9)
+    // two groups, one per accumulator stage: group g drains this CTA's tiles number g, g + 2, ... (see conv_umma.cu)
+    const int grp = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int etid = threadIdx.x - 64;
+    const int etid = threadIdx.x - 64 - grp * 128;
     float* s_scale = reinterpret_cast<float*>(smem_raw + (ss_base - smem_u32(smem_raw)));
     float* s_shift = s_scale + 128;
     for (int c = etid; c < p.nt; c += 128) {
       s_scale[c] = __ldg(p.scale + c);
       s_shift[c] = __ldg(p.shift + c);
     }
-    epi_bar(2);
+    epi_bar(1 + grp);
+    const uint32_t my_epi = epi_base + (uint32_t)grp * 2u * kFlatEpiBuf;
     const uint32_t wr_off = (uint32_t)row * 64u;
     const uint32_t wr_swz = (uint32_t)((row >> 1) & 3);
     const int st_chunk = etid & 3, st_row0 = etid >> 2;
     const int nt = p.nt, wp = p.wp, hpwp = p.hpwp, ho = p.ho, wo = p.wo;
     const bool relu = p.relu != 0;
-    int as = 0;
+    const int as = grp;
     uint32_t aphase = 0;
     uint32_t box_it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x) {
       const long long v0 = (long long)tile * kBlockM;
       // is this thread's output position a real output or a wrap-around cell of the padded grid (written as 0)?
       const long long v = v0 + row;
@@ -211,7 +214,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 256);
       for (int c0 = 0; c0 < nt; c0 += 32, ++box_it) {
-        const uint32_t buf = epi_base + (box_it & 1u) * kFlatEpiBuf;
+        const uint32_t buf = my_epi + (box_it & 1u) * kFlatEpiBuf;
         float f[32];
         {
           uint32_t a[32], b[32];
@@ -248,7 +251,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           st_shared_v4(buf + wr_off + (((uint32_t)j ^ wr_swz) << 4), pack_h2(f[8 * j], f[8 * j + 1]),
                        pack_h2(f[8 * j + 2], f[8 * j + 3]), pack_h2(f[8 * j + 4], f[8 * j + 5]),
                        pack_h2(f[8 * j + 6], f[8 * j + 7]));
-        epi_bar(1);
+        epi_bar(1 + grp);
         const int ccol = c0 + st_chunk * 8;
         if (ccol < nt) {
           char* obase = reinterpret_cast<char*>(p.out) + (size_t)ccol * 2;
@@ -264,10 +267,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
         }
       }
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1u;
-      }
+      aphase ^= 1u;
     }
   }
 
@@ -357,7 +357,7 @@ int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const
     TISE_CUDA(ctx, cudaFuncSetAttribute(conv_flat_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
     configured = smem_limit;
   }
-  const int fixed = 1024 + (int)align_up((size_t)L.R * L.S * p.wtile_bytes, 1024) + 2 * kFlatEpiBuf + 2 * 128 * 4 +
+  const int fixed = 1024 + (int)align_up((size_t)L.R * L.S * p.wtile_bytes, 1024) + 4 * kFlatEpiBuf + 2 * 128 * 4 +
                     8 * (2 * kFlatMaxStages + 6) + 16;
   int stages = (smem_limit - fixed) / p.stage_bytes;
   if (stages > kFlatMaxStages) stages = kFlatMaxStages;

@@ -38,7 +38,7 @@ namespace tise {
 
 constexpr int kMaxStages = 8;
 constexpr int kAccumCols = 256;  // TMEM columns per accumulator stage
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 320;  // TMA producer warp, MMA warp, 2 epilogue groups of 4 warps
 constexpr int kMaxNt = 256;
 constexpr int kMaxKb = 96;      // K blocks per tile: taps * ceil(cin / 64) (<= 63 in Inception-v3)
 constexpr int kMaxCout = 1344;  // widest (fused) layer: Mixed_7b 320 + 384 + 448 + 192
@@ -199,7 +199,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   // layout: [stages x group x (A | B_hi | B_lo)] [2 staged output boxes] [scale cout | shift cout] [barriers] [tmem slot]
   const uint32_t epi_base = smem_base + (uint32_t)p.stages * (uint32_t)p.stage_bytes;
-  const uint32_t ss_base = epi_base + 2u * kEpiBufBytes;
+  const uint32_t ss_base = epi_base + 4u * kEpiBufBytes;  // two staged boxes per epilogue group
   const uint32_t bar_base = ss_base + 2u * kMaxCout * 4u;
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base address word
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
@@ -382,20 +382,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       else mma_loop<kPair, kDebug, false, false>(ma, kbtab);
     }
   } else if (warp >= 2) {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 2..5 and 6..9)
+    // Two groups of 4 warps, one per TMEM accumulator stage: group g drains the work items with (index & 1) == g, so
+    // two tiles are in the epilogue at once (the single group was the bottleneck of every layer with few K blocks).
+    const int grp = (warp - 2) >> 2;
     constexpr int W = kF32 ? 16 : 32;  // channels per staged box (64-byte rows)
     constexpr int CPC = kF32 ? 4 : 8;  // channels per 16-byte chunk
     const int quarter = warp & 3;      // TMEM lanes [32 * quarter, 32 * quarter + 32) are accessible to this warp
     const int row = quarter * 32 + lane;
-    const int etid = threadIdx.x - 64;  // 0..127
+    const int etid = threadIdx.x - 64 - grp * 128;  // 0..127 within the group
     float* s_scale = reinterpret_cast<float*>(smem_raw + (ss_base - smem_u32(smem_raw)));
     float* s_shift = s_scale + kMaxCout;
-    // the whole layer's folded-BN scale / shift, once per CTA (a per-tile reload exposed ~1 us of L2 latency per tile)
+    // the whole layer's folded-BN scale / shift, once per CTA (a per-tile reload exposed ~1 us of L2 latency per tile);
+    // both groups write all (identical) values, so each only needs its own barrier
     for (int c = etid; c < p.n_ntiles * p.nt; c += 128) {
       s_scale[c] = __ldg(p.scale + c);
       s_shift[c] = __ldg(p.shift + c);
     }
-    epi_bar(2);
+    epi_bar(1 + grp);
+    const uint32_t my_epi = epi_base + (uint32_t)grp * 2u * kEpiBufBytes;
     // hands an accumulator stage back to the MMA warp -- which, in a pair, lives in the leader CTA
     const uint32_t tempty_leader = kPair ? mapa_u32(tempty_bar(0), 0) : 0u;
     auto release_accum = [&](int s) {
@@ -407,12 +412,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t wr_off = (uint32_t)row * 64u;
     const uint32_t wr_swz = (uint32_t)((row >> 1) & 3);
     const int st_chunk = etid & 3, st_row0 = etid >> 2;  // store phase: chunk st_chunk of rows st_row0 + 32 i
-    int as = 0;
+    const int as = grp;  // this group's accumulator stage
     uint32_t aphase = 0;
     uint32_t box_it = 0;
     unsigned long long w_tfull = 0;
     const long long t_begin = kDebug ? clock64() : 0;
-    for (int st = cluster_id; st < num_super; st += num_clusters) {
+    for (int st = cluster_id + grp * num_clusters; st < num_super; st += 2 * num_clusters) {
       const int m_group = st / p.n_ntiles, n_tile = st - m_group * p.n_ntiles;
       const int co0 = n_tile * p.nt;
       timed_wait<kDebug>(tfull_bar(as), aphase, dbg, w_tfull);
@@ -426,7 +431,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const long long m0 = (long long)((m_group * pcs + crank) * msub + sub) * kBlockM;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccumCols + sub * p.acc_cols);
       for (int c0 = 0; c0 < ((dbg & 8) ? 0 : p.nt); c0 += W, ++box_it) {
-        const uint32_t buf = epi_base + (box_it & 1u) * kEpiBufBytes;
+        const uint32_t buf = my_epi + (box_it & 1u) * kEpiBufBytes;
         float f[W];
         {
           uint32_t v[W];
@@ -488,7 +493,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             st_shared_v4(dst, pack_h2(f[8 * j], f[8 * j + 1]), pack_h2(f[8 * j + 2], f[8 * j + 3]),
                          pack_h2(f[8 * j + 4], f[8 * j + 5]), pack_h2(f[8 * j + 6], f[8 * j + 7]));
         }
-        epi_bar(1);  // box staged; also orders the reads of this buffer (box_it - 2) before these writes
+        epi_bar(1 + grp);  // box staged; also orders the reads of this buffer (box_it - 2) before these writes
         // store phase: thread -> (chunk, 4 rows); 4 consecutive lanes write one pixel's 64 contiguous bytes
         const int ccol = c0 + st_chunk * CPC;
         if (ccol < p.nt) {
@@ -510,10 +515,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
       }
       }
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1u;
-      }
+      aphase ^= 1u;
     }
     if (kDebug && (dbg & 64) && threadIdx.x == 64) {
       p.dbg_out[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - t_begin);
@@ -711,7 +713,7 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
       TISE_CUDA(ctx, cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
     configured_smem = smem_limit;
   }
-  const int reserve = 1024 /*alignment*/ + 2 * kEpiBufBytes + 2 * kMaxCout * 4 + 8 * (2 * kMaxStages + 4) + 16 + 16 * kMaxKb;
+  const int reserve = 1024 /*alignment*/ + 4 * kEpiBufBytes + 2 * kMaxCout * 4 + 8 * (2 * kMaxStages + 4) + 16 + 16 * kMaxKb;
   const int budget = smem_limit - reserve;
   // K blocks per pipeline stage.  The producer and MMA warps are single instruction streams (~10 cycles per dependent
   // instruction, measured), so a K block with little tensor work (small nt) cannot hide its own barrier wait /
