@@ -435,7 +435,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         float f[W];
         {
           uint32_t v[W];
-          if (kF32) {
+          if (kDebug && (dbg & 256)) {  // timing ablation: no TMEM reads
+#pragma unroll
+            for (int j = 0; j < W; ++j) v[j] = 0;
+          } else if (kF32) {
             tmem_ld16(taddr + (uint32_t)c0, reinterpret_cast<uint32_t(&)[16]>(v));
           } else {
             tmem_ld32(taddr + (uint32_t)c0, reinterpret_cast<uint32_t(&)[32]>(v));
@@ -443,7 +446,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < W; ++j) f[j] = __uint_as_float(v[j]);
-          if (wide2) {  // the W_lo products sit nt columns to the right
+          if (wide2 && !(kDebug && (dbg & 256))) {  // the W_lo products sit nt columns to the right
             if (kF32) {
               tmem_ld16(taddr + (uint32_t)(p.nt + c0), reinterpret_cast<uint32_t(&)[16]>(v));
             } else {
@@ -496,7 +499,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         epi_bar(1 + grp);  // box staged; also orders the reads of this buffer (box_it - 2) before these writes
         // store phase: thread -> (chunk, 4 rows); 4 consecutive lanes write one pixel's 64 contiguous bytes
         const int ccol = c0 + st_chunk * CPC;
-        if (ccol < p.nt) {
+        if (ccol < p.nt && !(kDebug && (dbg & 128))) {  // (debug & 128: timing ablation without the global stores)
           const int gcol = co0 + ccol;
           int sg = 0;
           while (sg < kMaxSegs - 1 && gcol >= p.seg_end[sg]) ++sg;
