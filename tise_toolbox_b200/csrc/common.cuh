@@ -87,6 +87,7 @@ struct ConvLayer {
 };
 int conv_chunk_of(int cin);
 int conv_ntile_of(int cout);
+bool umma_pdl_mode();   // conv_umma.cu: programmatic dependent launch unless TISE_PDL=0
 bool umma_pair_mode();  // conv_umma.cu: CTA pairs (cta_group::2) unless TISE_UMMA_PAIR=0
 static inline size_t conv_weight_row(const ConvLayer& L, int co, int plane) {
   return ((size_t)(co / L.nt) * 2 + plane) * L.nt + co % L.nt;

@@ -46,6 +46,7 @@ struct FlatParams {
   int run_rows, run_bytes;  // pixels per run (128 + S - 1) and its shared-memory footprint
   int wtile_bytes;          // one tap's weights: 2 * nt rows
   int stages, stage_bytes, num_tiles, relu;
+  int pdl;  // launched with programmatic stream serialization
 };
 
 // TR, TS, TK: compile-time filter size and K steps (0: taken from the parameters at run time).  The MMA warp is a single
@@ -93,6 +94,10 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (p.pdl) {
+    pdl_wait();
+    pdl_trigger();
+  }
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -364,10 +369,25 @@ int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const
   if (stages < 2) return fail(ctx, TISE_ERR_INVALID, "flat conv: does not fit shared memory");
   p.stages = stages;
   const int grid = p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kFlatThreads);
+  cfg.dynamicSmemBytes = (size_t)smem_limit;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  p.pdl = umma_pdl_mode() && !ctx->profiling ? 1 : 0;
+  if (p.pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  cudaError_t le;
   if (L.R == 3 && L.S == 3 && p.ksteps == 2)
-    conv_flat_kernel<3, 3, 2><<<grid, kFlatThreads, smem_limit, st>>>(plan.tm_a, plan.tm_w, p);
+    le = cudaLaunchKernelEx(&cfg, conv_flat_kernel<3, 3, 2>, plan.tm_a, plan.tm_w, p);
   else
-    conv_flat_kernel<0, 0, 0><<<grid, kFlatThreads, smem_limit, st>>>(plan.tm_a, plan.tm_w, p);
+    le = cudaLaunchKernelEx(&cfg, conv_flat_kernel<0, 0, 0>, plan.tm_a, plan.tm_w, p);
+  if (le != cudaSuccess) return fail(ctx, TISE_ERR_CUDA, "conv_flat_kernel launch failed: %s", cudaGetErrorString(le));
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;
 }

@@ -68,6 +68,7 @@ struct UmmaParams {
   int m_tiles;
   int msub;             // M tiles (1, 2) per work item: they share every weight load and barrier round trip (cs == 1 only)
   int acc_cols;         // TMEM columns of one M tile's accumulator: 2 nt (wide) or nt
+  int pdl;              // launched with programmatic stream serialization (see umma_ptx.cuh)
   unsigned long long* dbg_out;  // debug & 64: per-CTA cycle counters of the three roles (see launch_conv_umma)
   int debug;            // timing ablations (TISE_UMMA_DEBUG): 1 skip A loads, 2 skip B loads, 4 skip MMAs, 8 skip epilogue
 };
@@ -123,51 +124,43 @@ __device__ __forceinline__ void mma_loop(const MmaLoopArgs& a, const uint4* kbta
     timed_wait<kDebug>(tempty0 + 8u * (uint32_t)as, aphase ^ 1u, a.dbg, w_tempty);  // epilogue has drained this accumulator
     tc_fence_after();
     const uint32_t d0 = a.tmem_base + (uint32_t)(as * kAccumCols), d1 = d0 + a.acc_cols;
-    int jg = 0;
-    // descriptors differ from K block to K block only in the 14-bit start-address field (low word)
-    uint32_t alo = a.desc_lo0 + (uint32_t)stage * a.stage_step;
-    for (int kb = 0; kb < a.kb_per_tile; ++kb) {
-      if (jg == 0) {
-        timed_wait<kDebug>(full0 + 8u * (uint32_t)stage, phase, a.dbg, w_full);
-        tc_fence_after();
-      }
-      const int ksteps = a.uniform_ks ? a.ks_const : (int)kbtab[kb].w;
-      const bool last_in_group = (jg + 1 == a.group) || (kb == a.kb_per_tile - 1);
+    // one iteration per pipeline stage (1-2 K blocks): one wait, one election, one commit
+    for (int kb0 = 0; kb0 < a.kb_per_tile; kb0 += a.group) {
+      const int n = min(a.group, a.kb_per_tile - kb0);
+      timed_wait<kDebug>(full0 + 8u * (uint32_t)stage, phase, a.dbg, w_full);
+      tc_fence_after();
       if (elect_one()) {
-        const uint32_t blo = alo + a.b_off;
-        // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (>> 4) address field
+        // descriptors differ from K block to K block only in the 14-bit start-address field (low word)
+        uint32_t alo = a.desc_lo0 + (uint32_t)stage * a.stage_step;
+        for (int j = 0; j < n; ++j, alo += a.kb_step) {
+          const int kb = kb0 + j;
+          const int ksteps = a.uniform_ks ? a.ks_const : (int)kbtab[kb].w;
+          const uint32_t blo = alo + a.b_off;
+          // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the (>> 4) address field
 #pragma unroll 4
-        for (int k = 0; k < ksteps; ++k) {
-          const uint32_t acc = (uint32_t)(kb | k);
-          issue_mma<kPair>(d0, alo + 2u * k, blo + 2u * k, hi, idesc, acc);
-          if (kTwoMma) issue_mma<kPair>(d0, alo + 2u * k, blo + a.bplane + 2u * k, hi, idesc, 1u);
-          if (kTwoM) {  // second M tile against the same weights
-            issue_mma<kPair>(d1, alo + a.a1_off + 2u * k, blo + 2u * k, hi, idesc, acc);
-            if (kTwoMma) issue_mma<kPair>(d1, alo + a.a1_off + 2u * k, blo + a.bplane + 2u * k, hi, idesc, 1u);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint32_t acc = (uint32_t)(kb | k);
+            issue_mma<kPair>(d0, alo + 2u * k, blo + 2u * k, hi, idesc, acc);
+            if (kTwoMma) issue_mma<kPair>(d0, alo + 2u * k, blo + a.bplane + 2u * k, hi, idesc, 1u);
+            if (kTwoM) {  // second M tile against the same weights
+              issue_mma<kPair>(d1, alo + a.a1_off + 2u * k, blo + 2u * k, hi, idesc, acc);
+              if (kTwoMma) issue_mma<kPair>(d1, alo + a.a1_off + 2u * k, blo + a.bplane + 2u * k, hi, idesc, 1u);
+            }
           }
         }
-        if (last_in_group) {
-          // frees the smem stage once these MMAs have read it (pair: in both CTAs, each has its own producer)
-          const uint32_t eb = empty0 + 8u * (uint32_t)stage;
-          if (kDebug && !kPair && (a.dbg & 16)) mbar_arrive(eb);  // timing experiment only (needs debug & 4)
-          else if (kPair) umma_commit_pair(eb); else umma_commit(eb);
-          if (kb == a.kb_per_tile - 1) {  // accumulator complete -> epilogue (pair: of both CTAs)
-            const uint32_t tb = tfull0 + 8u * (uint32_t)as;
-            if (kDebug && !kPair && (a.dbg & 32)) mbar_arrive(tb);
-            else if (kPair) umma_commit_pair(tb); else umma_commit(tb);
-          }
+        // frees the smem stage once these MMAs have read it (pair: in both CTAs, each has its own producer)
+        const uint32_t eb = empty0 + 8u * (uint32_t)stage;
+        if (kDebug && !kPair && (a.dbg & 16)) mbar_arrive(eb);  // timing experiment only (needs debug & 4)
+        else if (kPair) umma_commit_pair(eb); else umma_commit(eb);
+        if (kb0 + n == a.kb_per_tile) {  // accumulator complete -> epilogue (pair: of both CTAs)
+          const uint32_t tb = tfull0 + 8u * (uint32_t)as;
+          if (kDebug && !kPair && (a.dbg & 32)) mbar_arrive(tb);
+          else if (kPair) umma_commit_pair(tb); else umma_commit(tb);
         }
       }
-      alo += a.kb_step;
-      if (last_in_group) {
-        jg = 0;
-        if (++stage == a.n_stages) {
-          stage = 0;
-          phase ^= 1u;
-        }
-        alo = a.desc_lo0 + (uint32_t)stage * a.stage_step;
-      } else {
-        ++jg;
+      if (++stage == a.n_stages) {
+        stage = 0;
+        phase ^= 1u;
       }
     }
     if (++as == 2) {
@@ -194,7 +187,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   // from the constant bank on every use), and the timing-ablation branches exist only in the kDebug instantiation.
   const int dbg = kDebug ? p.debug : 0;
   constexpr int pcs = kPair ? 2 : 1;  // CTAs per work item
-  const int msub = kPair ? 1 : p.msub;
+  const int msub = p.msub;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
   // layout: [stages x group x (A | B_hi | B_lo)] [2 staged output boxes] [scale cout | shift cout] [barriers] [tmem slot]
@@ -249,6 +242,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   if (kPair) cluster_sync_all();  // the peer's barriers are initialised before any load or commit can reach them
   tc_fence_after();
+  if (p.pdl) {  // everything above overlapped the previous kernel's tail; its outputs are needed from here on
+    pdl_wait();
+    pdl_trigger();
+  }
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int crank = kPair ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / pcs, num_clusters = gridDim.x / pcs;
@@ -271,7 +268,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ===================================================================== TMA producer
     const int group = p.group, n_stages = p.stages, nt = p.nt;
     const uint32_t stage_bytes = (uint32_t)p.stage_bytes, kb_bytes = (uint32_t)p.kb_bytes;
-    const bool two_loads = p.passes == 2 && !p.onebox;
+    const bool two_loads = p.passes == 2 && !p.onebox, onebox = p.onebox != 0, two_pass = p.passes == 2;
     const int half_rows = p.nt / 2;
     // pair: every load of both CTAs completes on the leader's full barrier, which alone carries the expect_tx
     const uint32_t full_base = kPair ? mapa_u32(bar_base, 0) : bar_base;
@@ -293,51 +290,49 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         hc[sub] = oy * p.stride - p.pad_h;
       }
       const int brow = n_tile * 2 * nt;  // first hi row of this tile's weight block; the lo rows follow
-      int jg = 0;
-      uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-      for (int kb = 0; kb < kb_per_tile; ++kb) {
-        if (jg == 0) timed_wait<kDebug>(empty_bar(stage), phase ^ 1u, dbg, w_empty);
-        if (kDebug) ++n_kb;
-        const uint4 e = kbtab[kb];
-        const uint32_t fb = full_base + 8u * (uint32_t)stage;
+      // one iteration per pipeline stage (1-2 K blocks): one wait, one election, one expect_tx
+      for (int kb0 = 0; kb0 < kb_per_tile; kb0 += group) {
+        const int n = min(group, kb_per_tile - kb0);
+        timed_wait<kDebug>(empty_bar(stage), phase ^ 1u, dbg, w_empty);
+        if (kDebug) n_kb += (unsigned long long)n;
         if (elect_one()) {
-          if (jg == 0 && crank == 0) {
-            const uint32_t g = (uint32_t)min(group, kb_per_tile - kb);
-            if (kb_tx) mbar_expect_tx(full_bar(stage), g * kb_tx * (uint32_t)pcs); else mbar_arrive(full_bar(stage));
+          const uint32_t fb = full_base + 8u * (uint32_t)stage;
+          if (crank == 0) {
+            if (kb_tx) mbar_expect_tx(full_bar(stage), (uint32_t)n * kb_tx * (uint32_t)pcs); else mbar_arrive(full_bar(stage));
           }
-          if (!(dbg & 1)) {
-            if (kPair) {
-              tma_load_im2col_pair(&tm_a, sa, fb, (int)e.x, wc[0], hc[0], img[0], (uint16_t)(e.y & 0xffffu), (uint16_t)(e.y >> 16));
-            } else {
-              tma_load_im2col(&tm_a, sa, fb, (int)e.x, wc[0], hc[0], img[0], (uint16_t)(e.y & 0xffffu), (uint16_t)(e.y >> 16));
-              if (msub == 2)
-                tma_load_im2col(&tm_a, sa + a_bytes, fb, (int)e.x, wc[1], hc[1], img[1], (uint16_t)(e.y & 0xffffu), (uint16_t)(e.y >> 16));
-            }
-          }
-          if (!(dbg & 2)) {
-            if (kPair) {
-              if (wide2) {  // N = 2 nt: the leader holds the W_hi rows, its peer the W_lo rows
-                tma_load_2d_pair(&tm_b, sa + a_bytes, fb, (int)e.z, brow + crank * nt);
-              } else {      // N = nt per pass: rows [0, nt / 2) of each plane in the leader, the rest in its peer
-                tma_load_2d_pair(&tm_bs, sa + a_bytes, fb, (int)e.z, brow + crank * half_rows);
-                if (p.passes == 2) tma_load_2d_pair(&tm_bs, sa + a_bytes + half_bytes, fb, (int)e.z, brow + nt + crank * half_rows);
+          uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+          for (int j = 0; j < n; ++j, sa += kb_bytes) {
+            const uint4 e = kbtab[kb0 + j];
+            const uint16_t ow = (uint16_t)(e.y & 0xffffu), oh = (uint16_t)(e.y >> 16);
+            if (!(kDebug && (dbg & 1))) {
+              if (kPair) {
+                tma_load_im2col_pair(&tm_a, sa, fb, (int)e.x, wc[0], hc[0], img[0], ow, oh);
+                if (msub == 2) tma_load_im2col_pair(&tm_a, sa + a_bytes, fb, (int)e.x, wc[1], hc[1], img[1], ow, oh);
+              } else {
+                tma_load_im2col(&tm_a, sa, fb, (int)e.x, wc[0], hc[0], img[0], ow, oh);
+                if (msub == 2) tma_load_im2col(&tm_a, sa + a_bytes, fb, (int)e.x, wc[1], hc[1], img[1], ow, oh);
               }
-            } else if (!two_loads) {
-              tma_load_2d(p.onebox ? &tm_b2 : &tm_b, sa + a_tot, fb, (int)e.z, brow);  // onebox: hi and lo rows together
-            } else {
-              tma_load_2d(&tm_b, sa + a_tot, fb, (int)e.z, brow);
-              tma_load_2d(&tm_b, sa + a_tot + b_bytes, fb, (int)e.z, brow + nt);
+            }
+            if (!(kDebug && (dbg & 2))) {
+              if (kPair) {
+                if (wide2) {  // N = 2 nt: the leader holds the W_hi rows, its peer the W_lo rows
+                  tma_load_2d_pair(&tm_b, sa + a_tot, fb, (int)e.z, brow + crank * nt);
+                } else {      // N = nt per pass: rows [0, nt / 2) of each plane in the leader, the rest in its peer
+                  tma_load_2d_pair(&tm_bs, sa + a_tot, fb, (int)e.z, brow + crank * half_rows);
+                  if (two_pass) tma_load_2d_pair(&tm_bs, sa + a_tot + half_bytes, fb, (int)e.z, brow + nt + crank * half_rows);
+                }
+              } else if (!two_loads) {
+                tma_load_2d(onebox ? &tm_b2 : &tm_b, sa + a_tot, fb, (int)e.z, brow);  // onebox: hi and lo rows together
+              } else {
+                tma_load_2d(&tm_b, sa + a_tot, fb, (int)e.z, brow);
+                tma_load_2d(&tm_b, sa + a_tot + b_bytes, fb, (int)e.z, brow + nt);
+              }
             }
           }
         }
-        sa += kb_bytes;
-        if (++jg == group || kb == kb_per_tile - 1) {
-          jg = 0;
-          if (++stage == n_stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
-          sa = smem_base + (uint32_t)stage * stage_bytes;
+        if (++stage == n_stages) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
@@ -375,10 +370,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     ma.dbg_out = p.dbg_out;
     // one instantiation per (W_lo as a second MMA, second M tile): the loop body is straight-line code
     if (two_mma) {
-      if (!kPair && msub == 2) mma_loop<kPair, kDebug, true, true>(ma, kbtab);
+      if (msub == 2) mma_loop<kPair, kDebug, true, true>(ma, kbtab);
       else mma_loop<kPair, kDebug, true, false>(ma, kbtab);
     } else {
-      if (!kPair && msub == 2) mma_loop<kPair, kDebug, false, true>(ma, kbtab);
+      if (msub == 2) mma_loop<kPair, kDebug, false, true>(ma, kbtab);
       else mma_loop<kPair, kDebug, false, false>(ma, kbtab);
     }
   } else if (warp >= 2) {
@@ -558,6 +553,13 @@ static CUtensorMapSwizzle swizzle_of(int kc) {
   return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
+// Programmatic dependent launch between consecutive tcgen05 conv kernels (default on; TISE_PDL=0 disables).
+bool umma_pdl_mode() {
+  static int pdl = -1;
+  if (pdl < 0) pdl = (getenv("TISE_PDL") && atoi(getenv("TISE_PDL")) == 0) ? 0 : 1;
+  return pdl != 0;
+}
+
 // CTA-pair (cta_group::2) execution is the default; TISE_UMMA_PAIR=0 selects the single-CTA form of the kernel.
 bool umma_pair_mode() {
   static int pair = -1;
@@ -685,6 +687,9 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   if (msub_env < 0) msub_env = getenv("TISE_UMMA_MSUB") ? atoi(getenv("TISE_UMMA_MSUB")) : 0;
   int msub = 1;
   if (cs == 1 && 2 * p.nt <= kAccumCols && cdiv(m_tiles, 2) * p.n_ntiles >= ctx->num_sms) msub = 2;  // enough work items for every SM
+  // pairs: two M tiles per CTA (512 output pixels per work item) where a K block would otherwise hold < 300 tensor
+  // cycles against ~600 cycles of producer / MMA-issue instructions (nt <= 64: the 5x5 convolutions)
+  if (cs == 2 && passes == 2 && 4 * p.nt <= kAccumCols && cdiv(m_tiles, 4) * p.n_ntiles >= ctx->num_sms / 2) msub = 2;
   if (msub_env == 1) msub = 1;
   p.msub = msub;
   p.onebox = (passes == 2 && 2 * p.nt <= 256) ? 1 : 0;
@@ -693,7 +698,7 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   // on the batch size
   p.wide = (p.onebox && (cs == 2 ? 2 : 4) * p.nt <= kAccumCols) ? 1 : 0;
   p.acc_cols = p.wide ? 2 * p.nt : p.nt;
-  p.kb_bytes = cs == 2 ? p.a_bytes + passes * (p.nt / 2) * L.kc * 2 : msub * p.a_bytes + passes * p.b_bytes;
+  p.kb_bytes = cs == 2 ? msub * p.a_bytes + passes * (p.nt / 2) * L.kc * 2 : msub * p.a_bytes + passes * p.b_bytes;
   static int debug_env = -1;
   if (debug_env < 0) debug_env = getenv("TISE_UMMA_DEBUG") ? atoi(getenv("TISE_UMMA_DEBUG")) : 0;
   p.debug = debug_env;
@@ -740,13 +745,19 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = (size_t)smem_limit;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  p.pdl = umma_pdl_mode() && !ctx->profiling ? 1 : 0;  // (per-launch profiling events would serialise the stream anyway)
+  if (p.pdl) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   // the schedule is static (persistent CTAs), so the grid must not exceed the clusters that can be co-resident
   static int max_clusters[5] = {0, 0, 0, 0, 0};
   if (!max_clusters[cs]) {

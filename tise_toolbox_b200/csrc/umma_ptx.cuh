@@ -103,6 +103,12 @@ __device__ __forceinline__ void tma_load_im2col(const CUtensorMap* map, uint32_t
       "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while
+// its predecessor in the stream is still running; pdl_wait() blocks until the predecessor has completed and its writes
+// are visible (everything before it -- barrier init, TMEM allocation, tables -- overlaps the predecessor's tail), and
+// pdl_trigger() lets the successor's CTAs take SMs as soon as this kernel's CTAs retire from them.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // One lane of a converged warp (elect.sync): true in exactly one lane.
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
