@@ -81,14 +81,14 @@ __global__ void avgpool3s1p1_kernel(const __half* __restrict__ in, int n, int h,
 // RAW (pre-BN) fp16 output of that convolution (pf = 32..192 channels instead of the block's 192..2048), so
 // avg_pool2d(3,1,1)(count_include_pad) + BN scale/shift + ReLU is applied here.  Exact: conv1x1 and the
 // zero-padded average are both linear and the convolution has no bias.
-// One thread produces a run of `xs` horizontally adjacent output pixels of one row for 8 channels, sliding a window of
-// three column sums (each the sum of the <= 3 valid rows): 3 (xs + 2) / xs loads per output instead of 9, and 32-bit
-// index arithmetic (the host checks the range).  Consecutive threads take consecutive channel groups (coalesced).
-template <bool kF32>
-__global__ void __launch_bounds__(256) avgpool_bn_kernel(const __half* __restrict__ in, int n, int h, int w, int c8, int xs,
-                                                         int segs, const float* __restrict__ scale,
-                                                         const float* __restrict__ shift, void* __restrict__ out,
-                                                         int out_stride) {
+// One thread produces a run of kXs horizontally adjacent output pixels of one row for 8 channels from the 3 x (kXs + 2)
+// input window: 3 (kXs + 2) / kXs loads per output instead of 9.  The window loop is fully unrolled with predicated
+// loads, so all loads of a thread are in flight together (the looped version ran at ~2 TB/s, latency-bound).
+// 32-bit index arithmetic (the host checks the range); consecutive threads take consecutive channel groups (coalesced).
+template <bool kF32, int kXs>
+__global__ void __launch_bounds__(256) avgpool_bn_kernel(const __half* __restrict__ in, int n, int h, int w, int c8, int segs,
+                                                         const float* __restrict__ scale, const float* __restrict__ shift,
+                                                         void* __restrict__ out, int out_stride) {
   const unsigned total = (unsigned)n * h * segs * c8;
   const int c = c8 * 8;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -98,41 +98,44 @@ __global__ void __launch_bounds__(256) avgpool_bn_kernel(const __half* __restric
     p /= (unsigned)segs;
     const int oy = (int)(p % (unsigned)h);
     const int img = (int)(p / (unsigned)h);
-    const int x0 = sg * xs, x1 = min(x0 + xs, w);
+    const int x0 = sg * kXs;
+    const __half* row = in + ((size_t)img * h + oy) * w * c + g * 8;
+    const bool up = oy > 0, down = oy + 1 < h;
+    // column sums (the <= 3 valid rows) of columns x0 - 1 ... x0 + kXs
+    float cs[kXs + 2][8];
+#pragma unroll
+    for (int t = 0; t < kXs + 2; ++t) {
+      const int x = x0 - 1 + t;
+      const bool okx = x >= 0 && x < w;
+      uint4 v[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const bool ok = okx && (r == 1 || (r == 0 ? up : down));
+        v[r] = ok ? __ldg(reinterpret_cast<const uint4*>(row + (ptrdiff_t)(r - 1) * w * c + (ptrdiff_t)x * c)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = __half22float2(reinterpret_cast<const __half2*>(&v[0])[j]);
+        const float2 b = __half22float2(reinterpret_cast<const __half2*>(&v[1])[j]);
+        const float2 d = __half22float2(reinterpret_cast<const __half2*>(&v[2])[j]);
+        cs[t][2 * j] = a.x + b.x + d.x;
+        cs[t][2 * j + 1] = a.y + b.y + d.y;
+      }
+    }
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sc[j] = __ldg(scale + g * 8 + j) * (1.0f / 9.0f);
       sh[j] = __ldg(shift + g * 8 + j);
     }
-    const __half* row = in + ((size_t)img * h + oy) * w * c + g * 8;
-    const bool up = oy > 0, down = oy + 1 < h;
-    float c0[8], c1[8], c2[8];  // column sums at x - 2, x - 1, x
 #pragma unroll
-    for (int j = 0; j < 8; ++j) c0[j] = c1[j] = 0.f;
-    for (int x = x0 - 1; x <= x1; ++x) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) c2[j] = 0.f;
-      if (x >= 0 && x < w) {
-        const __half* px = row + (size_t)x * c;
-#pragma unroll
-        for (int r = -1; r <= 1; ++r) {
-          if ((r < 0 && !up) || (r > 0 && !down)) continue;
-          const uint4 v = *reinterpret_cast<const uint4*>(px + (ptrdiff_t)r * w * c);
-          const __half2* hv = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(hv[j]);
-            c2[2 * j] += f.x;
-            c2[2 * j + 1] += f.y;
-          }
-        }
-      }
-      if (x > x0) {  // output pixel x - 1
+    for (int t = 0; t < kXs; ++t) {
+      const int x = x0 + t;
+      if (x < w) {
         float y8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y8[j] = fmaxf(fmaf(c0[j] + c1[j] + c2[j], sc[j], sh[j]), 0.f);
-        const size_t o = (((size_t)img * h + oy) * w + (x - 1)) * out_stride + g * 8;
+        for (int j = 0; j < 8; ++j) y8[j] = fmaxf(fmaf(cs[t][j] + cs[t + 1][j] + cs[t + 2][j], sc[j], sh[j]), 0.f);
+        const size_t o = (((size_t)img * h + oy) * w + x) * out_stride + g * 8;
         if (kF32) {
           float4* dst = reinterpret_cast<float4*>((float*)out + o);
           dst[0] = make_float4(y8[0], y8[1], y8[2], y8[3]);
@@ -143,11 +146,6 @@ __global__ void __launch_bounds__(256) avgpool_bn_kernel(const __half* __restric
           for (int j = 0; j < 4; ++j) hh[j] = __floats2half2_rn(fminf(y8[2 * j], 65504.f), fminf(y8[2 * j + 1], 65504.f));
           *reinterpret_cast<uint4*>((__half*)out + o) = *reinterpret_cast<uint4*>(hh);
         }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        c0[j] = c1[j];
-        c1[j] = c2[j];
       }
     }
   }
@@ -193,15 +191,15 @@ int launch_avgpool3s1p1(tise_ctx* ctx, const __half* in, int n, int h, int w, in
 
 int launch_avgpool_bn(tise_ctx* ctx, const __half* in, int n, int h, int w, int c, const float* scale,
                       const float* shift, void* out, int out_stride, int out_f32, cudaStream_t st) {
-  const int segs = (w + 6) / 7, xs = (w + segs - 1) / segs;  // runs of <= 7 pixels
+  constexpr int kXs = 4;  // pixels per thread
+  const int segs = (w + kXs - 1) / kXs;
   const long long total = (long long)n * h * segs * (c / 8);
   if (total >= (1ll << 31)) return fail(ctx, TISE_ERR_INVALID, "avgpool_bn: batch too large (%lld work items)", total);
+  const int grid = grid_for(total, 256, ctx->num_sms);
   if (out_f32)
-    avgpool_bn_kernel<true><<<grid_for(total, 256, ctx->num_sms), 256, 0, st>>>(in, n, h, w, c / 8, xs, segs, scale, shift,
-                                                                              out, out_stride);
+    avgpool_bn_kernel<true, kXs><<<grid, 256, 0, st>>>(in, n, h, w, c / 8, segs, scale, shift, out, out_stride);
   else
-    avgpool_bn_kernel<false><<<grid_for(total, 256, ctx->num_sms), 256, 0, st>>>(in, n, h, w, c / 8, xs, segs, scale, shift,
-                                                                               out, out_stride);
+    avgpool_bn_kernel<false, kXs><<<grid, 256, 0, st>>>(in, n, h, w, c / 8, segs, scale, shift, out, out_stride);
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;
 }

@@ -131,6 +131,7 @@ __global__ void resize_v_kernel(const uint8_t* __restrict__ tmp, const ImgDesc* 
 // rows fit in shared memory (always for up-scaling; the two-kernel path above remains for big down-scales).
 constexpr int kStripRows = 13;  // 299 = 23 * 13
 constexpr int kFusedSmem = 96 * 1024;
+constexpr int kTmpPitch = 900;  // bytes per row of the uint8 temporary in shared memory (897 rounded up to words)
 __global__ void __launch_bounds__(256) resize_fused_kernel(const uint8_t* __restrict__ imgs, const ImgDesc* __restrict__ descs,
                                                            const int* __restrict__ tabs, int kmax,
                                                            uint8_t* __restrict__ out) {
@@ -150,8 +151,8 @@ __global__ void __launch_bounds__(256) resize_fused_kernel(const uint8_t* __rest
   }
   const int n_in = y_hi - y_lo;
   const int in_row = d.w * 3, out_row = kOutSize * 3;
-  uint8_t* s_tmp = sm;                                   // [n_in][897]   horizontally resampled rows
-  uint8_t* s_in = sm + (((size_t)n_in * out_row + 15) & ~(size_t)15);  // [n_in][w * 3]  raw input rows
+  uint8_t* s_tmp = sm;                                          // [n_in][kTmpPitch]   horizontally resampled rows
+  uint8_t* s_in = sm + (((size_t)n_in * kTmpPitch + 15) & ~(size_t)15);  // [n_in][w * 3]  raw input rows
   const uint8_t* src = imgs + d.src_off + (size_t)y_lo * in_row;
   const int in_bytes = n_in * in_row;
   if (hpass) {
@@ -162,33 +163,58 @@ __global__ void __launch_bounds__(256) resize_fused_kernel(const uint8_t* __rest
       for (int i = threadIdx.x; i < in_bytes; i += blockDim.x) s_in[i] = __ldg(src + i);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_in * out_row; i += blockDim.x) {
-      const int y = i / out_row, j = i - y * out_row;
-      const int xx = j / 3, c = j - xx * 3;
+    // one thread per (row, output pixel): bounds and weights are fetched once for the 3 channels
+    for (int i = threadIdx.x; i < n_in * kOutSize; i += blockDim.x) {
+      const int y = i / kOutSize, xx = i - y * kOutSize;
       const int xmin = bounds_x[xx * 2], cnt = bounds_x[xx * 2 + 1];
       const int* k = kk_x + xx * kmax;
-      const uint8_t* row = s_in + y * in_row + xmin * 3 + c;
-      int acc = 1 << (kPrecisionBits - 1);
-      for (int x = 0; x < cnt; ++x) acc += (int)row[x * 3] * k[x];
-      s_tmp[i] = clip8(acc);
+      const uint8_t* px = s_in + y * in_row + xmin * 3;
+      int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+      for (int x = 0; x < cnt; ++x) {
+        const int kw = k[x];
+        a0 += (int)px[x * 3 + 0] * kw;
+        a1 += (int)px[x * 3 + 1] * kw;
+        a2 += (int)px[x * 3 + 2] * kw;
+      }
+      uint8_t* o = s_tmp + y * kTmpPitch + xx * 3;
+      o[0] = clip8(a0);
+      o[1] = clip8(a1);
+      o[2] = clip8(a2);
     }
   } else {  // Pillow skips the horizontal pass: the rows are already 897 bytes wide
-    for (int i = threadIdx.x; i < in_bytes; i += blockDim.x) s_tmp[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < in_bytes; i += blockDim.x) {
+      const int y = i / out_row;
+      s_tmp[y * kTmpPitch + (i - y * out_row)] = __ldg(src + i);
+    }
   }
   __syncthreads();
+  // one thread per (output row, group of 4 consecutive bytes): one 32-bit shared-memory load per filter tap
   uint8_t* dst = out + ((size_t)blockIdx.y * kOutSize + r0) * out_row;
-  for (int i = threadIdx.x; i < kStripRows * out_row; i += blockDim.x) {
-    const int yy = i / out_row, j = i - yy * out_row;
+  constexpr int kGroups = kTmpPitch / 4;
+  for (int i = threadIdx.x; i < kStripRows * kGroups; i += blockDim.x) {
+    const int yy = i / kGroups, j = (i - yy * kGroups) * 4;
+    uint32_t packed;
     if (!vpass) {
-      dst[i] = s_tmp[i];
-      continue;
+      packed = *reinterpret_cast<const uint32_t*>(s_tmp + yy * kTmpPitch + j);
+    } else {
+      const int ymin = bounds_y[(r0 + yy) * 2], cnt = bounds_y[(r0 + yy) * 2 + 1];
+      const int* k = kk_y + (r0 + yy) * kmax;
+      const uint8_t* col = s_tmp + (ymin - y_lo) * kTmpPitch + j;
+      int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0, a3 = a0;
+      for (int y = 0; y < cnt; ++y) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(col + y * kTmpPitch);
+        const int kw = k[y];
+        a0 += (int)(v & 0xffu) * kw;
+        a1 += (int)((v >> 8) & 0xffu) * kw;
+        a2 += (int)((v >> 16) & 0xffu) * kw;
+        a3 += (int)(v >> 24) * kw;
+      }
+      packed = (uint32_t)clip8(a0) | ((uint32_t)clip8(a1) << 8) | ((uint32_t)clip8(a2) << 16) | ((uint32_t)clip8(a3) << 24);
     }
-    const int ymin = bounds_y[(r0 + yy) * 2], cnt = bounds_y[(r0 + yy) * 2 + 1];
-    const int* k = kk_y + (r0 + yy) * kmax;
-    const uint8_t* col = s_tmp + (ymin - y_lo) * out_row + j;
-    int acc = 1 << (kPrecisionBits - 1);
-    for (int y = 0; y < cnt; ++y) acc += (int)col[y * out_row] * k[y];
-    dst[i] = clip8(acc);
+    uint8_t* o = dst + yy * out_row + j;  // rows of 897 bytes: not word-aligned in general
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (j + b < out_row) o[b] = (uint8_t)(packed >> (8 * b));
   }
 }
 
@@ -280,7 +306,7 @@ extern "C" int tise_resize_u8(tise_ctx* ctx, const uint8_t* d_imgs, const int64_
   {
     const double vscale = max_h > kOutSize ? (double)max_h / kOutSize : 1.0;
     const int n_in_max = (int)(kStripRows * ((double)max_h / kOutSize) + 2.0 * vscale + 3.0);
-    const size_t need = (((size_t)n_in_max * kOutSize * 3 + 15) & ~(size_t)15) + (size_t)n_in_max * max_w * 3 + 16;
+    const size_t need = (((size_t)n_in_max * kTmpPitch + 15) & ~(size_t)15) + (size_t)n_in_max * max_w * 3 + 16;
     static int fused_env = -1;
     if (fused_env < 0) fused_env = getenv("TISE_RESIZE_FUSED") ? atoi(getenv("TISE_RESIZE_FUSED")) : 1;
     if (fused_env && need <= (size_t)kFusedSmem) {

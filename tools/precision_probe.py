@@ -55,6 +55,11 @@ def install(net, mode):
     """mode: 'f32' | 'f16a' (fp16 activations, hi+lo fp16 weights) | 'bf16x3' | 'f16' | 'bf16'."""
     first = net.Conv2d_1a_3x3.conv
     stem = {id(net.Conv2d_2a_3x3.conv), id(net.Conv2d_2b_3x3.conv), id(net.Conv2d_3b_1x1.conv), id(net.Conv2d_4a_3x3.conv)}
+    if mode == "f16in":  # the product path with the stem conv on the tensor cores too: its input rounded to fp16 as well
+        w = first.weight.data
+        hi = w.half().float(); lo = (w - hi).half().float(); first.weight.data = hi + lo
+        first.register_forward_pre_hook(lambda m, inp: (inp[0].half().float(),))
+        mode = "f16a"
     for mod in net.modules():
         if isinstance(mod, torch.nn.Conv2d) and mod is not first:
             w = mod.weight.data
