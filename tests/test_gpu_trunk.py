@@ -57,7 +57,9 @@ def test_float_input_path_matches_u8_path(engine, batch, oracle_blocks):
     x = oracle_blocks[0]  # float32 [n,3,299,299], already normalised by the oracle
     a = engine.features_from_float(x.cuda()).cpu().numpy()
     b = engine.features(batch.cuda()).cpu().numpy()
-    assert np.array_equal(a, b)  # the LUT is bit-exact, so both inputs are the same floats
+    # Same floats in (the LUT is bit-exact), but the float path runs Conv2d_1a on the CUDA cores in fp32 and the uint8
+    # path on the tensor cores (input and weights as fp16 hi + lo pairs): equal up to the fp16 rounding of activations.
+    assert _rel_l2(a, b) <= 3e-4
 
 
 def test_micro_batching_is_invisible(engine, batch):

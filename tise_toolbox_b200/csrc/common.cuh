@@ -151,6 +151,11 @@ int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const
 int launch_stem(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, const float* d_w /*[27][32]*/,
                 const float* d_scale, const float* d_shift, __half* d_out, cudaStream_t st);
 
+// stem_umma.cu : the same layer on the tensor cores (uint8 input only): thread-built A tiles, resident weights
+void pack_stem_umma(const float* w_k_major /*[27][32]*/, float* scale /*[32], in/out*/, __half* out /*[64][64]*/);
+int launch_stem_umma(tise_ctx* ctx, const uint8_t* d_u8, int n, const __half* d_w16, const float* d_scale,
+                     const float* d_shift, __half* d_out, cudaStream_t st);
+
 // pool.cu
 // in_rows / in_pitch: physical rows per image and pixels per row of the input (>= h, w: flat-conv outputs keep the
 // padded grid); 0 = dense

@@ -243,19 +243,18 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           yv[1] = fmaf(yv[1], sc.y, sh.y);
           yv[2] = fmaf(yv[2], sc.z, sh.z);
           yv[3] = fmaf(yv[3], sc.w, sh.w);
-          if (relu) {
-            yv[0] = fmaxf(yv[0], 0.f);
-            yv[1] = fmaxf(yv[1], 0.f);
-            yv[2] = fmaxf(yv[2], 0.f);
-            yv[3] = fmaxf(yv[3], 0.f);
-          }
           if (!valid) yv[0] = yv[1] = yv[2] = yv[3] = 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          st_shared_v4(buf + wr_off + (((uint32_t)j ^ wr_swz) << 4), pack_h2(f[8 * j], f[8 * j + 1]),
-                       pack_h2(f[8 * j + 2], f[8 * j + 3]), pack_h2(f[8 * j + 4], f[8 * j + 5]),
-                       pack_h2(f[8 * j + 6], f[8 * j + 7]));
+        for (int j = 0; j < 4; ++j) {  // ReLU and saturation are part of the conversion
+          const uint32_t dst = buf + wr_off + (((uint32_t)j ^ wr_swz) << 4);
+          if (relu)
+            st_shared_v4(dst, pack_h2_sat<true>(f[8 * j], f[8 * j + 1]), pack_h2_sat<true>(f[8 * j + 2], f[8 * j + 3]),
+                         pack_h2_sat<true>(f[8 * j + 4], f[8 * j + 5]), pack_h2_sat<true>(f[8 * j + 6], f[8 * j + 7]));
+          else
+            st_shared_v4(dst, pack_h2_sat<false>(f[8 * j], f[8 * j + 1]), pack_h2_sat<false>(f[8 * j + 2], f[8 * j + 3]),
+                         pack_h2_sat<false>(f[8 * j + 4], f[8 * j + 5]), pack_h2_sat<false>(f[8 * j + 6], f[8 * j + 7]));
+        }
         epi_bar(1 + grp);
         const int ccol = c0 + st_chunk * 8;
         if (ccol < nt) {

@@ -457,13 +457,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           __syncwarp();
           if (lane == 0) release_accum(as);
         }
-        // scale / shift / ReLU (the ReLU flag can change every 16 channels: segment boundaries)
+        // scale / shift / ReLU (the ReLU flag can change every 16 channels: segment boundaries); for fp16 outputs the
+        // ReLU is part of the conversion instruction below
+        bool relu_h[2] = {false, false};
 #pragma unroll
         for (int h = 0; h < W / 16; ++h) {
           const int col = co0 + c0 + 16 * h;
           int sg = 0;
           while (sg < kMaxSegs - 1 && col >= p.seg_end[sg]) ++sg;
           const bool relu = p.seg_relu[sg] != 0;
+          relu_h[h] = relu;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 sc = *reinterpret_cast<const float4*>(s_scale + co0 + c0 + 16 * h + 4 * q);
@@ -473,7 +476,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             y[1] = fmaf(y[1], sc.y, sh.y);
             y[2] = fmaf(y[2], sc.z, sh.z);
             y[3] = fmaf(y[3], sc.w, sh.w);
-            if (relu) {
+            if (kF32 && relu) {
               y[0] = fmaxf(y[0], 0.f);
               y[1] = fmaxf(y[1], 0.f);
               y[2] = fmaxf(y[2], 0.f);
@@ -487,9 +490,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (kF32)
             st_shared_v4(dst, __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
                          __float_as_uint(f[4 * j + 3]));
+          else if (relu_h[(8 * j) / 16])
+            st_shared_v4(dst, pack_h2_sat<true>(f[8 * j], f[8 * j + 1]), pack_h2_sat<true>(f[8 * j + 2], f[8 * j + 3]),
+                         pack_h2_sat<true>(f[8 * j + 4], f[8 * j + 5]), pack_h2_sat<true>(f[8 * j + 6], f[8 * j + 7]));
           else
-            st_shared_v4(dst, pack_h2(f[8 * j], f[8 * j + 1]), pack_h2(f[8 * j + 2], f[8 * j + 3]),
-                         pack_h2(f[8 * j + 4], f[8 * j + 5]), pack_h2(f[8 * j + 6], f[8 * j + 7]));
+            st_shared_v4(dst, pack_h2_sat<false>(f[8 * j], f[8 * j + 1]), pack_h2_sat<false>(f[8 * j + 2], f[8 * j + 3]),
+                         pack_h2_sat<false>(f[8 * j + 4], f[8 * j + 5]), pack_h2_sat<false>(f[8 * j + 6], f[8 * j + 7]));
         }
         epi_bar(1 + grp);  // box staged; also orders the reads of this buffer (box_it - 2) before these writes
         // store phase: thread -> (chunk, 4 rows); 4 consecutive lanes write one pixel's 64 contiguous bytes

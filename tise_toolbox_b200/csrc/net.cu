@@ -511,6 +511,13 @@ int net_load(tise_ctx* ctx, const tise_weight_desc* tensors, int n_tensors, int 
     TISE_CUDA(ctx, cudaMemcpy(net->d_stem_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
     TISE_CUDA(ctx, cudaMemcpy(net->d_stem_scale, scale.data(), 32 * 4, cudaMemcpyHostToDevice));
     TISE_CUDA(ctx, cudaMemcpy(net->d_stem_shift, shift.data(), 32 * 4, cudaMemcpyHostToDevice));
+    std::vector<__half> w16(64 * 64);
+    std::vector<float> scale16(scale);
+    pack_stem_umma(w.data(), scale16.data(), w16.data());
+    if ((rc = dev_alloc(ctx, &net->device_allocs, (void**)&net->d_stem_w16, w16.size() * 2))) return rc;
+    if ((rc = dev_alloc(ctx, &net->device_allocs, (void**)&net->d_stem_scale16, 32 * 4))) return rc;
+    TISE_CUDA(ctx, cudaMemcpy(net->d_stem_w16, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
+    TISE_CUDA(ctx, cudaMemcpy(net->d_stem_scale16, scale16.data(), 32 * 4, cudaMemcpyHostToDevice));
   }
   // declare-only walks: create every layer, size the workspace per tap
   for (int tap = 0; tap < 4; ++tap) {
@@ -587,6 +594,9 @@ int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, i
   Plan* plan = nullptr;
   int rc = get_plan(ctx, d_ws, n, tap, &plan);
   if (rc) return rc;
+  static int stem_env = -1;
+  if (stem_env < 0) stem_env = getenv("TISE_STEM_UMMA") ? atoi(getenv("TISE_STEM_UMMA")) : 1;
+  const bool stem_umma = ctx->conv_impl == TISE_CONV_UMMA && ctx->passes == 2 && stem_env != 0;
   for (Step& s : plan->steps) {
     tise_ctx::ProfRec rec{s.kind == STEP_FLATCONV ? (int)STEP_CONV : (int)s.kind, nullptr, nullptr, 0.0, {0}};
     if (ctx->profiling) {
@@ -608,7 +618,10 @@ int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, i
     }
     switch (s.kind) {
       case STEP_STEM:
-        rc = launch_stem(ctx, d_u8, d_f32, n, net->d_stem_w, net->d_stem_scale, net->d_stem_shift, (__half*)s.out, st);
+        if (d_u8 && stem_umma)  // tensor-core stem (uint8 input, tcgen05 engine, two passes); else the fp32 CUDA-core kernel
+          rc = launch_stem_umma(ctx, d_u8, n, net->d_stem_w16, net->d_stem_scale16, net->d_stem_shift, (__half*)s.out, st);
+        else
+          rc = launch_stem(ctx, d_u8, d_f32, n, net->d_stem_w, net->d_stem_scale, net->d_stem_shift, (__half*)s.out, st);
         break;
       case STEP_CONV:
         if (ctx->conv_impl == TISE_CONV_UMMA) {

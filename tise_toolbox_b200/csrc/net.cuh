@@ -47,6 +47,8 @@ struct Net {
   float* d_stem_w = nullptr;                      // [27][32]
   float* d_stem_scale = nullptr;
   float* d_stem_shift = nullptr;
+  __half* d_stem_w16 = nullptr;                   // [64][64] tensor-core operand of the stem (stem_umma.cu)
+  float* d_stem_scale16 = nullptr;                // scale with the weight pre-scaling folded out
   float* d_fc_w = nullptr;  // [num_classes][2048]
   float* d_fc_b = nullptr;
   int num_classes = 0;

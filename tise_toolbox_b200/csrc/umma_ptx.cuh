@@ -200,6 +200,15 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// fp32 pair -> packed fp16 pair (a in the low half) with round-to-nearest, saturation to +-65504 and, for kRelu, ReLU,
+// all in ONE conversion instruction (the epilogues are instruction-bound: this replaces max + min + min + cvt).
+template <bool kRelu>
+__device__ __forceinline__ uint32_t pack_h2_sat(float a, float b) {
+  uint32_t d;
+  if (kRelu) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
