@@ -33,6 +33,7 @@ constexpr int kSuSmem = 1024 + kSuStages * kSuATile + kSuBTile + 4 * kSuEpiBuf +
 
 struct StemUmmaParams {
   const uint8_t* u8;      // [n][299][299][3]
+  const uint8_t* u8_end;  // one past its last byte
   const float* lut;       // [3][256]
   const __half* w16;      // [64][64] rows as described above (unswizzled)
   const float* scale;     // [32] folded BN scale x 2^-e of the weight pre-scaling
@@ -123,7 +124,15 @@ __global__ void __launch_bounds__(kSuThreads, 1) stem_umma_kernel(const StemUmma
           const uint8_t* rp = base + (size_t)r * (kOutSize * 3);
           const uint32_t off = (uint32_t)((uintptr_t)rp & 3u);
           const uint32_t* wp = reinterpret_cast<const uint32_t*>(rp - off);
-          const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+          const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
+          uint32_t w2 = 0;
+          if (reinterpret_cast<const uint8_t*>(wp + 3) <= p.u8_end) {
+            w2 = __ldg(wp + 2);
+          } else {  // the very last pixels of the batch: never read past the end of the caller's buffer
+            const uint8_t* bp = reinterpret_cast<const uint8_t*>(wp + 2);
+            for (int b = 0; b < 4; ++b)
+              if (bp + b < p.u8_end) w2 |= (uint32_t)__ldg(bp + b) << (8 * b);
+          }
           const uint32_t sel = 0x3210u + 0x1111u * off;  // bytes off .. off + 3 of a register pair
           const uint32_t b0 = __byte_perm(w0, w1, sel), b1 = __byte_perm(w1, w2, sel), b2 = __byte_perm(w2, 0u, sel);
 #pragma unroll
@@ -282,6 +291,7 @@ int launch_stem_umma(tise_ctx* ctx, const uint8_t* d_u8, int n, const __half* d_
   }
   StemUmmaParams p;
   p.u8 = d_u8;
+  p.u8_end = d_u8 + (size_t)n * kOutSize * kOutSize * 3;
   p.lut = ctx->d_lut;
   p.w16 = d_w16;
   p.scale = d_scale;
