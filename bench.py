@@ -163,10 +163,20 @@ def run_reference(args, rank):
                              "sample": "%d steps x %d images, torch CPU fp32, os.cpu_count()=%s" % (args.steps, per_step, os.cpu_count())},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+# stdout carries exactly ONE line, the JSON result: everything else a library may print there (e.g. the "NCCL version"
+# banner on some boxes) is sent to stderr by pointing fd 1 at fd 2 for the lifetime of the process.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def _emit(text: str) -> None:
+    os.write(_RESULT_FD, (text + "\n").encode())
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -329,7 +339,7 @@ def main():
                                               "reference path), os.cpu_count()=%s" % (args.cpu_sample, secs, os.cpu_count())}
         if not args.no_frechet:
             line["frechet"] = frechet_latency(eng, res, world == 1 and not args.no_cpu_baseline)
-        print(json.dumps(line), flush=True)
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
