@@ -78,6 +78,36 @@ typedef struct {
  * Synchronises the device. */
 int tise_load_inception(tise_ctx* ctx, const tise_weight_desc* tensors, int n_tensors, int num_classes);
 
+/* ---- A1: PNG files -> RGB8 in HBM --------------------------------------------------------- */
+/* Replaces PIL.Image.open(f).convert("RGB") on the DataLoader workers
+ * (image_realism/FID/img_data.py:19-25, object_centric_inception_score.py:100-102) for PNG files:
+ * zlib inflate, scanline unfiltering and conversion to RGB run on the device, one warp per image,
+ * and the result is the packed uint8 HWC layout tise_resize_u8 / tise_crop_resize_u8 read.
+ * Handled: bit depth 8, non-interlaced, colour types 0 (grey), 2 (RGB), 3 (palette), 4 (grey+alpha),
+ * 6 (RGBA); alpha / tRNS are dropped exactly as convert("RGB") drops them.  Everything else
+ * (16-bit, 1/2/4-bit, Adam7, JPEG) is reported with supported = 0 and stays with the caller. */
+typedef struct {
+  int32_t width, height;
+  int32_t bit_depth, color_type, interlace;
+  int32_t channels;   /* bytes per pixel of the filtered scanlines */
+  int32_t n_idat;     /* IDAT chunks */
+  int32_t supported;  /* 1: tise_png_decode handles this file */
+  int64_t idat_bytes; /* compressed bytes in all IDAT chunks */
+} tise_png_info;
+/* Host only (no ctx, no device): parses the chunk list of one file.  TISE_ERR_INVALID if the bytes are
+ * not a well-formed PNG container. */
+int tise_png_probe(const uint8_t* h_file, int64_t file_bytes, tise_png_info* info);
+size_t tise_png_decode_workspace_bytes(const tise_png_info* infos, int n);
+/* n files packed in one buffer that exists both on the host (h_files, only chunk headers are read) and
+ * on the device (d_files, same bytes); file i = [h_file_off[i], + h_file_bytes[i]).  Image i is written as
+ * height x width x 3 uint8 at d_out + h_out_off[i].  d_status[i] (device int32): 0 ok, > 0 a corrupt
+ * stream (bad Huffman code, size mismatch, bad filter byte, Adler-32 mismatch ...), -1 not reached; the
+ * caller reads it back after the stream is synchronised.  Chunk CRCs are not verified.
+ * TISE_ERR_INVALID if a file is unsupported (see tise_png_probe). */
+int tise_png_decode(tise_ctx* ctx, const uint8_t* h_files, const uint8_t* d_files, const int64_t* h_file_off,
+                    const int64_t* h_file_bytes, int n, uint8_t* d_out, const int64_t* h_out_off,
+                    int32_t* d_status, void* d_ws, size_t ws_bytes, tise_stream stream);
+
 /* ---- A2: Pillow-exact bilinear resize to 299x299 ---------------------------------------- */
 /* transforms.Resize((299,299)) at fid_score.py:210 / object_centric_inception_score.py:89 and
  * scipy.misc.imresize at inception_score_star_coco.py:118, inception_score_star_bird.py:67:

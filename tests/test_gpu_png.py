@@ -1,0 +1,102 @@
+"""-m gpu: PNG ingest on the device through the C ABI (tise_png_decode), bit-exact against
+Pillow's ``Image.open(f).convert("RGB")`` -- the call it replaces (image_realism/FID/img_data.py:21)."""
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import restate
+from tise_toolbox_b200 import img_data, synth
+from tise_toolbox_b200.engine import ImageDecodeError
+
+from test_png_host import MODES, SIZES, png_bytes, smooth_image
+
+pytestmark = pytest.mark.gpu
+
+
+def _pil(blob):
+    return np.asarray(Image.open(io.BytesIO(blob)).convert("RGB"))
+
+
+def test_decode_mixed_batch_bit_exact(engine):
+    rng = np.random.default_rng(0)
+    blobs = []
+    for mode, c in MODES:
+        for (h, w) in SIZES:
+            a = smooth_image(rng, h, w, c)
+            if mode == "P":
+                im = Image.fromarray(a).convert("P", palette=Image.ADAPTIVE, colors=200)
+            elif mode == "L":
+                im = Image.fromarray(a[..., 0])
+            else:
+                im = Image.fromarray(a, mode)
+            blobs.append(png_bytes(im, compress_level=int(rng.integers(0, 10))))
+    jpg = io.BytesIO()
+    Image.fromarray(smooth_image(rng, 40, 50, 3)).save(jpg, "JPEG")
+    blobs.append(jpg.getvalue())  # not a PNG: decoded by PIL like the reference does, uploaded into the same pack
+    blobs.append(png_bytes(Image.fromarray(rng.integers(0, 65536, (20, 20)).astype(np.uint16))))  # 16-bit: host
+    packed = engine.decode_images(blobs)
+    assert len(packed) == len(blobs)
+    for i, b in enumerate(blobs):
+        ref = _pil(b)
+        got = packed[i].cpu().numpy()
+        assert got.shape == ref.shape and np.array_equal(got, ref), i
+    with pytest.raises(ValueError):
+        engine.decode_images([jpg.getvalue()], host_fallback=False)
+
+
+def test_decode_synthetic_set_and_resize(engine):
+    """cfg1-shaped inputs (256 x 256 RGB) + ragged crops: decode -> resize without a copy in between."""
+    imgs = [im.numpy() for im in synth.images(1, 0, 0, 24)]
+    sizes = synth.crop_sizes(8, 0, 8)
+    imgs += [synth.images(5, 1, i, 1, h, w)[0].numpy() for i, (h, w) in enumerate(sizes)]
+    blobs = [png_bytes(a) for a in imgs]
+    packed = engine.decode_images(blobs)
+    for i, a in enumerate(imgs):
+        assert np.array_equal(packed[i].cpu().numpy(), a), i
+    out = engine.resize(packed).cpu().numpy()
+    ref = np.stack([restate.pillow_resize_bilinear(a) for a in imgs])
+    assert np.array_equal(out, ref)
+
+
+def test_decode_large_batch_many_idat_chunks(engine):
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 256, (700, 900, 3), dtype=np.uint8)  # ~1.9 MB incompressible: dozens of IDAT chunks
+    blobs = [png_bytes(a), png_bytes(a[:1]), png_bytes(np.zeros((1000, 1000, 3), np.uint8))] + \
+            [png_bytes(smooth_image(rng, 64, 64, 3)) for _ in range(300)]
+    packed = engine.decode_images(blobs)
+    for i in (0, 1, 2, 3, 150, 302):
+        assert np.array_equal(packed[i].cpu().numpy(), _pil(blobs[i])), i
+
+
+def test_corrupt_png_is_reported(engine):
+    rng = np.random.default_rng(9)
+    good = png_bytes(smooth_image(rng, 64, 64, 3))
+    bad = bytearray(good)
+    idat = good.find(b"IDAT") + 4
+    bad[idat + 40] ^= 0x10
+    with pytest.raises(ImageDecodeError):
+        engine.decode_images([good, bytes(bad), good])
+    assert np.array_equal(engine.decode_images([good])[0].cpu().numpy(), _pil(good))  # the context stays usable
+    assert len(engine.decode_images([])) == 0
+
+
+def test_device_image_loader_order_and_drop_last(tmp_path, engine):
+    imgs = synth.images(3, 0, 0, 23)
+    for i, im in enumerate(imgs):
+        Image.fromarray(im.numpy()).save(str(tmp_path / ("img_%05d.png" % i)))
+    names = img_data.Dataset(str(tmp_path)).file_names
+    loader = img_data.DeviceImageLoader(names, engine, batch_size=5, drop_last=True)
+    assert len(loader) == 4
+    seen = 0
+    for k, batch in enumerate(loader):
+        assert len(batch) == 5
+        for j in range(5):
+            ref = np.asarray(Image.open(names[k * 5 + j]).convert("RGB"))
+            assert np.array_equal(batch[j].cpu().numpy(), ref)
+            seen += 1
+    assert seen == 20
+    assert sum(len(b) for b in img_data.DeviceImageLoader(names, engine, 5, drop_last=False)) == 23

@@ -1,0 +1,238 @@
+"""CPU checks of the PNG ingest.  The device decoder's algorithms live in
+tise_toolbox_b200/csrc/png_core.h, written for host and device alike; tests/png_host.cpp compiles that header
+with g++ (one "lane") so the inflate / unfilter / chunk-parser LOGIC is checked here against zlib and Pillow
+(the oracle for this row: the reference calls PIL.Image.open(f).convert("RGB"), img_data.py:21).
+The GPU build of the same source is checked in test_gpu_png.py.  Nothing in the package uses this host build."""
+import ctypes as C
+import io
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+from PIL import Image
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def host():
+    out_dir = os.path.join(HERE, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "png_host.so")
+    src = os.path.join(HERE, "png_host.cpp")
+    core = os.path.join(HERE, "..", "tise_toolbox_b200", "csrc", "png_core.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", src, "-o", so])
+    lib = C.CDLL(so)
+    lib.host_inflate.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
+                                 C.POINTER(C.c_uint32)]
+    lib.host_png_decode.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]
+    return lib
+
+
+def _inflate(lib, z, cap):
+    out = np.zeros(cap + 8, np.uint8)
+    n, ad = C.c_uint32(), C.c_uint32()
+    st = lib.host_inflate(z, len(z), out.ctypes.data, cap, C.byref(n), C.byref(ad))
+    return st, out[:n.value].tobytes(), ad.value
+
+
+def _decode(lib, blob, cap=1 << 24):
+    hw = (C.c_int32 * 2)()
+    out = np.zeros(cap, np.uint8)
+    st = lib.host_png_decode(blob, len(blob), out.ctypes.data, out.size, hw)
+    return st, (out[:hw[0] * hw[1] * 3].reshape(hw[0], hw[1], 3) if st == 0 else None)
+
+
+def smooth_image(rng, h, w, c):
+    """Low-frequency colour field + noise (like the synthetic sets): exercises matches AND literals."""
+    gh, gw = max(h // 16, 1) + 1, max(w // 16, 1) + 1
+    planes = [np.asarray(Image.fromarray(rng.integers(0, 256, (gh, gw)).astype(np.uint8)).resize((w, h), Image.BICUBIC))
+              for _ in range(c)]
+    a = np.stack(planes, -1).astype(np.int32) + rng.integers(-6, 7, (h, w, c))
+    return np.clip(a, 0, 255).astype(np.uint8)
+
+
+def png_bytes(arr_or_img, **kw):
+    im = arr_or_img if isinstance(arr_or_img, Image.Image) else Image.fromarray(arr_or_img)
+    b = io.BytesIO()
+    im.save(b, "PNG", **kw)
+    return b.getvalue()
+
+
+@pytest.mark.parametrize("level", [0, 1, 6, 9])
+def test_inflate_matches_zlib(host, level):
+    rng = np.random.default_rng(level)
+    for kind in range(6):
+        n = int(rng.integers(0, 150000))
+        if kind == 0:
+            d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()  # incompressible -> stored blocks
+        elif kind == 1:
+            d = bytes(n)  # one long run: distance 1, length 258
+        elif kind == 2:
+            d = (b"abcabcabd" * (n // 9 + 1))[:n]
+        elif kind == 3:
+            d = rng.integers(0, 4, n, dtype=np.uint8).tobytes()
+        elif kind == 4:
+            d = np.cumsum(rng.integers(-2, 3, n)).astype(np.uint8).tobytes()
+        else:
+            d = b""
+        z = zlib.compress(d, level)
+        st, out, adler = _inflate(host, z, len(d))
+        assert st == 0 and out == d and adler == zlib.adler32(d), (kind, n, st)
+
+
+def test_inflate_fixed_huffman_and_long_codes(host):
+    co = zlib.compressobj(6, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)
+    d = b"hello hello hello world" * 100
+    z = co.compress(d) + co.flush()
+    st, out, _ = _inflate(host, z, len(d))
+    assert st == 0 and out == d
+    # a very skewed literal distribution forces code lengths beyond the 10-bit lookup table (slow path)
+    rng = np.random.default_rng(1)
+    p = 0.5 ** np.arange(1, 41)
+    p = np.concatenate([p, np.full(216, (1 - p.sum()) / 216)])
+    d = rng.choice(256, size=300000, p=p / p.sum()).astype(np.uint8).tobytes()
+    co = zlib.compressobj(9, zlib.DEFLATED, 15, 9, zlib.Z_HUFFMAN_ONLY)
+    z = co.compress(d) + co.flush()
+    st, out, _ = _inflate(host, z, len(d))
+    assert st == 0 and out == d
+
+
+def test_inflate_rejects_corrupt_streams(host):
+    rng = np.random.default_rng(7)
+    d = smooth_image(rng, 64, 64, 3).tobytes()
+    z = bytearray(zlib.compress(d, 6))
+    assert _inflate(host, bytes(z[:len(z) // 2]), len(d))[0] != 0  # truncated
+    assert _inflate(host, bytes(z), len(d) - 100)[0] != 0  # output too small
+    bad = bytearray(z)
+    bad[0] = 0x79
+    assert _inflate(host, bytes(bad), len(d))[0] != 0  # header
+    n_detected = 0
+    for k in range(200):  # random damage must never crash or overrun; most flips are detected
+        bad = bytearray(z)
+        i = int(rng.integers(2, len(bad) - 4))
+        bad[i] ^= 1 << int(rng.integers(0, 8))
+        st, out, adler = _inflate(host, bytes(bad), len(d))
+        n_detected += int(st != 0 or out != d or adler != zlib.adler32(out))
+    assert n_detected >= 190
+
+
+MODES = [("RGB", 3), ("L", 1), ("RGBA", 4), ("LA", 2), ("P", 3)]
+SIZES = [(256, 256), (1, 1), (17, 333), (64, 48), (500, 375), (3, 1000), (299, 299)]
+
+
+@pytest.mark.parametrize("mode,c", MODES)
+def test_png_decode_matches_pillow(host, mode, c):
+    rng = np.random.default_rng(len(mode) * 31 + c)
+    n_ok = 0
+    for (h, w) in SIZES:
+        for level in (1, 6, 9):
+            a = smooth_image(rng, h, w, c)
+            if mode == "P":
+                im = Image.fromarray(a).convert("P", palette=Image.ADAPTIVE, colors=200)
+            elif mode == "L":
+                im = Image.fromarray(a[..., 0])
+            else:
+                im = Image.fromarray(a, mode)
+            blob = png_bytes(im, compress_level=level)
+            ref = np.asarray(Image.open(io.BytesIO(blob)).convert("RGB"))
+            st, got = _decode(host, blob)
+            if st == -2:  # Pillow packs tiny palettes at 1/2/4 bits: outside the device decoder, reported as such
+                assert blob[24] != 8
+                continue
+            assert st == 0, (mode, h, w, level, st)
+            assert np.array_equal(got, ref), (mode, h, w, level)
+            n_ok += 1
+    assert n_ok >= 15
+
+
+def test_png_every_filter_type(host):
+    """Hand-built PNGs with each scanline filter (0..4) forced for every row, 3 and 4 bytes per pixel."""
+    import struct
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+
+    def paeth(a, b, c):
+        p = a + b - c
+        pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
+        return a if pa <= pb and pa <= pc else (b if pb <= pc else c)
+
+    rng = np.random.default_rng(3)
+    for ch, ctype in ((3, 2), (4, 6), (1, 0), (2, 4)):
+        img = smooth_image(rng, 37, 53, ch)
+        for ft in range(5):
+            raw = bytearray()
+            prev = np.zeros(53 * ch, np.int32)
+            for y in range(37):
+                cur = img[y].reshape(-1).astype(np.int32)
+                line = np.zeros_like(cur)
+                for x in range(cur.size):
+                    a = cur[x - ch] if x >= ch else 0
+                    b = prev[x]
+                    c = prev[x - ch] if x >= ch else 0
+                    pred = (0, a, b, (a + b) >> 1, paeth(a, b, c))[ft]
+                    line[x] = (cur[x] - pred) & 255
+                raw += bytes([ft]) + line.astype(np.uint8).tobytes()
+                prev = cur
+            ihdr = struct.pack(">IIBBBBB", 53, 37, 8, ctype, 0, 0, 0)
+            z = zlib.compress(bytes(raw), 6)
+            # IDAT split into three chunks, one of them tiny: the gather path
+            blob = (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", z[:5]) + chunk(b"IDAT", z[5:len(z) // 2]) +
+                    chunk(b"IDAT", z[len(z) // 2:]) + chunk(b"IEND", b""))
+            ref = np.asarray(Image.open(io.BytesIO(blob)).convert("RGB"))
+            st, got = _decode(host, blob)
+            assert st == 0 and np.array_equal(got, ref), (ch, ft, st)
+
+
+def test_png_transparency_chunks_are_dropped_like_convert_rgb(host):
+    rng = np.random.default_rng(11)
+    a = smooth_image(rng, 40, 60, 3)
+    p = Image.fromarray(a).convert("P", palette=Image.ADAPTIVE, colors=256)
+    blob = png_bytes(p, transparency=3)
+    assert blob[24] == 8
+    st, got = _decode(host, blob)
+    assert st == 0 and np.array_equal(got, np.asarray(Image.open(io.BytesIO(blob)).convert("RGB")))
+    blob = png_bytes(Image.fromarray(a), transparency=(1, 2, 3))
+    st, got = _decode(host, blob)
+    assert st == 0 and np.array_equal(got, np.asarray(Image.open(io.BytesIO(blob)).convert("RGB")))
+
+
+def test_png_detects_damage(host):
+    rng = np.random.default_rng(5)
+    blob = bytearray(png_bytes(smooth_image(rng, 64, 64, 3)))
+    ref = np.asarray(Image.open(io.BytesIO(bytes(blob))).convert("RGB"))
+    assert _decode(host, bytes(blob[:50]))[0] == -1  # truncated container
+    assert _decode(host, b"\xff\xd8\xff\xe0" + bytes(100))[0] == -1  # a JPEG
+    idat = bytes(blob).find(b"IDAT") + 4
+    hits = 0
+    for k in range(100):
+        bad = bytearray(blob)
+        bad[idat + 2 + int(rng.integers(0, len(blob) - idat - 30))] ^= 1 << int(rng.integers(0, 8))
+        st, got = _decode(host, bytes(bad))
+        hits += int(st != 0)
+        assert st != 0 or np.array_equal(got, ref)  # the Adler-32 check catches silent corruption
+    assert hits >= 95
+
+
+def test_c_abi_probe_reports_what_the_device_handles():
+    """tise_png_probe is host-only: callable without a GPU."""
+    from tise_toolbox_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(2)
+    info = _lib.PngInfo()
+    blob = png_bytes(smooth_image(rng, 300, 200, 3))
+    assert lib.tise_png_probe(blob, len(blob), C.byref(info)) == 0
+    assert (info.width, info.height, info.bit_depth, info.color_type, info.channels, info.supported) == (200, 300, 8, 2, 3, 1)
+    assert info.n_idat >= 1 and info.idat_bytes > 0
+    assert lib.tise_png_decode_workspace_bytes(C.byref(info), 1) >= info.idat_bytes + 300 * 601
+    a16 = (rng.integers(0, 65536, (20, 20))).astype(np.uint16)
+    blob = png_bytes(Image.fromarray(a16))
+    assert lib.tise_png_probe(blob, len(blob), C.byref(info)) == 0 and info.supported == 0 and info.bit_depth == 16
+    jpg = io.BytesIO()
+    Image.fromarray(smooth_image(rng, 32, 32, 3)).save(jpg, "JPEG")
+    assert lib.tise_png_probe(jpg.getvalue(), len(jpg.getvalue()), C.byref(info)) < 0 and info.supported == 0

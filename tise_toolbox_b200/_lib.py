@@ -17,6 +17,12 @@ class WeightDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_float)), ("numel", C.c_int64)]
 
 
+class PngInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bit_depth", C.c_int32), ("color_type", C.c_int32),
+                ("interlace", C.c_int32), ("channels", C.c_int32), ("n_idat", C.c_int32), ("supported", C.c_int32),
+                ("idat_bytes", C.c_int64)]
+
+
 class TiseError(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__("libtise_b200: %s (status %d)" % (message, status))
@@ -36,6 +42,10 @@ _SIGNATURES = {
     "tise_resize_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "tise_resize_u8": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_size_t, c_stream]),
+    "tise_png_probe": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(PngInfo)]),
+    "tise_png_decode_workspace_bytes": (C.c_size_t, [C.POINTER(PngInfo), C.c_int]),
+    "tise_png_decode": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
     "tise_set_input_lut": (C.c_int, [c_ctx_p, C.c_void_p]),
     "tise_inception_workspace_bytes": (C.c_size_t, [c_ctx_p, C.c_int]),
     "tise_inception_features": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -52,6 +52,31 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class PackedImages:
+    """n uint8 HWC RGB images of arbitrary sizes in ONE device buffer: image i is ``buf[offsets[i]:][:h*w*3]``.
+    This is the layout tise_png_decode writes and tise_resize_u8 reads, so decode -> resize moves no bytes."""
+
+    def __init__(self, buf: torch.Tensor, offsets: np.ndarray, hw: np.ndarray):
+        self.buf = buf
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.hw = np.ascontiguousarray(hw, dtype=np.int32).reshape(-1, 2)
+
+    def __len__(self):
+        return int(self.hw.shape[0])
+
+    def __getitem__(self, i) -> torch.Tensor:
+        h, w = int(self.hw[i, 0]), int(self.hw[i, 1])
+        o = int(self.offsets[i])
+        return self.buf[o:o + h * w * 3].view(h, w, 3)
+
+    def tensors(self) -> List[torch.Tensor]:
+        return [self[i] for i in range(len(self))]
+
+
+class ImageDecodeError(ValueError):
+    """A file the device decoder accepted turned out to be corrupt (status codes: csrc/png_core.h)."""
+
+
 class Engine:
     """One libtise_b200 context on one GPU with an Inception-v3 ``state_dict`` loaded."""
 
@@ -75,6 +100,7 @@ class Engine:
         self._rs_ws: Optional[torch.Tensor] = None
         self._u8: Optional[torch.Tensor] = None
         self._fr_ws: Optional[torch.Tensor] = None
+        self._png_ws: Optional[torch.Tensor] = None
         self.num_classes = 0
         self.variant = None
         self.set_conv_mode(conv_impl, passes)
@@ -146,12 +172,85 @@ class Engine:
             setattr(self, name, cur)
         return cur
 
+    # ------------------------------------------------------------------ A1 decode
+    def png_probe(self, blob: bytes) -> Optional[_lib.PngInfo]:
+        """IHDR / chunk walk of one file on the host; None if the bytes are not a PNG container."""
+        info = _lib.PngInfo()
+        rc = self.lib.tise_png_probe(blob, len(blob), C.byref(info))
+        return info if rc == 0 else None
+
+    def decode_images(self, blobs: Sequence[bytes], host_fallback: bool = True) -> PackedImages:
+        """Encoded image files -> RGB8 HWC images in HBM (what ``PIL.Image.open(f).convert("RGB")`` returns,
+        img_data.py:21).  8-bit non-interlaced PNGs are inflated / unfiltered on the device (tise_png_decode);
+        any other format (JPEG, 16-bit or interlaced PNG) is outside the device decoder and, with
+        ``host_fallback``, is decoded by PIL exactly like the reference does and uploaded."""
+        n = len(blobs)
+        infos = (_lib.PngInfo * max(n, 1))()
+        on_dev, on_host = [], []
+        for i, b in enumerate(blobs):
+            rc = self.lib.tise_png_probe(b, len(b), C.byref(infos[i]))
+            (on_dev if rc == 0 and infos[i].supported else on_host).append(i)
+        if on_host and not host_fallback:
+            raise ValueError("decode_images: file %d is not an 8-bit non-interlaced PNG" % on_host[0])
+        host_imgs = {}
+        if on_host:
+            import io
+
+            from PIL import Image
+
+            for i in on_host:
+                host_imgs[i] = np.ascontiguousarray(np.asarray(Image.open(io.BytesIO(blobs[i])).convert("RGB")))
+        hw = np.zeros((n, 2), dtype=np.int32)
+        for i in range(n):
+            hw[i] = host_imgs[i].shape[:2] if i in host_imgs else (infos[i].height, infos[i].width)
+        nbytes = hw[:, 0].astype(np.int64) * hw[:, 1] * 3
+        out_off = np.zeros(n, dtype=np.int64)
+        if n:
+            out_off[1:] = np.cumsum((nbytes + 15) // 16 * 16)[:-1]
+        total = int(out_off[-1] + nbytes[-1]) if n else 0
+        out = torch.empty(max(total, 16), dtype=torch.uint8, device=self.device)
+        if on_dev:
+            m = len(on_dev)
+            sizes = np.array([len(blobs[i]) for i in on_dev], dtype=np.int64)
+            f_off = np.zeros(m, dtype=np.int64)
+            f_off[1:] = np.cumsum((sizes + 15) // 16 * 16)[:-1]
+            f_total = int(f_off[-1] + sizes[-1]) + 16
+            pinned = torch.empty(f_total, dtype=torch.uint8, pin_memory=True)
+            hbuf = pinned.numpy()
+            for k, i in enumerate(on_dev):
+                hbuf[f_off[k]:f_off[k] + sizes[k]] = np.frombuffer(blobs[i], dtype=np.uint8)
+            d_files = pinned.to(self.device, non_blocking=True)
+            sub = (_lib.PngInfo * m)(*[infos[i] for i in on_dev])
+            ws = self._buf("_png_ws", int(self.lib.tise_png_decode_workspace_bytes(sub, m)))
+            status = torch.empty(m, dtype=torch.int32, device=self.device)
+            o_off = np.ascontiguousarray(out_off[on_dev])
+            with torch.cuda.device(self.device):
+                self._check(self.lib.tise_png_decode(self.ctx, pinned.data_ptr(), d_files.data_ptr(), f_off.ctypes.data,
+                                                     sizes.ctypes.data, m, out.data_ptr(), o_off.ctypes.data,
+                                                     status.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+            st = status.cpu().numpy()  # synchronises: the pinned staging buffer may be released afterwards
+            if st.any():
+                k = int(np.nonzero(st)[0][0])
+                raise ImageDecodeError("corrupt PNG stream in file %d (decoder status %d)" % (on_dev[k], int(st[k])))
+        for i, a in host_imgs.items():
+            o = int(out_off[i])
+            out[o:o + a.size].copy_(torch.from_numpy(a.reshape(-1)))
+        return PackedImages(out, out_off, hw)
+
     # ------------------------------------------------------------------ A2 resize
-    def resize(self, images: Union[torch.Tensor, Sequence[torch.Tensor]], out: Optional[torch.Tensor] = None
-               ) -> torch.Tensor:
+    def resize(self, images: Union[torch.Tensor, Sequence[torch.Tensor], "PackedImages"],
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """uint8 HWC RGB images on the device -> uint8 [n, 299, 299, 3] (Pillow-exact bilinear).
-        ``images``: one [n, H, W, 3] tensor, or a sequence of [H_i, W_i, 3] tensors (ragged crops)."""
-        if torch.is_tensor(images):
+        ``images``: one [n, H, W, 3] tensor, a sequence of [H_i, W_i, 3] tensors (ragged crops), or a
+        :class:`PackedImages` (the decoder's output, consumed in place)."""
+        if isinstance(images, PackedImages):
+            n = len(images)
+            hw = images.hw.reshape(-1)
+            offs = images.offsets
+            src = images.buf
+            offs_p, uniform = offs.ctypes.data, 0
+            max_h, max_w = (int(images.hw[:, 0].max()), int(images.hw[:, 1].max())) if n else (1, 1)
+        elif torch.is_tensor(images):
             assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] == 3
             imgs = images.contiguous()
             n, h, w = int(imgs.shape[0]), int(imgs.shape[1]), int(imgs.shape[2])

@@ -15,7 +15,7 @@ import torch
 import torch.utils.data
 
 from . import img_data
-from .engine import Moments, default_engine
+from .engine import Moments, PackedImages, default_engine
 from .inception import InceptionV3
 
 warnings.filterwarnings("ignore")
@@ -35,7 +35,7 @@ parser.add_argument("--ofid", action="store_true", help="write 'O-FID:' instead 
 def _batch_features(batch, model, dims):
     """One batch -> device float32 [B, dims].  uint8 HWC batches (tensor or ragged list) take the fused
     GPU path; float Bx3xHxW batches in [0,1] take the reference's ``model(batch)[0]`` contract."""
-    if isinstance(batch, (list, tuple)) or batch.dtype == torch.uint8:
+    if isinstance(batch, (list, tuple, PackedImages)) or batch.dtype == torch.uint8:
         return model.features_u8(batch, dims=dims)
     pred = model(batch)[0]
     return pred.reshape(pred.shape[0], -1)
@@ -100,10 +100,14 @@ def _compute_statistics_of_path(path, model, batch_size, dims, cuda):
         m, s = f["mu"][:], f["sigma"][:]
         f.close()
     else:
-        # fid_score.py:206-217 with the Resize/ToTensor transform moved onto the GPU: workers only decode
+        # fid_score.py:206-217 with decode, Resize and ToTensor moved onto the GPU: host threads only read bytes.
+        # TISE_GPU_DECODE=0 keeps PIL decode on DataLoader workers (resize / ToTensor still on the GPU).
         dataset = img_data.Dataset(path, raw_u8=True)
-        dataloader = torch.utils.data.DataLoader(dataset=dataset, batch_size=batch_size, shuffle=False,
-                                                 drop_last=True, num_workers=8, collate_fn=img_data.collate_u8)
+        if os.environ.get("TISE_GPU_DECODE", "1") != "0":
+            dataloader = img_data.DeviceImageLoader(dataset.file_names, model.engine, batch_size, drop_last=True)
+        else:
+            dataloader = torch.utils.data.DataLoader(dataset=dataset, batch_size=batch_size, shuffle=False,
+                                                     drop_last=True, num_workers=8, collate_fn=img_data.collate_u8)
         m, s = calculate_activation_statistics(dataloader, model, batch_size, dims, cuda)
     return m, s
 

@@ -3,8 +3,13 @@
 With ``transform=None`` the reference returns the PIL image; here ``raw_u8=True`` returns the decoded
 uint8 HWC tensor instead, which is what the GPU resize kernel consumes (the CPU ``transforms.Resize``
 of fid_score.py:208-213 then never runs).
+
+``DeviceImageLoader`` replaces ``DataLoader(Dataset(path, transform), num_workers=8)`` of fid_score.py:206-217
+altogether: host threads only read file BYTES; PNG inflate / unfilter, the resize and
+ToTensor all run on the GPU.
 """
 import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -48,3 +53,43 @@ def collate_u8(batch):
     if all(b.shape == batch[0].shape for b in batch):
         return torch.stack(batch)
     return list(batch)
+
+
+def _read_file(name):
+    with open(name, "rb") as f:
+        return f.read()
+
+
+class DeviceImageLoader:
+    """Iterable of batches for ``calculate_activation_statistics`` / ``get_activations``: same order, same
+    ``batch_size`` / ``drop_last`` semantics as the reference's DataLoader(shuffle=False) (fid_score.py:214-217),
+    but every batch is an :class:`~tise_toolbox_b200.engine.PackedImages` decoded on the device
+    (``Engine.decode_images``).  File reads of the next ``prefetch`` batches overlap the GPU work."""
+
+    def __init__(self, file_names, engine, batch_size, drop_last=True, io_threads=8, prefetch=2):
+        self.file_names = list(file_names)
+        self.engine = engine
+        self.batch_size = int(batch_size)
+        self.drop_last = bool(drop_last)
+        self.io_threads = int(io_threads)
+        self.prefetch = max(1, int(prefetch))
+
+    def __len__(self):
+        n, b = len(self.file_names), self.batch_size
+        return n // b if self.drop_last else (n + b - 1) // b
+
+    def __iter__(self):
+        b = self.batch_size
+        chunks = [self.file_names[i * b:(i + 1) * b] for i in range(len(self))]
+        with ThreadPoolExecutor(max_workers=self.io_threads) as pool:
+            pending = []
+            nxt = 0
+            while nxt < len(chunks) and len(pending) < self.prefetch:
+                pending.append([pool.submit(_read_file, f) for f in chunks[nxt]])
+                nxt += 1
+            while pending:
+                blobs = [f.result() for f in pending.pop(0)]
+                if nxt < len(chunks):
+                    pending.append([pool.submit(_read_file, f) for f in chunks[nxt]])
+                    nxt += 1
+                yield self.engine.decode_images(blobs)

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .engine import Engine
+from .engine import Engine, PackedImages
 
 _DIMS = {0: 64, 1: 192, 2: 768, 3: 2048}
 
@@ -80,7 +80,9 @@ class InceptionV3(nn.Module):
         """Fast path: uint8 HWC images of any size (tensor [B,H,W,3] or list of [H,W,3]) -> [B, dims]
         float32; Pillow-exact resize, ToTensor and the affine above all happen on the GPU."""
         self.engine.set_variant("fid")
-        if torch.is_tensor(images):
+        if isinstance(images, PackedImages):
+            pass  # already on the device (Engine.decode_images)
+        elif torch.is_tensor(images):
             images = images.to(self.engine.device, non_blocking=True)
         else:
             images = [t.to(self.engine.device, non_blocking=True) for t in images]

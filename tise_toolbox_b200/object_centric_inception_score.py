@@ -15,6 +15,7 @@ from torch.nn import functional as F
 
 from . import inception_score as _is
 from .engine import Engine, ISPartials
+from .img_data import DeviceImageLoader
 from .inception import load_state_dict_file
 
 WEIGHTS = "weights/inceptionv3_fine_to_with_80_coco_classes.pth"  # object_centric_inception_score.py:46
@@ -33,12 +34,19 @@ def inception_score(imgs, cuda=True, batch_size=32, resize=False, splits=1, stat
         engine = Engine(state_dict, variant="ois")
     engine.set_variant("ois")
     raw = bool(getattr(imgs, "raw_u8", False))
-    dataloader = torch.utils.data.DataLoader(imgs, batch_size=batch_size,
-                                             collate_fn=(lambda b: list(b)) if raw else None)
+    on_device = raw and hasattr(imgs, "imgspath") and os.environ.get("TISE_GPU_DECODE", "1") != "0"
+    if on_device:  # host threads read bytes; PNG decode, resize and normalisation run on the GPU
+        files = [os.path.join(imgs.imgspath, name) for name in imgs.namelist]
+        dataloader = DeviceImageLoader(files, engine, batch_size, drop_last=False)
+    else:
+        dataloader = torch.utils.data.DataLoader(imgs, batch_size=batch_size,
+                                                 collate_fn=(lambda b: list(b)) if raw else None)
     parts = ISPartials(engine, engine.num_classes, splits)
     start = 0
     for batch in dataloader:
-        if raw:
+        if on_device:
+            feat = engine.features(batch)
+        elif raw:
             feat = engine.features([t.to(engine.device) for t in batch])
         else:
             x = batch.to(engine.device, torch.float32)
