@@ -119,6 +119,19 @@ size_t tise_resize_workspace_bytes(int n, int max_h, int max_w);
 int tise_resize_u8(tise_ctx* ctx, const uint8_t* d_imgs, const int64_t* h_offsets, const int32_t* h_hw,
                    int uniform, int n, uint8_t* d_out, void* d_ws, size_t ws_bytes, tise_stream stream);
 
+/* Crop hand-off: object_fidelity/crop_object.py:38-46 writes every detected object as
+ * img.crop(box) to a PNG which O-FID / O-IS later re-open and resize to 299x299
+ * (fid_score.py:210, object_centric_inception_score.py:89).  This entry point does crop + resize in one
+ * pass straight from the source images in HBM: crop i = pixels [y0, y1) x [x0, x1) of the image at
+ * d_imgs + h_offsets[i] (h_hw[2i] rows x h_hw[2i+1] columns; several crops may name the same image),
+ * h_box = n x (x0, y0, x1, y1) already rounded as PIL's Image.crop rounds (int(round(v))).
+ * Output bytes are identical to Image.crop(box).resize((299, 299), BILINEAR).  Boxes must be non-empty
+ * and inside their image (Detectron2 clips its boxes); otherwise TISE_ERR_INVALID.
+ * Workspace: tise_resize_workspace_bytes(n, max box height, max box width). */
+int tise_crop_resize_u8(tise_ctx* ctx, const uint8_t* d_imgs, const int64_t* h_offsets, const int32_t* h_hw,
+                        const int32_t* h_box, int n, uint8_t* d_out, void* d_ws, size_t ws_bytes,
+                        tise_stream stream);
+
 /* ---- A3/A4: uint8 level -> network input ------------------------------------------------ */
 /* lut[c*256 + v] = float fed to Conv2d_1a_3x3 for channel c and uint8 level v; covers ToTensor
  * (fid_score.py:211) + the affine at image_realism/FID/inception.py:120-124, or

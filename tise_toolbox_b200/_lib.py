@@ -42,6 +42,8 @@ _SIGNATURES = {
     "tise_resize_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "tise_resize_u8": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_size_t, c_stream]),
+    "tise_crop_resize_u8": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_size_t, c_stream]),
     "tise_png_probe": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(PngInfo)]),
     "tise_png_decode_workspace_bytes": (C.c_size_t, [C.POINTER(PngInfo), C.c_int]),
     "tise_png_decode": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,

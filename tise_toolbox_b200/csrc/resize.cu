@@ -67,10 +67,11 @@ __global__ void resize_coeffs_kernel(const int* __restrict__ sizes, int kmax, in
 }
 
 struct ImgDesc {
-  long long src_off;  // byte offset of the image in d_imgs
+  long long src_off;  // byte offset of the image (of the crop's first pixel) in d_imgs
   long long tmp_off;  // byte offset of its [h][299][3] horizontal-pass temporary
-  int h, w;
-  int tab_x, tab_y;  // table indices (by input width / height)
+  int h, w;           // size of the image / of the crop box
+  int tab_x, tab_y;   // table indices (by input width / height)
+  int pitch, pad;     // bytes between consecutive source rows (w * 3 unless this is a crop of a wider image)
 };
 
 __device__ __forceinline__ uint8_t clip8(int acc) {
@@ -89,7 +90,7 @@ __global__ void resize_h_kernel(const uint8_t* __restrict__ imgs, const ImgDesc*
   const int j = blockIdx.x * blockDim.x + threadIdx.x;  // xx * 3 + c
   if (j >= kOutSize * 3) return;
   const int xx = j / 3, c = j - xx * 3;
-  const uint8_t* row = imgs + d.src_off + (size_t)y * d.w * 3;
+  const uint8_t* row = imgs + d.src_off + (size_t)y * d.pitch;
   uint8_t* out = tmp + d.tmp_off + (size_t)y * kOutSize * 3;
   if (d.w == kOutSize) {  // Pillow skips a pass that does not change the size
     out[j] = row[j];
@@ -153,10 +154,15 @@ __global__ void __launch_bounds__(256) resize_fused_kernel(const uint8_t* __rest
   const int in_row = d.w * 3, out_row = kOutSize * 3;
   uint8_t* s_tmp = sm;                                          // [n_in][kTmpPitch]   horizontally resampled rows
   uint8_t* s_in = sm + (((size_t)n_in * kTmpPitch + 15) & ~(size_t)15);  // [n_in][w * 3]  raw input rows
-  const uint8_t* src = imgs + d.src_off + (size_t)y_lo * in_row;
+  const uint8_t* src = imgs + d.src_off + (size_t)y_lo * d.pitch;
   const int in_bytes = n_in * in_row;
   if (hpass) {
-    if ((((uintptr_t)src | (uintptr_t)in_bytes) & 15) == 0) {
+    if (d.pitch != in_row) {  // a crop box: rows are not contiguous
+      for (int i = threadIdx.x; i < in_bytes; i += blockDim.x) {
+        const int y = i / in_row;
+        s_in[i] = __ldg(src + (size_t)y * d.pitch + (i - y * in_row));
+      }
+    } else if ((((uintptr_t)src | (uintptr_t)in_bytes) & 15) == 0) {
       for (int i = threadIdx.x; i < in_bytes / 16; i += blockDim.x)
         reinterpret_cast<uint4*>(s_in)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
     } else {
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(256) resize_fused_kernel(const uint8_t* __rest
   } else {  // Pillow skips the horizontal pass: the rows are already 897 bytes wide
     for (int i = threadIdx.x; i < in_bytes; i += blockDim.x) {
       const int y = i / out_row;
-      s_tmp[y * kTmpPitch + (i - y * out_row)] = __ldg(src + i);
+      s_tmp[y * kTmpPitch + (i - y * out_row)] = __ldg(src + (size_t)y * d.pitch + (i - y * out_row));
     }
   }
   __syncthreads();
@@ -247,25 +253,34 @@ extern "C" size_t tise_resize_workspace_bytes(int n, int max_h, int max_w) {
   return resize_ws_layout(n, max_h, max_w).total;
 }
 
-extern "C" int tise_resize_u8(tise_ctx* ctx, const uint8_t* d_imgs, const int64_t* h_offsets, const int32_t* h_hw,
-                              int uniform, int n, uint8_t* d_out, void* d_ws, size_t ws_bytes,
-                              tise_stream stream) {
+// h_box: NULL (whole images) or n x (x0, y0, x1, y1) crop boxes inside the images
+static int resize_impl(tise_ctx* ctx, const char* who, const uint8_t* d_imgs, const int64_t* h_offsets, const int32_t* h_hw,
+                       const int32_t* h_box, int uniform, int n, uint8_t* d_out, void* d_ws, size_t ws_bytes,
+                       tise_stream stream) {
   if (!ctx) return TISE_ERR_INVALID;
   if (n == 0) return TISE_OK;
-  if (!d_imgs || !h_hw || !d_out || !d_ws || n < 0) return fail(ctx, TISE_ERR_INVALID, "tise_resize_u8: null argument");
-  if (!uniform && !h_offsets) return fail(ctx, TISE_ERR_INVALID, "tise_resize_u8: ragged batch needs h_offsets");
+  if (!d_imgs || !h_hw || !d_out || !d_ws || n < 0) return fail(ctx, TISE_ERR_INVALID, "%s: null argument", who);
+  if (!uniform && !h_offsets) return fail(ctx, TISE_ERR_INVALID, "%s: ragged batch needs h_offsets", who);
   cudaStream_t st = (cudaStream_t)stream;
 
   int max_h = 0, max_w = 0;
-  for (int i = 0; i < (uniform ? 1 : n); ++i) {
-    const int h = h_hw[2 * i], w = h_hw[2 * i + 1];
-    if (h <= 0 || w <= 0) return fail(ctx, TISE_ERR_INVALID, "tise_resize_u8: image %d has size %dx%d", i, h, w);
+  for (int i = 0; i < n; ++i) {
+    int h = h_hw[uniform ? 0 : 2 * i], w = h_hw[uniform ? 1 : 2 * i + 1];
+    if (h <= 0 || w <= 0) return fail(ctx, TISE_ERR_INVALID, "%s: image %d has size %dx%d", who, i, h, w);
+    if (h_box) {
+      const int x0 = h_box[4 * i], y0 = h_box[4 * i + 1], x1 = h_box[4 * i + 2], y1 = h_box[4 * i + 3];
+      if (x0 < 0 || y0 < 0 || x1 > w || y1 > h || x1 <= x0 || y1 <= y0)
+        return fail(ctx, TISE_ERR_INVALID, "%s: box %d = (%d, %d, %d, %d) is empty or outside its %dx%d image", who, i, x0,
+                    y0, x1, y1, h, w);
+      h = y1 - y0;
+      w = x1 - x0;
+    }
     max_h = h > max_h ? h : max_h;
     max_w = w > max_w ? w : max_w;
+    if (uniform && !h_box) break;
   }
   const ResizeWs L = resize_ws_layout(n, max_h, max_w);
-  if (ws_bytes < L.total)
-    return fail(ctx, TISE_ERR_WORKSPACE, "tise_resize_u8: workspace %zu < %zu bytes", ws_bytes, L.total);
+  if (ws_bytes < L.total) return fail(ctx, TISE_ERR_WORKSPACE, "%s: workspace %zu < %zu bytes", who, ws_bytes, L.total);
   const int kmax = resize_ksize(max_h > max_w ? max_h : max_w);
 
   // distinct sizes -> table indices
@@ -282,11 +297,18 @@ extern "C" int tise_resize_u8(tise_ctx* ctx, const uint8_t* d_imgs, const int64_
   };
   long long tmp_off = 0;
   for (int i = 0; i < n; ++i) {
-    const int h = h_hw[uniform ? 0 : 2 * i], w = h_hw[uniform ? 1 : 2 * i + 1];
+    int h = h_hw[uniform ? 0 : 2 * i], w = h_hw[uniform ? 1 : 2 * i + 1];
     ImgDesc& d = descs[i];
+    d.src_off = uniform ? (long long)i * h * w * 3 : (long long)h_offsets[i];
+    d.pitch = w * 3;
+    d.pad = 0;
+    if (h_box) {
+      d.src_off += (long long)h_box[4 * i + 1] * d.pitch + (long long)h_box[4 * i] * 3;
+      h = h_box[4 * i + 3] - h_box[4 * i + 1];
+      w = h_box[4 * i + 2] - h_box[4 * i];
+    }
     d.h = h;
     d.w = w;
-    d.src_off = uniform ? (long long)i * h * w * 3 : (long long)h_offsets[i];
     d.tmp_off = tmp_off;
     tmp_off += (long long)h * kOutSize * 3;
     d.tab_x = table(w);
@@ -336,4 +358,16 @@ extern "C" int tise_resize_u8(tise_ctx* ctx, const uint8_t* d_imgs, const int64_
     TISE_LAUNCH_CHECK(ctx);
   }
   return TISE_OK;
+}
+
+extern "C" int tise_resize_u8(tise_ctx* ctx, const uint8_t* d_imgs, const int64_t* h_offsets, const int32_t* h_hw,
+                              int uniform, int n, uint8_t* d_out, void* d_ws, size_t ws_bytes, tise_stream stream) {
+  return resize_impl(ctx, "tise_resize_u8", d_imgs, h_offsets, h_hw, nullptr, uniform, n, d_out, d_ws, ws_bytes, stream);
+}
+
+extern "C" int tise_crop_resize_u8(tise_ctx* ctx, const uint8_t* d_imgs, const int64_t* h_offsets, const int32_t* h_hw,
+                                   const int32_t* h_box, int n, uint8_t* d_out, void* d_ws, size_t ws_bytes,
+                                   tise_stream stream) {
+  if (ctx && n > 0 && (!h_box || !h_offsets)) return fail(ctx, TISE_ERR_INVALID, "tise_crop_resize_u8: null argument");
+  return resize_impl(ctx, "tise_crop_resize_u8", d_imgs, h_offsets, h_hw, h_box, 0, n, d_out, d_ws, ws_bytes, stream);
 }

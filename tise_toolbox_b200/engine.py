@@ -279,6 +279,41 @@ class Engine:
                                                 out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
         return out
 
+    def resize_crops(self, images: Union[torch.Tensor, "PackedImages"], image_index: Sequence[int], boxes,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Crop hand-off (object_fidelity/crop_object.py:38-46 + the Resize of the O-FID / O-IS datasets):
+        ``boxes`` [n, 4] = (x0, y0, x1, y1) in pixels (floats are rounded like ``PIL.Image.crop`` rounds);
+        crop i is cut from ``images[image_index[i]]`` and resized to 299 x 299 in one kernel ->
+        uint8 [n, 299, 299, 3], byte-identical to ``img.crop(box).resize((299, 299), BILINEAR)``."""
+        b = np.asarray(boxes, dtype=np.float64).reshape(-1, 4)
+        box = np.array([[int(round(float(v))) for v in row] for row in b], dtype=np.int32).reshape(-1, 4)
+        idx = np.asarray(image_index, dtype=np.int64).reshape(-1)
+        n = int(box.shape[0])
+        assert idx.shape[0] == n
+        if isinstance(images, PackedImages):
+            src, offs_all, hw_all = images.buf, images.offsets, images.hw
+        else:
+            assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[3] == 3
+            src = images.contiguous()
+            m, h, w = int(src.shape[0]), int(src.shape[1]), int(src.shape[2])
+            offs_all = np.arange(m, dtype=np.int64) * (h * w * 3)
+            hw_all = np.tile(np.array([[h, w]], dtype=np.int32), (m, 1))
+        if out is None:
+            out = torch.empty((n, 299, 299, 3), dtype=torch.uint8, device=self.device)
+        if n == 0:
+            return out
+        offs = np.ascontiguousarray(offs_all[idx])
+        hw = np.ascontiguousarray(hw_all[idx]).astype(np.int32)
+        box = np.ascontiguousarray(box)
+        max_h = int(max(1, (box[:, 3] - box[:, 1]).max()))
+        max_w = int(max(1, (box[:, 2] - box[:, 0]).max()))
+        ws = self._buf("_rs_ws", int(self.lib.tise_resize_workspace_bytes(n, max_h, max_w)))
+        with torch.cuda.device(self.device):
+            self._check(self.lib.tise_crop_resize_u8(self.ctx, src.data_ptr(), offs.ctypes.data, hw.ctypes.data,
+                                                     box.ctypes.data, n, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                     _stream()))
+        return out
+
     # ------------------------------------------------------------------ A5 trunk
     def _trunk(self, u8: Optional[torch.Tensor], f32: Optional[torch.Tensor], n: int, tap: int, feat: torch.Tensor):
         need = int(self.lib.tise_inception_workspace_bytes(self.ctx, self.micro_batch))
