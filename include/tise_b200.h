@@ -174,6 +174,20 @@ int tise_is_update(tise_ctx* ctx, const float* d_logits, int n, int C, int class
                    const int32_t* d_split_id, int n_splits, double* d_splogp, double* d_marg,
                    long long* d_cnt, long long* d_zeros, tise_stream stream);
 
+/* ---- A14: temperature calibration ---------------------------------------------------------- */
+/* One closure evaluation of classifier_calibration/temperature_scaling.py:56-63 plus the ECE of :97-119 on
+ * n x C validation logits and int64 labels:  accumulates into d_out (double, zeroed by the caller,
+ * 4 + 3 n_bins + 1 entries)
+ *   [0] sum_i nll_i of CrossEntropyLoss(logits / T, labels)      [1] sum_i d nll_i / dT  (closed form)
+ *   [2] rows                                                       [3] correct top-1 predictions
+ *   [4 ..) per confidence bin (h_bin_bounds[b] < conf <= h_bin_bounds[b+1], n_bins + 1 bounds as
+ *   torch.linspace(0, 1, n_bins + 1) gives them): count, sum of confidences, sum of accuracies
+ *   [4 + 3 n_bins] an int32 flag, non-zero if a label was outside [0, C).
+ * The LBFGS iteration itself is a scalar recurrence and stays with the caller. */
+int tise_calibration_eval(tise_ctx* ctx, const float* d_logits, const int64_t* d_labels, int n, int C,
+                          float temperature, const float* h_bin_bounds, int n_bins, double* d_out,
+                          tise_stream stream);
+
 /* ---- A9: Frechet distance ------------------------------------------------------------------- */
 /* calculate_frechet_distance (fid_score.py:121-171):
  *   |mu1-mu2|^2 + tr(s1) + tr(s2) - 2 tr sqrt(s1 s2),

@@ -110,3 +110,27 @@ def test_result_file_formats(tmp_path):
     assert pipeline.format_result("coco", 54.63, 1.54) == "[Inception Score] mean: 54.63000 std: 1.54000"
     assert pipeline.format_result("bird", 15.13, 0.2) == "IS = 15.13  +-  0.2"
     assert pipeline.format_result("ois", 8.63, 0.06) == "O-IS: 8.63 +-  0.06"
+
+
+def test_ranking_table_matches_the_reference_script_golden(tmp_path):
+    """tests/golden/calibration.json["ranking"]: the reference's ranking_score.py run on its own methods/*.json."""
+    import json
+    from collections import OrderedDict
+
+    from tise_toolbox_b200 import ranking_score as rs
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "calibration.json")) as f:
+        g = json.load(f)["ranking"]
+    ordered = OrderedDict((m, g["methods"][m]) for m in g["listdir_order"])
+    assert rs.ranking_table(method_scores=ordered) == g["table"]
+    # emission in the reference's schema, then the directory form
+    for m in g["listdir_order"]:
+        rs.update_method_scores(str(tmp_path), m, **{k: g["methods"][m][k] for k in rs.METRICS})
+    p = rs.update_method_scores(str(tmp_path), g["listdir_order"][0], FID=g["methods"][g["listdir_order"][0]]["FID"])
+    assert json.load(open(p))["FID"] == float(g["methods"][g["listdir_order"][0]]["FID"])
+    scores = rs.ranking_scores(ordered)
+    table_dir = rs.ranking_table(str(tmp_path))
+    for m in ordered:
+        assert ("%g" % scores[m][-1]) in table_dir
+    with pytest.raises(KeyError):
+        rs.update_method_scores(str(tmp_path), "x", BLEU=1.0)

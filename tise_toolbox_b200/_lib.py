@@ -58,6 +58,8 @@ _SIGNATURES = {
                                         c_stream]),
     "tise_is_update": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_stream]),
+    "tise_calibration_eval": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int,
+                                        C.c_void_p, c_stream]),
     "tise_frechet_workspace_bytes": (C.c_size_t, [C.c_int]),
     "tise_frechet": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
                                C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p, C.c_size_t, c_stream]),

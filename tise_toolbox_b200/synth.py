@@ -19,6 +19,7 @@ from __future__ import annotations
 import math
 from typing import Dict
 
+import numpy as np
 import torch
 
 _M32 = 0xFFFFFFFF
@@ -165,3 +166,15 @@ def calibrate_head(state_dict: Dict[str, torch.Tensor], feats: torch.Tensor, tem
     out["fc.weight"] = w.float().contiguous()
     out["fc.bias"] = (torch.randn(c, generator=g) * 0.1).float()
     return out
+
+
+def calibration_logits(seed: int, n: int, num_classes: int, sharpness: float = 3.0, label_noise: float = 0.25):
+    """Seeded validation logits / labels for the temperature-calibration path: an over-confident classifier
+    (logit gap ``sharpness`` towards a class that is the true label only with probability 1 - label_noise), so
+    that the optimal temperature is well above 1 and NLL(T) has an interior minimum."""
+    rng = np.random.RandomState(seed)
+    labels = rng.randint(0, num_classes, size=n).astype(np.int64)
+    guess = np.where(rng.rand(n) < label_noise, rng.randint(0, num_classes, size=n), labels)
+    logits = rng.randn(n, num_classes).astype(np.float32)
+    logits[np.arange(n), guess] += np.float32(sharpness) * (1.0 + rng.rand(n).astype(np.float32))
+    return torch.from_numpy(logits), torch.from_numpy(labels)
