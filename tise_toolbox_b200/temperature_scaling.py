@@ -81,7 +81,10 @@ class ModelWithTemperature(nn.Module):
 
         def eval():
             r = calibration_eval(logits, labels, float(self.temperature.item()))
-            self.temperature.grad = torch.full_like(self.temperature, r["dnll_dT"])
+            g = torch.full_like(self.temperature, r["dnll_dT"])
+            # the reference's closure (:58-61) calls loss.backward() WITHOUT zeroing the gradient first, so autograd
+            # accumulates over the closure calls of the LBFGS step; kept, because it decides where T ends up
+            self.temperature.grad = g if self.temperature.grad is None else self.temperature.grad + g
             return torch.tensor(r["nll"], dtype=torch.float32)
 
         optimizer.step(eval)
