@@ -278,6 +278,50 @@ TISE_HD int inflate_zlib(const uint32_t* words, uint32_t stream_bytes, uint8_t* 
 
     for (;;) {
       br_refill(r);
+      // Literal runs, the bulk of a photographic PNG: lane k looks up the code that would start at bit offset k of the
+      // buffered window (one shared-memory access for 32 candidate positions); the chain of actual code boundaries
+      // 0 -> len_0 -> len_0 + len_1 ... is then followed through registers (one shuffle per symbol) instead of one
+      // dependent table access, 64-bit shift and store per symbol, and the literals found are stored side by side.
+      // The chain stops at the first code that is not a <= 10-bit literal or does not lie inside the buffered bits;
+      // that symbol takes the general path below.
+      {
+        int p = 0, nlit = 0;
+#if defined(__CUDA_ARCH__)
+        const uint32_t mine = hl->fast[(uint32_t)(r.buf >> lane) & (kFastSize - 1)];
+        uint32_t my_sym = 0;
+        while (p < 32) {
+          const uint32_t e = __shfl_sync(0xffffffffu, mine, p);
+          const int l = (int)(e >> 9);
+          if (e == 0u || (e & 256u) || p + l > r.cnt) break;
+          if (lane == nlit) my_sym = e & 255u;
+          ++nlit;
+          p += l;
+        }
+        if (nlit) {
+          if (op + (uint32_t)nlit > out_cap) return kOutputOverflow;
+          if (lane < nlit) out[op + lane] = (uint8_t)my_sym;
+        }
+#else
+        uint8_t syms[32];
+        while (p < 32) {
+          const uint32_t e = hl->fast[(uint32_t)(r.buf >> p) & (kFastSize - 1)];
+          const int l = (int)(e >> 9);
+          if (e == 0u || (e & 256u) || p + l > r.cnt) break;
+          syms[nlit++] = (uint8_t)(e & 255u);
+          p += l;
+        }
+        if (nlit) {
+          if (op + (uint32_t)nlit > out_cap) return kOutputOverflow;
+          for (int k = 0; k < nlit; ++k) out[op + k] = syms[k];
+        }
+#endif
+        if (nlit) {
+          op += (uint32_t)nlit;
+          r.buf >>= p;
+          r.cnt -= p;
+          continue;
+        }
+      }
       int sym = huff_decode(hl, r);
       if (sym < 256) {
         if (sym < 0) return kBadSymbol;

@@ -8,6 +8,7 @@ The reference-facing modules (``fid_score``, ``inception``, ``object_centric_inc
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -179,63 +180,131 @@ class Engine:
         rc = self.lib.tise_png_probe(blob, len(blob), C.byref(info))
         return info if rc == 0 else None
 
-    def decode_images(self, blobs: Sequence[bytes], host_fallback: bool = True) -> PackedImages:
-        """Encoded image files -> RGB8 HWC images in HBM (what ``PIL.Image.open(f).convert("RGB")`` returns,
-        img_data.py:21).  8-bit non-interlaced PNGs are inflated / unfiltered on the device (tise_png_decode);
-        any other format (JPEG, 16-bit or interlaced PNG) is outside the device decoder and, with
-        ``host_fallback``, is decoded by PIL exactly like the reference does and uploaded."""
-        n = len(blobs)
-        infos = (_lib.PngInfo * max(n, 1))()
-        on_dev, on_host = [], []
-        for i, b in enumerate(blobs):
-            rc = self.lib.tise_png_probe(b, len(b), C.byref(infos[i]))
-            (on_dev if rc == 0 and infos[i].supported else on_host).append(i)
-        if on_host and not host_fallback:
-            raise ValueError("decode_images: file %d is not an 8-bit non-interlaced PNG" % on_host[0])
+    def _pinned(self, nbytes: int) -> torch.Tensor:
+        """Two grow-only pinned staging buffers used alternately (allocating pinned memory costs milliseconds)."""
+        if not hasattr(self, "_pin"):
+            self._pin, self._pin_next = [None, None], 0
+        k = self._pin_next
+        self._pin_next = 1 - k
+        if self._pin[k] is None or self._pin[k].numel() < nbytes:
+            self._pin[k] = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, pin_memory=True)
+        return self._pin[k]
+
+    def _probe_staged(self, pinned: torch.Tensor, f_off: np.ndarray, sizes: np.ndarray) -> dict:
+        m = int(sizes.shape[0])
+        infos = (_lib.PngInfo * max(m, 1))()
+        base = pinned.data_ptr()
+        supported = np.zeros(m, dtype=bool)
+        for i in range(m):
+            rc = self.lib.tise_png_probe(base + int(f_off[i]), int(sizes[i]), C.byref(infos[i]))
+            supported[i] = rc == 0 and bool(infos[i].supported)
+        return {"pinned": pinned, "f_off": f_off, "sizes": sizes, "infos": infos, "supported": supported, "n": m,
+                "total": int(f_off[-1] + sizes[-1]) + 16 if m else 16}
+
+    @staticmethod
+    def _layout(sizes: np.ndarray):
+        f_off = np.zeros(sizes.shape[0], dtype=np.int64)
+        if sizes.shape[0]:
+            f_off[1:] = np.cumsum((sizes + 15) // 16 * 16)[:-1]
+        return f_off, (int(f_off[-1] + sizes[-1]) + 16 if sizes.shape[0] else 16)
+
+    def stage_blobs(self, blobs: Sequence[bytes]) -> dict:
+        """Encoded files (bytes objects) -> one pinned host buffer + their chunk-level description (host work only)."""
+        sizes = np.array([len(b) for b in blobs], dtype=np.int64)
+        f_off, total = self._layout(sizes)
+        pinned = self._pinned(total)
+        hbuf = pinned.numpy()
+        for k, b in enumerate(blobs):
+            hbuf[f_off[k]:f_off[k] + sizes[k]] = np.frombuffer(b, dtype=np.uint8)
+        return self._probe_staged(pinned, f_off, sizes)
+
+    def stage_files(self, paths: Sequence[str], pool=None) -> dict:
+        """Reads files straight into pinned memory (``readinto``, optionally on the threads of ``pool``): no
+        intermediate bytes objects, no second host copy.  Host work only -- safe to run on a worker thread."""
+        sizes = np.array([os.path.getsize(p) for p in paths], dtype=np.int64)
+        f_off, total = self._layout(sizes)
+        pinned = self._pinned(total)
+        view = memoryview(pinned.numpy())
+
+        def read(i):
+            with open(paths[i], "rb") as f:
+                got = f.readinto(view[int(f_off[i]):int(f_off[i] + sizes[i])])
+            if got != sizes[i]:
+                raise IOError("short read of %s" % paths[i])
+
+        if pool is not None:
+            list(pool.map(read, range(len(paths))))
+        else:
+            for i in range(len(paths)):
+                read(i)
+        return self._probe_staged(pinned, f_off, sizes)
+
+    def decode_staged_png(self, staged: dict, d_files: torch.Tensor, index: np.ndarray, out: torch.Tensor,
+                          out_off: np.ndarray) -> torch.Tensor:
+        """tise_png_decode on the staged files ``index`` (already uploaded as ``d_files``) -> images at
+        ``out[out_off[k]:]``; returns the device status vector (asynchronous: nothing is read back here)."""
+        m = int(index.shape[0])
+        infos = (_lib.PngInfo * m)(*[staged["infos"][int(i)] for i in index])
+        f_off = np.ascontiguousarray(staged["f_off"][index])
+        sizes = np.ascontiguousarray(staged["sizes"][index])
+        out_off = np.ascontiguousarray(out_off, dtype=np.int64)
+        ws = self._buf("_png_ws", int(self.lib.tise_png_decode_workspace_bytes(infos, m)))
+        status = torch.empty(m, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.tise_png_decode(self.ctx, staged["pinned"].data_ptr(), d_files.data_ptr(),
+                                                 f_off.ctypes.data, sizes.ctypes.data, m, out.data_ptr(),
+                                                 out_off.ctypes.data, status.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                 _stream()))
+        return status
+
+    def decode_staged(self, staged: dict, host_fallback: bool = True) -> PackedImages:
+        """Staged files -> RGB8 HWC images in HBM (what ``PIL.Image.open(f).convert("RGB")`` returns, img_data.py:21).
+        8-bit non-interlaced PNGs are inflated / unfiltered on the device (tise_png_decode); any other format (JPEG,
+        16-bit or interlaced PNG) is outside the device decoder and, with ``host_fallback``, is decoded by PIL exactly
+        like the reference does and uploaded into the same pack."""
+        n = staged["n"]
+        on_dev = np.nonzero(staged["supported"])[0]
+        on_host = np.nonzero(~staged["supported"])[0]
+        if len(on_host) and not host_fallback:
+            raise ValueError("decode: file %d is not an 8-bit non-interlaced PNG" % int(on_host[0]))
+        hbuf = staged["pinned"].numpy()
         host_imgs = {}
-        if on_host:
+        if len(on_host):
             import io
 
             from PIL import Image
 
             for i in on_host:
-                host_imgs[i] = np.ascontiguousarray(np.asarray(Image.open(io.BytesIO(blobs[i])).convert("RGB")))
+                o, sz = int(staged["f_off"][i]), int(staged["sizes"][i])
+                host_imgs[int(i)] = np.array(Image.open(io.BytesIO(hbuf[o:o + sz].tobytes())).convert("RGB"), dtype=np.uint8)
         hw = np.zeros((n, 2), dtype=np.int32)
         for i in range(n):
-            hw[i] = host_imgs[i].shape[:2] if i in host_imgs else (infos[i].height, infos[i].width)
+            hw[i] = host_imgs[i].shape[:2] if i in host_imgs else (staged["infos"][i].height, staged["infos"][i].width)
         nbytes = hw[:, 0].astype(np.int64) * hw[:, 1] * 3
         out_off = np.zeros(n, dtype=np.int64)
         if n:
             out_off[1:] = np.cumsum((nbytes + 15) // 16 * 16)[:-1]
         total = int(out_off[-1] + nbytes[-1]) if n else 0
         out = torch.empty(max(total, 16), dtype=torch.uint8, device=self.device)
-        if on_dev:
-            m = len(on_dev)
-            sizes = np.array([len(blobs[i]) for i in on_dev], dtype=np.int64)
-            f_off = np.zeros(m, dtype=np.int64)
-            f_off[1:] = np.cumsum((sizes + 15) // 16 * 16)[:-1]
-            f_total = int(f_off[-1] + sizes[-1]) + 16
-            pinned = torch.empty(f_total, dtype=torch.uint8, pin_memory=True)
-            hbuf = pinned.numpy()
-            for k, i in enumerate(on_dev):
-                hbuf[f_off[k]:f_off[k] + sizes[k]] = np.frombuffer(blobs[i], dtype=np.uint8)
-            d_files = pinned.to(self.device, non_blocking=True)
-            sub = (_lib.PngInfo * m)(*[infos[i] for i in on_dev])
-            ws = self._buf("_png_ws", int(self.lib.tise_png_decode_workspace_bytes(sub, m)))
-            status = torch.empty(m, dtype=torch.int32, device=self.device)
-            o_off = np.ascontiguousarray(out_off[on_dev])
-            with torch.cuda.device(self.device):
-                self._check(self.lib.tise_png_decode(self.ctx, pinned.data_ptr(), d_files.data_ptr(), f_off.ctypes.data,
-                                                     sizes.ctypes.data, m, out.data_ptr(), o_off.ctypes.data,
-                                                     status.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
-            st = status.cpu().numpy()  # synchronises: the pinned staging buffer may be released afterwards
+        if len(on_dev):
+            d_files = staged["pinned"][:staged["total"]].to(self.device, non_blocking=True)
+            status = self.decode_staged_png(staged, d_files, on_dev, out, out_off[on_dev])
+            st = status.cpu().numpy()  # synchronises: the pinned staging buffer may be reused afterwards
             if st.any():
                 k = int(np.nonzero(st)[0][0])
-                raise ImageDecodeError("corrupt PNG stream in file %d (decoder status %d)" % (on_dev[k], int(st[k])))
+                raise ImageDecodeError("corrupt PNG stream in file %d (decoder status %d)" % (int(on_dev[k]), int(st[k])))
         for i, a in host_imgs.items():
             o = int(out_off[i])
             out[o:o + a.size].copy_(torch.from_numpy(a.reshape(-1)))
         return PackedImages(out, out_off, hw)
+
+    def decode_images(self, blobs: Sequence[bytes], host_fallback: bool = True) -> PackedImages:
+        """Encoded image files as bytes objects -> :class:`PackedImages` (see :meth:`decode_staged`)."""
+        return self.decode_staged(self.stage_blobs(blobs), host_fallback)
+
+    def decode_files(self, paths: Sequence[str], host_fallback: bool = True, pool=None) -> PackedImages:
+        """Image files on disk -> :class:`PackedImages`; bytes go file -> pinned memory -> HBM."""
+        return self.decode_staged(self.stage_files(paths, pool), host_fallback)
 
     # ------------------------------------------------------------------ A2 resize
     def resize(self, images: Union[torch.Tensor, Sequence[torch.Tensor], "PackedImages"],

@@ -55,41 +55,47 @@ def collate_u8(batch):
     return list(batch)
 
 
-def _read_file(name):
-    with open(name, "rb") as f:
-        return f.read()
-
-
 class DeviceImageLoader:
     """Iterable of batches for ``calculate_activation_statistics`` / ``get_activations``: same order, same
     ``batch_size`` / ``drop_last`` semantics as the reference's DataLoader(shuffle=False) (fid_score.py:214-217),
-    but every batch is an :class:`~tise_toolbox_b200.engine.PackedImages` decoded on the device
-    (``Engine.decode_images``).  File reads of the next ``prefetch`` batches overlap the GPU work."""
+    but every batch is a :class:`~tise_toolbox_b200.engine.PackedImages` decoded on the device
+    (``Engine.decode_images``).
 
-    def __init__(self, file_names, engine, batch_size, drop_last=True, io_threads=8, prefetch=2):
+    One warp inflates one image, so the decoder needs thousands of images in flight to fill the GPU: files are read
+    and decoded ``decode_batch`` at a time (default 2048, whatever the consumer's ``batch_size`` is -- the
+    reference's 50 / 64 would leave 97 % of the SMs idle) and handed out as ``batch_size`` slices of that pack.
+    File reads of the next group run on ``io_threads`` host threads while the GPU works on the current one."""
+
+    def __init__(self, file_names, engine, batch_size, drop_last=True, io_threads=8, decode_batch=2048):
         self.file_names = list(file_names)
         self.engine = engine
         self.batch_size = int(batch_size)
         self.drop_last = bool(drop_last)
         self.io_threads = int(io_threads)
-        self.prefetch = max(1, int(prefetch))
+        per = max(1, int(decode_batch) // self.batch_size)
+        self.group = per * self.batch_size  # files per decode call: a whole number of consumer batches
 
     def __len__(self):
         n, b = len(self.file_names), self.batch_size
         return n // b if self.drop_last else (n + b - 1) // b
 
     def __iter__(self):
+        from .engine import PackedImages
+
         b = self.batch_size
-        chunks = [self.file_names[i * b:(i + 1) * b] for i in range(len(self))]
-        with ThreadPoolExecutor(max_workers=self.io_threads) as pool:
-            pending = []
-            nxt = 0
-            while nxt < len(chunks) and len(pending) < self.prefetch:
-                pending.append([pool.submit(_read_file, f) for f in chunks[nxt]])
-                nxt += 1
-            while pending:
-                blobs = [f.result() for f in pending.pop(0)]
-                if nxt < len(chunks):
-                    pending.append([pool.submit(_read_file, f) for f in chunks[nxt]])
-                    nxt += 1
-                yield self.engine.decode_images(blobs)
+        n_used = len(self) * b if self.drop_last else len(self.file_names)
+        names = self.file_names[:n_used]
+        groups = [names[i:i + self.group] for i in range(0, len(names), self.group)]
+        if not groups:
+            return
+        # one staging thread reads group k + 1 into the engine's other pinned buffer (itself fanning the reads out over
+        # `io_threads`) while this thread uploads / decodes group k and the consumer runs the trunk on its batches
+        with ThreadPoolExecutor(max_workers=self.io_threads) as readers, ThreadPoolExecutor(max_workers=1) as stager:
+            nxt = stager.submit(self.engine.stage_files, groups[0], readers)
+            for gi, g in enumerate(groups):
+                staged = nxt.result()
+                pack = self.engine.decode_staged(staged)  # returns after the H2D + decode of this group completed
+                if gi + 1 < len(groups):
+                    nxt = stager.submit(self.engine.stage_files, groups[gi + 1], readers)
+                for i in range(0, len(g), b):
+                    yield PackedImages(pack.buf, pack.offsets[i:i + b], pack.hw[i:i + b])
