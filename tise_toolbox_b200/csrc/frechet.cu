@@ -13,6 +13,7 @@
 //   4. Sturm-sequence bisection, one thread per eigenvalue, then sum sqrt(max(lambda, 0)).
 // Everything is fp64 FMA on the CUDA cores; the two GEMMs are the only O(d^3) dense steps.
 #include <math.h>
+#include <stdlib.h>
 
 #include "net.cuh"
 
@@ -314,6 +315,183 @@ __global__ void __launch_bounds__(TRI_THREADS) tri_rank2_kernel(double* __restri
   }
 }
 
+// ---------------------------------------------------------------------------- persistent tridiagonalisation
+// The two kernels above, run per column, cost 2 x 2046 launches whose ~10 us launch + drain latency was 60 % of
+// tise_frechet at d = 2048 (profiles/frechet_launches_r01.txt).  This kernel walks all columns in ONE cooperative
+// launch: every CTA rebuilds the reflector of column k from row k of M (so nothing but p is exchanged), the CTAs
+// split the rows of the symmetric matrix-vector product and of the rank-2 update, and a grid-wide barrier (monotonic
+// atomic counter, acquire / release at gpu scope) separates the two phases.  Data written by other CTAs is read
+// with ld.global.cg (L2): L1 is not coherent across SMs inside one launch.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Reflector of x (length n, in shared memory, x[0] = alpha): returns tau and beta, writes v (v[0] = 1) to out.
+__device__ __forceinline__ void make_reflector(const double* x, int n, double* out, double* red, double& tau, double& beta) {
+  double ss = 0.0;
+  for (int i = 1 + threadIdx.x; i < n; i += TRI_THREADS) ss += x[i] * x[i];
+  ss = block_sum(ss, red);
+  const double alpha = x[0];
+  double scale;
+  if (ss == 0.0) {
+    tau = 0.0;
+    beta = alpha;
+    scale = 0.0;
+  } else {
+    beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+    tau = (beta - alpha) / beta;
+    scale = 1.0 / (alpha - beta);
+  }
+  for (int i = threadIdx.x; i < n; i += TRI_THREADS) out[i] = (i == 0) ? 1.0 : x[i] * scale;
+  __syncthreads();
+}
+
+// Column k's rank-2 update and column k+1's matrix-vector product in ONE pass over the trailing matrix: once
+// w_k is known every CTA can form the updated row k+1 on its own (O(m) work), hence the next reflector v_{k+1};
+// the warp that updates a piece of row i then accumulates its part of p_{k+1}[i] = tau' sum_j Mnew[i][j] v_{k+1}[j]
+// from the values it has in registers.  One grid barrier and one read + write of the trailing matrix per column (the
+// two-kernel form: two launches, three passes).  The matrix is L2-resident and every step is a round trip to L2
+// (~1 us), so the work is cut into (row, 1024-column chunk) items with 16 independent loads in flight per lane, and
+// the chunk partials of p are summed by the readers (no atomics: the result does not depend on the schedule).
+constexpr int TRI_CHUNK = 1024;
+constexpr int TRI_MAX_CHUNKS = 4;  // d <= 4096
+
+__device__ __forceinline__ void tri_pass(double* M, int d, int row0, int col0, int mn, const double* v, const double* w,
+                                         const double* vn, double tau_n, bool update, double* p_out) {
+  // rows row0 + t, columns col0 + u, t, u in [0, mn); v / w are indexed from the trailing index of (row0, col0)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWarps = TRI_THREADS / 32;
+  const int nch = (mn + TRI_CHUNK - 1) / TRI_CHUNK;
+  const int items = mn * nch;
+  for (int it = blockIdx.x * kWarps + warp; it < items; it += gridDim.x * kWarps) {
+    const int t = it / nch, ch = it - t * nch;
+    double* row = M + (size_t)(row0 + t) * d + col0;
+    const double vi = update ? v[t] : 0.0, wi = update ? w[t] : 0.0;
+    double acc = 0.0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      double val[16];
+      const int u0 = ch * TRI_CHUNK + half * 512 + lane;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int u = u0 + e * 32;
+        val[e] = u < mn ? __ldcg(row + u) : 0.0;
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int u = u0 + e * 32;
+        if (u < mn) {
+          if (update) {
+            val[e] -= vi * w[u] + wi * v[u];
+            row[u] = val[e];
+          }
+          acc = fma(val[e], vn[u], acc);
+        }
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) p_out[(size_t)ch * d + t] = tau_n * acc;
+  }
+}
+
+__global__ void __launch_bounds__(TRI_THREADS) tri_persistent_kernel(double* M, int d, double* pbuf0, double* pbuf1,
+                                                                     double* diag, double* off, unsigned* bar) {
+  extern __shared__ double sm[];  // v[d], w[d], r[d], vn[d]
+  __shared__ double red[32];
+  double* v = sm;
+  double* w = sm + d;
+  double* r = sm + 2 * (size_t)d;
+  double* vn = sm + 3 * (size_t)d;
+  const unsigned nb = gridDim.x;
+  unsigned phase = 0;
+  double tau, beta;
+  // prologue: reflector of column 0 and p_0 = tau M22 v
+  {
+    const int m = d - 1;
+    for (int i = threadIdx.x; i < m; i += TRI_THREADS) r[i] = __ldcg(M + 1 + i);
+    __syncthreads();
+    make_reflector(r, m, v, red, tau, beta);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      diag[0] = __ldcg(M);
+      off[0] = beta;
+    }
+    tri_pass(M, d, 1, 1, m, nullptr, nullptr, v, tau, false, pbuf0);
+    grid_barrier(bar, ++phase * nb);
+  }
+  for (int k = 0; k + 2 < d; ++k) {
+    const int m = d - k - 1;  // trailing matrix of column k: rows / columns k+1 .. d-1
+    // p_k is read from one buffer while p_{k+1} is written to the other: a CTA that is ahead must not overwrite the
+    // vector a slower CTA is still reading
+    const double* p_in = (k & 1) ? pbuf1 : pbuf0;
+    double* p_out = (k & 1) ? pbuf0 : pbuf1;
+    const int nch = (m + TRI_CHUNK - 1) / TRI_CHUNK;
+    // w = p - (tau / 2)(p . v) v, and the old row k+1 (index 0 of the trailing matrix; nobody writes it during this
+    // column) -- all loads of a thread issued before the first use
+    const double* row0 = M + (size_t)(k + 1) * d + k + 1;
+    double dot = 0.0;
+    for (int i0 = threadIdx.x; i0 < m; i0 += 4 * TRI_THREADS) {
+      double pv[4][TRI_MAX_CHUNKS], rv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i0 + e * TRI_THREADS;
+#pragma unroll
+        for (int c = 0; c < TRI_MAX_CHUNKS; ++c) pv[e][c] = (i < m && c < nch) ? __ldcg(p_in + (size_t)c * d + i) : 0.0;
+        rv[e] = i < m ? __ldcg(row0 + i) : 0.0;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i0 + e * TRI_THREADS;
+        if (i < m) {
+          double pi = pv[e][0];
+#pragma unroll
+          for (int c = 1; c < TRI_MAX_CHUNKS; ++c) pi += pv[e][c];
+          w[i] = pi;
+          r[i] = rv[e];
+          dot += v[i] * pi;
+        }
+      }
+    }
+    dot = block_sum(dot, red);
+    const double c = 0.5 * tau * dot;
+    for (int i = threadIdx.x; i < m; i += TRI_THREADS) w[i] -= c * v[i];
+    __syncthreads();
+    const double v0 = v[0], w0 = w[0];
+    for (int j = threadIdx.x; j < m; j += TRI_THREADS) r[j] -= v0 * w[j] + w0 * v[j];  // updated row k+1
+    __syncthreads();
+    if (m == 2) {  // last column: the 2 x 2 tail is the end of the tridiagonal
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        diag[d - 2] = r[0];
+        off[d - 2] = r[1];
+        diag[d - 1] = __ldcg(M + (size_t)(d - 1) * d + d - 1) - 2.0 * v[1] * w[1];
+      }
+      break;
+    }
+    double tau_n, beta_n;
+    make_reflector(r + 1, m - 1, vn, red, tau_n, beta_n);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      diag[k + 1] = r[0];
+      off[k + 1] = beta_n;
+    }
+    // fused pass over rows / columns k+2 .. d-1
+    tri_pass(M, d, k + 2, k + 2, m - 1, v + 1, w + 1, vn, tau_n, true, p_out);
+    grid_barrier(bar, ++phase * nb);
+    double* tmp = v;
+    v = vn;
+    vn = tmp;
+    tau = tau_n;
+  }
+}
+
 __global__ void tri_tail_kernel(const double* M, int d, double* diag, double* off) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (d >= 2) {
@@ -374,23 +552,38 @@ __global__ void __launch_bounds__(256) sturm_sqrt_trace_kernel(const double* __r
   const double norm = fmax(fabs(glo), fabs(ghi));
   const double tiny = fmax(norm * 1e-300, 1e-300);
   double part = 0.0, negmax = 0.0;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < d; idx += gridDim.x * blockDim.x) {
+  // One WARP per eigenvalue, 32-way multisection: lane j counts the eigenvalues below l + (j + 1)(h - l) / 33, so the
+  // bracket shrinks 33x per sweep of the d-long (serial, division-bound) Sturm recurrence: ~11 sweeps instead of the
+  // ~55 of plain bisection.
+  const int lane = threadIdx.x & 31, warp_in_grid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int warps_in_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int idx = warp_in_grid; idx < d; idx += warps_in_grid) {
     double l = glo, h = ghi;
-    for (int it = 0; it < 120; ++it) {
-      const double mid = 0.5 * (l + h);
-      if (mid <= l || mid >= h) break;
-      int cnt = 0;  // number of eigenvalues < mid
+    for (int it = 0; it < 64; ++it) {
+      const double step = (h - l) * (1.0 / 33.0);
+      const double xq = l + step * (double)(lane + 1);
+      int cnt = 0;  // number of eigenvalues < xq
       double q = 1.0;
       for (int j = 0; j < d; ++j) {
-        q = a[j] - mid - (j > 0 ? b2[j] / q : 0.0);
+        q = a[j] - xq - (j > 0 ? b2[j] / q : 0.0);
         if (fabs(q) < tiny) q = -tiny;
         cnt += q < 0.0;
       }
-      if (cnt > idx) h = mid; else l = mid;
+      const unsigned above = __ballot_sync(0xffffffffu, cnt > idx && xq < h);  // candidates for the new upper end
+      const int first = above ? __ffs(above) - 1 : 32;
+      const double x_hi = __shfl_sync(0xffffffffu, xq, first & 31), x_lo = __shfl_sync(0xffffffffu, xq, (first + 31) & 31);
+      const double nh = first < 32 ? x_hi : h;
+      double nl = first > 0 ? x_lo : l;
+      if (!(nl > l)) nl = l;
+      if (!(nh - nl < h - l)) break;  // no progress: the bracket is at the resolution of the arithmetic
+      l = nl;
+      h = nh;
     }
     const double lam = 0.5 * (l + h);
-    if (lam > 0.0) part += sqrt(lam);
-    else negmax = fmax(negmax, -lam);
+    if (lane == 0) {
+      if (lam > 0.0) part += sqrt(lam);
+      else negmax = fmax(negmax, -lam);
+    }
   }
   part = block_sum(part, red);
   if (threadIdx.x == 0 && part != 0.0) atomicAdd(scal + FR_TRSQRT, part);
@@ -413,8 +606,8 @@ static FrWs fr_layout(int d) {
   w.off_S2 = o; o += mat;
   w.off_T = o; o += mat;
   w.off_M = o; o += mat;
-  w.off_v = o; o += vec;
-  w.off_p = o; o += vec;
+  w.off_v = o; o += 4 * vec;  // (TRI_MAX_CHUNKS chunk partials of p, double-buffered: v and p)
+  w.off_p = o; o += 4 * vec;
   w.off_diag = o; o += vec;
   w.off_off = o; o += vec;
   w.off_scal = o; o += 256;
@@ -470,21 +663,41 @@ static int frechet_once(tise_ctx* ctx, const double* mu1, const double* s1, cons
   TISE_LAUNCH_CHECK(ctx);
 
   // 3. tridiagonalise
-  for (int k = 0; k + 2 < d; ++k) {
-    const int m = d - k - 1;
-    int g1 = (m + 7) / 8;
-    if (g1 > 2 * ctx->num_sms) g1 = 2 * ctx->num_sms;
-    tri_reflect_symv_kernel<<<g1, TRI_THREADS, (size_t)m * 8, st>>>(M, d, k, vbuf, pbuf, diag, off, scal);
-    TISE_LAUNCH_CHECK(ctx);
-    int g2 = m < 2 * ctx->num_sms ? m : 2 * ctx->num_sms;
-    tri_rank2_kernel<<<g2, TRI_THREADS, (size_t)m * 16, st>>>(M, d, k, vbuf, pbuf, scal);
+  static int legacy = -1;
+  if (legacy < 0) legacy = getenv("TISE_FRECHET_LEGACY") ? atoi(getenv("TISE_FRECHET_LEGACY")) : 0;
+  if (!legacy && d > 2) {  // one cooperative launch for all columns
+    unsigned* bar = (unsigned*)(scal + FR_NSLOTS);
+    TISE_CUDA(ctx, cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+    const size_t smem = (size_t)d * 32;
+    int per_sm = 0;
+    TISE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tri_persistent_kernel, TRI_THREADS, smem));
+    if (per_sm < 1) return fail(ctx, TISE_ERR_CUDA, "tise_frechet: tri_persistent_kernel does not fit on an SM");
+    static int want = -1;
+    if (want < 0) want = getenv("TISE_FRECHET_CTAS_PER_SM") ? atoi(getenv("TISE_FRECHET_CTAS_PER_SM")) : 2;
+    int grid = (per_sm > want ? (want > 0 ? want : 1) : per_sm) * ctx->num_sms;
+    int dd = d;
+    void* args[] = {(void*)&M, (void*)&dd, (void*)&pbuf, (void*)&vbuf, (void*)&diag, (void*)&off, (void*)&bar};
+    TISE_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)tri_persistent_kernel, dim3(grid), dim3(TRI_THREADS), args, smem, st));
+    ctx->launches++;
+  } else {
+    for (int k = 0; k + 2 < d; ++k) {
+      const int m = d - k - 1;
+      int g1 = (m + 7) / 8;
+      if (g1 > 2 * ctx->num_sms) g1 = 2 * ctx->num_sms;
+      tri_reflect_symv_kernel<<<g1, TRI_THREADS, (size_t)m * 8, st>>>(M, d, k, vbuf, pbuf, diag, off, scal);
+      TISE_LAUNCH_CHECK(ctx);
+      int g2 = m < 2 * ctx->num_sms ? m : 2 * ctx->num_sms;
+      tri_rank2_kernel<<<g2, TRI_THREADS, (size_t)m * 16, st>>>(M, d, k, vbuf, pbuf, scal);
+      TISE_LAUNCH_CHECK(ctx);
+    }
+  }
+  if (legacy || d <= 2) {  // (the persistent kernel publishes the 2 x 2 tail itself)
+    tri_tail_kernel<<<1, 32, 0, st>>>(M, d, diag, off);
     TISE_LAUNCH_CHECK(ctx);
   }
-  tri_tail_kernel<<<1, 32, 0, st>>>(M, d, diag, off);
-  TISE_LAUNCH_CHECK(ctx);
 
   // 4. eigenvalues -> sum of square roots
-  sturm_sqrt_trace_kernel<<<(d + 255) / 256, 256, (size_t)d * 16, st>>>(diag, off, d, scal);
+  sturm_sqrt_trace_kernel<<<(d + 7) / 8, 256, (size_t)d * 16, st>>>(diag, off, d, scal);  // one warp per eigenvalue
   TISE_LAUNCH_CHECK(ctx);
 
   TISE_CUDA(ctx, cudaMemcpyAsync(h_scal, scal, FR_NSLOTS * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -511,6 +724,7 @@ extern "C" int tise_frechet(tise_ctx* ctx, const double* d_mu1, const double* d_
   static bool configured = false;
   if (!configured) {
     TISE_CUDA(ctx, cudaFuncSetAttribute(tri_rank2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
+    TISE_CUDA(ctx, cudaFuncSetAttribute(tri_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 32));
     TISE_CUDA(ctx, cudaFuncSetAttribute(sturm_sqrt_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
     configured = true;
   }
