@@ -367,7 +367,7 @@ constexpr int TRI_CHUNK = 1024;
 constexpr int TRI_MAX_CHUNKS = 4;  // d <= 4096
 
 __device__ __forceinline__ void tri_pass(double* M, int d, int row0, int col0, int mn, const double* v, const double* w,
-                                         const double* vn, double tau_n, bool update, double* p_out) {
+                                         const double* vn, double tau_n, bool update, double* p_out, int debug = 0) {
   // rows row0 + t, columns col0 + u, t, u in [0, mn); v / w are indexed from the trailing index of (row0, col0)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarps = TRI_THREADS / 32;
@@ -393,7 +393,7 @@ __device__ __forceinline__ void tri_pass(double* M, int d, int row0, int col0, i
         if (u < mn) {
           if (update) {
             val[e] -= vi * w[u] + wi * v[u];
-            row[u] = val[e];
+            if (!(debug & 4)) row[u] = val[e];
           }
           acc = fma(val[e], vn[u], acc);
         }
@@ -405,7 +405,7 @@ __device__ __forceinline__ void tri_pass(double* M, int d, int row0, int col0, i
 }
 
 __global__ void __launch_bounds__(TRI_THREADS) tri_persistent_kernel(double* M, int d, double* pbuf0, double* pbuf1,
-                                                                     double* diag, double* off, unsigned* bar) {
+                                                                     double* diag, double* off, unsigned* bar, int debug) {
   extern __shared__ double sm[];  // v[d], w[d], r[d], vn[d]
   __shared__ double red[32];
   double* v = sm;
@@ -483,8 +483,8 @@ __global__ void __launch_bounds__(TRI_THREADS) tri_persistent_kernel(double* M, 
       off[k + 1] = beta_n;
     }
     // fused pass over rows / columns k+2 .. d-1
-    tri_pass(M, d, k + 2, k + 2, m - 1, v + 1, w + 1, vn, tau_n, true, p_out);
-    grid_barrier(bar, ++phase * nb);
+    if (!(debug & 1)) tri_pass(M, d, k + 2, k + 2, m - 1, v + 1, w + 1, vn, tau_n, !(debug & 8), p_out, debug);
+    if (!(debug & 2)) grid_barrier(bar, ++phase * nb);
     double* tmp = v;
     v = vn;
     vn = tmp;
@@ -676,7 +676,9 @@ static int frechet_once(tise_ctx* ctx, const double* mu1, const double* s1, cons
     if (want < 0) want = getenv("TISE_FRECHET_CTAS_PER_SM") ? atoi(getenv("TISE_FRECHET_CTAS_PER_SM")) : 2;
     int grid = (per_sm > want ? (want > 0 ? want : 1) : per_sm) * ctx->num_sms;
     int dd = d;
-    void* args[] = {(void*)&M, (void*)&dd, (void*)&pbuf, (void*)&vbuf, (void*)&diag, (void*)&off, (void*)&bar};
+    static int dbg = -1;
+    if (dbg < 0) dbg = getenv("TISE_FRECHET_DEBUG") ? atoi(getenv("TISE_FRECHET_DEBUG")) : 0;
+    void* args[] = {(void*)&M, (void*)&dd, (void*)&pbuf, (void*)&vbuf, (void*)&diag, (void*)&off, (void*)&bar, (void*)&dbg};
     TISE_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)tri_persistent_kernel, dim3(grid), dim3(TRI_THREADS), args, smem, st));
     ctx->launches++;
   } else {
