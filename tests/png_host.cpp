@@ -20,7 +20,8 @@ int host_inflate(const uint8_t* stream, uint32_t n, uint8_t* out, uint32_t cap, 
   Huff* hl = new Huff;
   Huff* hd = new Huff;
   uint8_t lens[320];
-  const int st = inflate_zlib<1>(words.data(), n, out, cap, out_len, adler, hl, hd, lens, 0);
+  uint16_t win[32];
+  const int st = inflate_zlib<1>(words.data(), n, out, cap, out_len, adler, hl, hd, lens, win, 0);
   delete hl;
   delete hd;
   return st;

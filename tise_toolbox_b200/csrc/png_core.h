@@ -181,11 +181,12 @@ TISE_HD int huff_decode(const Huff* h, BitReader& r) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// zlib (RFC 1950) stream -> out[0 .. out_cap).  lens: 320 bytes of scratch next to the two tables.
+// zlib (RFC 1950) stream -> out[0 .. out_cap).  lens: 320 bytes, win: 32 x uint16 of scratch next to the two tables.
 // Returns a Status; *out_len = bytes produced, *adler = the stream's Adler-32 trailer.
 template <int LANES>
 TISE_HD int inflate_zlib(const uint32_t* words, uint32_t stream_bytes, uint8_t* out, uint32_t out_cap, uint32_t* out_len,
-                         uint32_t* adler, Huff* hl, Huff* hd, uint8_t* lens, int lane) {
+                         uint32_t* adler, Huff* hl, Huff* hd, uint8_t* lens, uint16_t* win, int lane) {
+  (void)win;  // 32 entries of per-warp scratch for the literal-run decoder (device build only)
   BitReader r;
   br_init(r, words, stream_bytes);
   *out_len = 0;
@@ -287,15 +288,23 @@ TISE_HD int inflate_zlib(const uint32_t* words, uint32_t stream_bytes, uint8_t* 
       {
         int p = 0, nlit = 0;
 #if defined(__CUDA_ARCH__)
+        // lane k: (bit position after the code starting at k) << 8 | literal, or 0xff00 if no <= 10-bit literal code
+        // starts at k / it does not end inside the buffered bits.  The 32 candidates go to shared memory so that a hop
+        // is one broadcast load instead of a warp-synchronous shuffle.
         const uint32_t mine = hl->fast[(uint32_t)(r.buf >> lane) & (kFastSize - 1)];
+        const int l_mine = (int)(mine >> 9);
+        const bool ok = mine != 0u && !(mine & 256u) && lane + l_mine <= r.cnt;
+        TISE_SYNCWARP();  // the previous window's readers are done
+        win[lane] = ok ? (uint16_t)(((lane + l_mine) << 8) | (mine & 255u)) : (uint16_t)0xff00;
+        TISE_SYNCWARP();
         uint32_t my_sym = 0;
         while (p < 32) {
-          const uint32_t e = __shfl_sync(0xffffffffu, mine, p);
-          const int l = (int)(e >> 9);
-          if (e == 0u || (e & 256u) || p + l > r.cnt) break;
-          if (lane == nlit) my_sym = e & 255u;
+          const uint32_t e = win[p];
+          const int np = (int)(e >> 8);
+          if (np == 0xff) break;
+          if (lane == nlit) my_sym = e;
           ++nlit;
-          p += l;
+          p = np;
         }
         if (nlit) {
           if (op + (uint32_t)nlit > out_cap) return kOutputOverflow;

@@ -61,6 +61,7 @@ constexpr int kInflateWarps = 4;
 struct InflateSmem {
   png::Huff hl, hd;
   uint8_t lens[320];
+  uint16_t win[32];
 };
 
 __global__ void __launch_bounds__(kInflateWarps * 32) png_inflate_kernel(PngDesc* __restrict__ descs, int n, uint8_t* ws,
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(kInflateWarps * 32) png_inflate_kernel(PngDesc
   uint32_t out_len = 0, adler = 0;
   int st = png::inflate_zlib<32>(reinterpret_cast<const uint32_t*>(ws + d.stream_off), (uint32_t)d.stream_bytes,
                                  ws + d.raw_off, (uint32_t)d.raw_bytes, &out_len, &adler, &sm[warp].hl, &sm[warp].hd,
-                                 sm[warp].lens, lane);
+                                 sm[warp].lens, sm[warp].win, lane);
   if (st == png::kOk && out_len != (uint32_t)d.raw_bytes) st = png::kSizeMismatch;
   if (lane == 0) {
     d.adler = adler;

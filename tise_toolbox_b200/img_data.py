@@ -62,11 +62,11 @@ class DeviceImageLoader:
     (``Engine.decode_images``).
 
     One warp inflates one image, so the decoder needs thousands of images in flight to fill the GPU: files are read
-    and decoded ``decode_batch`` at a time (default 2048, whatever the consumer's ``batch_size`` is -- the
+    and decoded ``decode_batch`` at a time (default 4096, whatever the consumer's ``batch_size`` is -- the
     reference's 50 / 64 would leave 97 % of the SMs idle) and handed out as ``batch_size`` slices of that pack.
     File reads of the next group run on ``io_threads`` host threads while the GPU works on the current one."""
 
-    def __init__(self, file_names, engine, batch_size, drop_last=True, io_threads=8, decode_batch=2048):
+    def __init__(self, file_names, engine, batch_size, drop_last=True, io_threads=8, decode_batch=4096):
         self.file_names = list(file_names)
         self.engine = engine
         self.batch_size = int(batch_size)
