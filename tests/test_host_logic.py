@@ -134,3 +134,12 @@ def test_ranking_table_matches_the_reference_script_golden(tmp_path):
         assert ("%g" % scores[m][-1]) in table_dir
     with pytest.raises(KeyError):
         rs.update_method_scores(str(tmp_path), "x", BLEU=1.0)
+
+
+def test_shard_batches_partition_is_exactly_the_drop_last_set():
+    for n, b, world in [(1000, 50, 8), (1003, 50, 8), (23, 5, 2), (7, 10, 4), (30000, 64, 8), (49, 50, 3)]:
+        ranges = [pipeline.shard_batches(n, b, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == (n // b) * b
+        for (lo, hi), (lo2, _) in zip(ranges, ranges[1:]):
+            assert hi == lo2
+        assert all((hi - lo) % b == 0 and hi >= lo for lo, hi in ranges)

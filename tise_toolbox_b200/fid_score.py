@@ -79,9 +79,7 @@ def calculate_frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
     return np.float64(value)
 
 
-def calculate_activation_statistics(images, model, batch_size=64, dims=2048, cuda=False, verbose=True):
-    """fid_score.py:174-196, one pass: the batches' sum(x) and sum(x x^T) accumulate in fp64 on the device
-    and only (mu, sigma) come back -- the N x dims activation matrix is never materialised."""
+def _accumulate_moments(images, model, batch_size, dims):
     model.eval()
     mom = Moments(model.engine, dims)
     for batch in images:
@@ -89,9 +87,24 @@ def calculate_activation_statistics(images, model, batch_size=64, dims=2048, cud
             raise ValueError("calculate_activation_statistics: batch of %d, expected %d (drop_last=True, "
                              "fid_score.py:216)" % (len(batch), batch_size))
         mom.update(_batch_features(batch, model, dims))
+    return mom
+
+
+def calculate_activation_statistics(images, model, batch_size=64, dims=2048, cuda=False, verbose=True):
+    """fid_score.py:174-196, one pass: the batches' sum(x) and sum(x x^T) accumulate in fp64 on the device
+    and only (mu, sigma) come back -- the N x dims activation matrix is never materialised."""
+    mom = _accumulate_moments(images, model, batch_size, dims)
     if verbose:
         print(" done")
     return mom.finalize()
+
+
+def _world():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
 
 
 def _compute_statistics_of_path(path, model, batch_size, dims, cuda):
@@ -103,12 +116,24 @@ def _compute_statistics_of_path(path, model, batch_size, dims, cuda):
         # fid_score.py:206-217 with decode, Resize and ToTensor moved onto the GPU: host threads only read bytes.
         # TISE_GPU_DECODE=0 keeps PIL decode on DataLoader workers (resize / ToTensor still on the GPU).
         dataset = img_data.Dataset(path, raw_u8=True)
+        rank, world = _world()
+        if world > 1:
+            # launched under torchrun: every rank takes a contiguous run of whole batches of the folder and the packed
+            # moments are summed with ONE all-reduce; each rank ends up with the same (mu, sigma)
+            from .pipeline import shard_batches
+
+            lo, hi = shard_batches(len(dataset.file_names), batch_size, rank, world)
+            dataset.file_names = dataset.file_names[lo:hi]
         if os.environ.get("TISE_GPU_DECODE", "1") != "0":
             dataloader = img_data.DeviceImageLoader(dataset.file_names, model.engine, batch_size, drop_last=True)
         else:
             dataloader = torch.utils.data.DataLoader(dataset=dataset, batch_size=batch_size, shuffle=False,
                                                      drop_last=True, num_workers=8, collate_fn=img_data.collate_u8)
-        m, s = calculate_activation_statistics(dataloader, model, batch_size, dims, cuda)
+        mom = _accumulate_moments(dataloader, model, batch_size, dims)
+        if world > 1:
+            mom.allreduce()
+        print(" done")
+        m, s = mom.finalize()
     return m, s
 
 
@@ -130,17 +155,37 @@ def save_statistics(path, mu, sigma):
     np.savez(path, mu=mu, sigma=sigma)
 
 
-if __name__ == "__main__":
-    args = parser.parse_args()
-    if args.gpu != "":
+def main(argv=None):
+    args = parser.parse_args(argv)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:  # torchrun --nproc-per-node N -m tise_toolbox_b200.fid_score ...: one process per GPU
+        import torch.distributed as dist
+
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    elif args.gpu != "":
         os.environ["CUDA_VISIBLE_DEVICES"] = args.gpu
     if args.weights:
         os.environ["TISE_INCEPTION_WEIGHTS"] = args.weights
     paths = [args.path1, args.path2]
-    print(paths)
+    rank = int(os.environ.get("RANK", "0"))
+    if rank == 0:
+        print(paths)
     fid_value = calculate_fid_given_paths(paths, args.batch_size, args.gpu, args.dims).item()
     tag = "O-FID" if args.ofid else "FID"
-    if args.saved_file:
-        with open(args.saved_file, "w") as f:
-            f.write(f"{tag}: {fid_value}")
-    print(f"{tag}: {fid_value}")
+    if rank == 0:
+        if args.saved_file:
+            with open(args.saved_file, "w") as f:
+                f.write(f"{tag}: {fid_value}")
+        print(f"{tag}: {fid_value}")
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+    return fid_value
+
+
+if __name__ == "__main__":
+    main()

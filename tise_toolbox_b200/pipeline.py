@@ -20,6 +20,14 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return (rank * n) // world, ((rank + 1) * n) // world
 
 
+def shard_batches(n_files: int, batch_size: int, rank: int, world: int) -> Tuple[int, int]:
+    """File index range [lo, hi) of ``rank`` when a folder is evaluated by ``world`` processes: the reference's
+    ``drop_last=True`` (fid_score.py:216) is applied to the whole set first, then whole batches are dealt out in
+    contiguous runs, so every rank sees full batches only and the union is exactly what one process would use."""
+    lo, hi = shard_range(n_files // batch_size if batch_size > 0 else 0, rank, world)
+    return lo * batch_size, hi * batch_size
+
+
 def format_result(kind: str, a: float, b: Optional[float] = None) -> str:
     """The one-line result files of the reference, byte for byte."""
     if kind == "fid":
