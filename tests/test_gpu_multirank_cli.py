@@ -41,6 +41,8 @@ def test_fid_cli_two_ranks_equals_one(tmp_path):
                          ["--saved_file", str(tmp_path / "fid.txt")], env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert two.returncode == 0, two.stderr[-2000:]
     a, b = _fid(one.stdout), _fid(two.stdout)
-    assert abs(a - b) <= 1e-9 * abs(a), (a, b)
+    # 130 / 127 images in 2048 dimensions: rank-deficient covariances, where tr sqrt(s1 s2) responds to the 1e-16
+    # summation-order differences of the fp64 moments with O(sqrt(eps)) -- measured 1.6e-8 relative on 2 x B200
+    assert abs(a - b) <= 1e-6 * abs(a), (a, b)
     assert open(str(tmp_path / "fid.txt")).read() == "FID: %s" % re.findall(r"^FID: (\S+)$", two.stdout, flags=re.M)[-1]
     assert two.stdout.count("FID: ") == 1  # rank 0 alone reports
