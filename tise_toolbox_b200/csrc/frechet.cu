@@ -559,23 +559,52 @@ __global__ void __launch_bounds__(256) sturm_sqrt_trace_kernel(const double* __r
   const int warps_in_grid = (gridDim.x * blockDim.x) >> 5;
   for (int idx = warp_in_grid; idx < d; idx += warps_in_grid) {
     double l = glo, h = ghi;
-    for (int it = 0; it < 64; ++it) {
-      const double step = (h - l) * (1.0 / 33.0);
-      const double xq = l + step * (double)(lane + 1);
+    for (int it = 0; it < 16; ++it) {  // 33^11 > 2^53: eleven sweeps resolve a bracket of any width
+      const double width = h - l;
+      if (!(width > 4.0 * 2.220446049250313e-16 * fmax(fabs(l), fabs(h)))) break;  // at the resolution of fp64
+      const double xq = l + width * (1.0 / 33.0) * (double)(lane + 1);
+      const bool inside = xq > l && xq < h;
+      // Sturm count = sign changes of the leading principal minors p_j(xq) = (a_j - xq) p_{j-1} - b_j^2 p_{j-2}:
+      // the multiplicative form of the recurrence (no fp64 division on the d-long dependent chain; the quotient form
+      // q_j = p_j / p_{j-1} costs ~300 cycles per step), both minors rescaled by a power of two whenever they leave
+      // [2^-500, 2^500].  An exact zero counts like a negative quotient (sign opposite to its predecessor), and
+      // b_j^2 == 0 splits the matrix: the recurrence restarts and the counts of the blocks add up.
       int cnt = 0;  // number of eigenvalues < xq
-      double q = 1.0;
-      for (int j = 0; j < d; ++j) {
-        q = a[j] - xq - (j > 0 ? b2[j] / q : 0.0);
-        if (fabs(q) < tiny) q = -tiny;
-        cnt += q < 0.0;
+      double pp = 1.0, pc = a[0] - xq;
+      bool neg = !(pc > 0.0);  // sign of pc relative to "+": a zero takes the sign opposite to its predecessor (+)
+      cnt += neg;
+      for (int j = 1; j < d; ++j) {
+        const double bj = b2[j];
+        double pn;
+        bool nneg;
+        if (bj == 0.0) {
+          pn = a[j] - xq;
+          pc = 1.0;
+          nneg = !(pn > 0.0);
+          cnt += nneg;
+        } else {
+          pn = fma(a[j] - xq, pc, -(bj * pp));
+          nneg = pn == 0.0 ? !neg : pn < 0.0;
+          cnt += nneg != neg;
+          const double m = fabs(pn);
+          if (m > 0x1p500) {
+            pn *= 0x1p-500;
+            pc *= 0x1p-500;
+          } else if (m < 0x1p-500 && m != 0.0) {
+            pn *= 0x1p500;
+            pc *= 0x1p500;
+          }
+        }
+        pp = pc;
+        pc = pn;
+        neg = nneg;
       }
-      const unsigned above = __ballot_sync(0xffffffffu, cnt > idx && xq < h);  // candidates for the new upper end
-      const int first = above ? __ffs(above) - 1 : 32;
-      const double x_hi = __shfl_sync(0xffffffffu, xq, first & 31), x_lo = __shfl_sync(0xffffffffu, xq, (first + 31) & 31);
-      const double nh = first < 32 ? x_hi : h;
-      double nl = first > 0 ? x_lo : l;
-      if (!(nl > l)) nl = l;
-      if (!(nh - nl < h - l)) break;  // no progress: the bracket is at the resolution of the arithmetic
+      const unsigned above = __ballot_sync(0xffffffffu, inside && cnt > idx);   // candidates for the new upper end
+      const unsigned below = __ballot_sync(0xffffffffu, inside && cnt <= idx);  // candidates for the new lower end
+      const int first = above ? __ffs(above) - 1 : 0, last = below ? 31 - __clz(below) : 0;
+      const double x_hi = __shfl_sync(0xffffffffu, xq, first), x_lo = __shfl_sync(0xffffffffu, xq, last);
+      const double nh = above ? x_hi : h, nl = below ? x_lo : l;
+      if (!(nl < nh) || !(nh - nl < width)) break;  // (a non-monotonic count or no progress: keep the current bracket)
       l = nl;
       h = nh;
     }

@@ -82,6 +82,12 @@ def calculate_frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
 def _accumulate_moments(images, model, batch_size, dims):
     model.eval()
     mom = Moments(model.engine, dims)
+    if hasattr(images, "groups"):
+        # DeviceImageLoader: the sums do not depend on how the set is cut into batches, so whole decode groups (a whole
+        # number of drop_last batches each) go through the trunk at once instead of batch_size images per call
+        for pack in images.groups():
+            mom.update(_batch_features(pack, model, dims))
+        return mom
     for batch in images:
         if len(batch) != batch_size:
             raise ValueError("calculate_activation_statistics: batch of %d, expected %d (drop_last=True, "

@@ -79,9 +79,10 @@ class DeviceImageLoader:
         n, b = len(self.file_names), self.batch_size
         return n // b if self.drop_last else (n + b - 1) // b
 
-    def __iter__(self):
-        from .engine import PackedImages
-
+    def groups(self):
+        """The decoded packs themselves, ``decode_batch`` files at a time (a whole number of consumer batches each).
+        Consumers whose result does not depend on how the set is cut into batches (the FID moments, the IS partial
+        sums) take these instead of the ``batch_size`` slices: 50 images per trunk call would leave the GPU idle."""
         b = self.batch_size
         n_used = len(self) * b if self.drop_last else len(self.file_names)
         names = self.file_names[:n_used]
@@ -89,7 +90,7 @@ class DeviceImageLoader:
         if not groups:
             return
         # one staging thread reads group k + 1 into the engine's other pinned buffer (itself fanning the reads out over
-        # `io_threads`) while this thread uploads / decodes group k and the consumer runs the trunk on its batches
+        # `io_threads`) while this thread uploads / decodes group k and the consumer runs the trunk on it
         with ThreadPoolExecutor(max_workers=self.io_threads) as readers, ThreadPoolExecutor(max_workers=1) as stager:
             nxt = stager.submit(self.engine.stage_files, groups[0], readers)
             for gi, g in enumerate(groups):
@@ -97,5 +98,12 @@ class DeviceImageLoader:
                 pack = self.engine.decode_staged(staged)  # returns after the H2D + decode of this group completed
                 if gi + 1 < len(groups):
                     nxt = stager.submit(self.engine.stage_files, groups[gi + 1], readers)
-                for i in range(0, len(g), b):
-                    yield PackedImages(pack.buf, pack.offsets[i:i + b], pack.hw[i:i + b])
+                yield pack
+
+    def __iter__(self):
+        from .engine import PackedImages
+
+        b = self.batch_size
+        for pack in self.groups():
+            for i in range(0, len(pack), b):
+                yield PackedImages(pack.buf, pack.offsets[i:i + b], pack.hw[i:i + b])

@@ -43,8 +43,8 @@ def inception_score(imgs, cuda=True, batch_size=32, resize=False, splits=1, stat
                                                  collate_fn=(lambda b: list(b)) if raw else None)
     parts = ISPartials(engine, engine.num_classes, splits)
     start = 0
-    for batch in dataloader:
-        if on_device:
+    for batch in (dataloader.groups() if on_device else dataloader):
+        if on_device:  # whole decode groups: the split of an image depends on its global index, not on the batching
             feat = engine.features(batch)
         elif raw:
             feat = engine.features([t.to(engine.device) for t in batch])
