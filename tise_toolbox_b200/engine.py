@@ -279,11 +279,12 @@ class Engine:
                                                  _stream()))
         return status
 
-    def decode_staged(self, staged: dict, host_fallback: bool = True) -> PackedImages:
+    def decode_staged(self, staged: dict, host_fallback: bool = True, host_decoder=None) -> PackedImages:
         """Staged files -> RGB8 HWC images in HBM (what ``PIL.Image.open(f).convert("RGB")`` returns, img_data.py:21).
         8-bit non-interlaced PNGs are inflated / unfiltered on the device (tise_png_decode); any other format (JPEG,
         16-bit or interlaced PNG) is outside the device decoder and, with ``host_fallback``, is decoded by PIL exactly
-        like the reference does and uploaded into the same pack."""
+        like the reference does and uploaded into the same pack.  ``host_decoder`` (bytes -> HWC uint8 array) replaces
+        that PIL call for callers whose reference decodes differently (the IS* scripts, inception_score_star.py)."""
         n = staged["n"]
         on_dev = np.nonzero(staged["supported"])[0]
         on_host = np.nonzero(~staged["supported"])[0]
@@ -298,7 +299,9 @@ class Engine:
 
             for i in on_host:
                 o, sz = int(staged["f_off"][i]), int(staged["sizes"][i])
-                host_imgs[int(i)] = np.array(Image.open(io.BytesIO(hbuf[o:o + sz].tobytes())).convert("RGB"), dtype=np.uint8)
+                blob = hbuf[o:o + sz].tobytes()
+                host_imgs[int(i)] = (np.ascontiguousarray(host_decoder(blob), dtype=np.uint8) if host_decoder else
+                                     np.array(Image.open(io.BytesIO(blob)).convert("RGB"), dtype=np.uint8))
         hw = np.zeros((n, 2), dtype=np.int32)
         for i in range(n):
             hw[i] = host_imgs[i].shape[:2] if i in host_imgs else (staged["infos"][i].height, staged["infos"][i].width)

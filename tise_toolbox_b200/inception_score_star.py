@@ -82,6 +82,30 @@ def get_inception_score(images, splits=10, variant="coco", engine=None, state_di
         n = _is.kept_images(n, "bird", batch_size)
         order = order[:n]
     parts = ISPartials(engine, engine.num_classes - off, splits)
+    if n and all(isinstance(images[i], str) for i in order) and os.environ.get("TISE_GPU_DECODE", "1") != "0":
+        # file paths (coco): bytes go file -> pinned memory -> HBM and 8-bit RGB / RGBA PNGs are decoded on the device,
+        # 4096 files per call (the split of an image depends on its global index only, so the batching is free).
+        # scipy.misc.imread keeps the file's own mode, and the scripts' grey -> RGB step is np.resize (a tiling quirk,
+        # :116-117), so every other kind of file takes exactly that host path.
+        import io
+        from concurrent.futures import ThreadPoolExecutor
+
+        def host_decode(blob):
+            return to_rgb_u8(np.array(Image.open(io.BytesIO(blob))))
+
+        group = max(1, 4096 // batch_size) * batch_size
+        with ThreadPoolExecutor(max_workers=8) as readers:
+            for start in range(0, n, group):
+                paths = [images[i] for i in order[start:start + group]]
+                staged = engine.stage_files(paths, readers)
+                for k in range(staged["n"]):
+                    if staged["supported"][k] and staged["infos"][k].color_type not in (2, 6):
+                        staged["supported"][k] = False
+                pack = engine.decode_staged(staged, host_decoder=host_decode)
+                logits = engine.logits(engine.features(pack), use_bias=use_bias)
+                _is.update_from_logits(engine, parts, logits, variant, n, start)
+        mean, std, _ = parts.finalize(nan_on_zero=nan_on_zero)
+        return mean, std
     for start in range(0, n, batch_size):
         idx = order[start:start + batch_size]
         batch = [torch.from_numpy(to_rgb_u8(imread(images[i]) if isinstance(images[i], str) else images[i]))
