@@ -186,9 +186,15 @@ __global__ void __launch_bounds__(256) dgemm_kernel(const double* __restrict__ A
   __shared__ double sa[BK][BM + 1];
   __shared__ double sb[BK][BN + 1];
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // Both products have a lower-triangular factor (L[k][j] = 0 for k < j, exact zeros from zero_upper_kernel):
+  //   TA = false: T = S2 L      -> only k >= n0 contributes to column block n0        (half of the k range on average)
+  //   TA = true:  M = L^T T     -> only k >= m0 contributes to row block m0, and M is symmetric: tiles above the
+  //                                diagonal are not computed at all (mirror_lower_kernel fills them)   (a quarter)
+  if (TA && n0 > m0) return;
+  const int k_begin = TA ? m0 : n0;
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   double acc[4][4] = {};
-  for (int k0 = 0; k0 < d; k0 += BK) {
+  for (int k0 = k_begin; k0 < d; k0 += BK) {
     for (int t = threadIdx.x; t < BM * BK; t += 256) {
       if (TA) {  // op(A)[m][k] = A[k][m]: consecutive threads walk m (contiguous)
         const int kk = t / BM, mm = t % BM;
@@ -224,14 +230,13 @@ __global__ void __launch_bounds__(256) dgemm_kernel(const double* __restrict__ A
     }
 }
 
+// M[j][i] = M[i][j] for j < i: the strictly upper triangle is a copy of the computed lower one
 __global__ void symmetrize_kernel(double* M, int d) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)d * d) return;
   const int i = (int)(idx / d), j = (int)(idx % d);
   if (j >= i) return;
-  const double v = 0.5 * (M[(size_t)i * d + j] + M[(size_t)j * d + i]);
-  M[(size_t)i * d + j] = v;
-  M[(size_t)j * d + i] = v;
+  M[(size_t)j * d + i] = M[(size_t)i * d + j];
 }
 
 // ---------------------------------------------------------------------------- Householder tridiagonalisation
@@ -361,10 +366,10 @@ __device__ __forceinline__ void make_reflector(const double* x, int n, double* o
 // the warp that updates a piece of row i then accumulates its part of p_{k+1}[i] = tau' sum_j Mnew[i][j] v_{k+1}[j]
 // from the values it has in registers.  One grid barrier and one read + write of the trailing matrix per column (the
 // two-kernel form: two launches, three passes).  The matrix is L2-resident and every step is a round trip to L2
-// (~1 us), so the work is cut into (row, 1024-column chunk) items with 16 independent loads in flight per lane, and
+// (~1 us), so the work is cut into (row, 512-column chunk) items with 16 independent loads in flight per lane, and
 // the chunk partials of p are summed by the readers (no atomics: the result does not depend on the schedule).
-constexpr int TRI_CHUNK = 1024;
-constexpr int TRI_MAX_CHUNKS = 4;  // d <= 4096
+constexpr int TRI_CHUNK = 512;
+constexpr int TRI_MAX_CHUNKS = 8;  // d <= 4096
 
 __device__ __forceinline__ void tri_pass(double* M, int d, int row0, int col0, int mn, const double* v, const double* w,
                                          const double* vn, double tau_n, bool update, double* p_out, int debug = 0) {
@@ -378,10 +383,9 @@ __device__ __forceinline__ void tri_pass(double* M, int d, int row0, int col0, i
     double* row = M + (size_t)(row0 + t) * d + col0;
     const double vi = update ? v[t] : 0.0, wi = update ? w[t] : 0.0;
     double acc = 0.0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    {
       double val[16];
-      const int u0 = ch * TRI_CHUNK + half * 512 + lane;
+      const int u0 = ch * TRI_CHUNK + lane;
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int u = u0 + e * 32;
@@ -635,8 +639,8 @@ static FrWs fr_layout(int d) {
   w.off_S2 = o; o += mat;
   w.off_T = o; o += mat;
   w.off_M = o; o += mat;
-  w.off_v = o; o += 4 * vec;  // (TRI_MAX_CHUNKS chunk partials of p, double-buffered: v and p)
-  w.off_p = o; o += 4 * vec;
+  w.off_v = o; o += 8 * vec;  // (TRI_MAX_CHUNKS chunk partials of p, double-buffered: v and p)
+  w.off_p = o; o += 8 * vec;
   w.off_diag = o; o += vec;
   w.off_off = o; o += vec;
   w.off_scal = o; o += 256;
