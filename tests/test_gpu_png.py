@@ -12,7 +12,7 @@ from oracle import restate
 from tise_toolbox_b200 import img_data, synth
 from tise_toolbox_b200.engine import ImageDecodeError
 
-from test_png_host import MODES, SIZES, png_bytes, smooth_image
+from test_png_host import MODES, SIZES, exotic_pngs, png_bytes, smooth_image
 
 pytestmark = pytest.mark.gpu
 
@@ -38,6 +38,16 @@ def test_decode_mixed_batch_bit_exact(engine):
     Image.fromarray(smooth_image(rng, 40, 50, 3)).save(jpg, "JPEG")
     blobs.append(jpg.getvalue())  # not a PNG: decoded by PIL like the reference does, uploaded into the same pack
     blobs.append(png_bytes(Image.fromarray(rng.integers(0, 65536, (20, 20)).astype(np.uint16))))  # 16-bit: host
+    exotic = [b for _, b in exotic_pngs(rng)]  # 16-bit RGB(A) / GA, 1 / 2 / 4-bit grey and palette, all filter types
+    usable = []
+    for b in exotic:
+        try:
+            _pil(b)
+            usable.append(b)
+        except IndexError:  # Pillow refuses palette indices beyond PLTE
+            pass
+    assert all(engine.png_probe(b).supported for b in usable)
+    blobs += usable
     packed = engine.decode_images(blobs)
     assert len(packed) == len(blobs)
     for i, b in enumerate(blobs):

@@ -236,3 +236,78 @@ def test_c_abi_probe_reports_what_the_device_handles():
     jpg = io.BytesIO()
     Image.fromarray(smooth_image(rng, 32, 32, 3)).save(jpg, "JPEG")
     assert lib.tise_png_probe(jpg.getvalue(), len(jpg.getvalue()), C.byref(info)) < 0 and info.supported == 0
+
+
+def _filter_rows(rows, bpp, filters):
+    """PNG scanline filtering (spec 9.2) of raw row bytes with the given filter type per row."""
+    def paeth(a, b, c):
+        p = a + b - c
+        pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
+        return a if pa <= pb and pa <= pc else (b if pb <= pc else c)
+
+    out = bytearray()
+    prev = np.zeros(len(rows[0]), np.int32)
+    for y, r in enumerate(rows):
+        cur = np.frombuffer(r, np.uint8).astype(np.int32)
+        ft = filters[y % len(filters)]
+        line = np.zeros_like(cur)
+        for x in range(cur.size):
+            a = cur[x - bpp] if x >= bpp else 0
+            b = prev[x]
+            c = prev[x - bpp] if x >= bpp else 0
+            line[x] = (cur[x] - (0, a, b, (a + b) >> 1, paeth(a, b, c))[ft]) & 255
+        out += bytes([ft]) + line.astype(np.uint8).tobytes()
+        prev = cur
+    return bytes(out)
+
+
+def build_png(width, height, depth, ctype, rows, bpp, filters=(0, 1, 2, 3, 4), plte=None):
+    import struct
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+
+    blob = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", width, height, depth, ctype, 0, 0, 0))
+    if plte is not None:
+        blob += chunk(b"PLTE", plte)
+    return blob + chunk(b"IDAT", zlib.compress(_filter_rows(rows, bpp, filters), 6)) + chunk(b"IEND", b"")
+
+
+def exotic_pngs(rng):
+    """16-bit RGB / RGBA / grey+alpha and 1 / 2 / 4-bit grey and palette files, every filter type, odd widths."""
+    out = []
+    h = 9
+    for ctype, samples in ((2, 3), (6, 4), (4, 2)):
+        w = 13
+        a = rng.integers(0, 65536, (h, w, samples)).astype(">u2")
+        out.append(("16-bit ctype %d" % ctype, build_png(w, h, 16, ctype, [a[y].tobytes() for y in range(h)], samples * 2)))
+    for depth in (1, 2, 4):
+        for w in (1, 7, 8, 37):
+            vals = rng.integers(0, 1 << depth, (h, w))
+            rows = []
+            for y in range(h):
+                bits = "".join(format(int(v), "0%db" % depth) for v in vals[y])
+                bits += "0" * ((-len(bits)) % 8)
+                rows.append(bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8)))
+            out.append(("%d-bit grey w%d" % (depth, w), build_png(w, h, depth, 0, rows, 1)))
+            pal = rng.integers(0, 256, ((1 << depth) - (1 if depth > 1 else 0)) * 3, dtype=np.uint8).tobytes()  # short palette
+            out.append(("%d-bit palette w%d" % (depth, w), build_png(w, h, depth, 3, rows, 1, plte=pal)))
+    out.append(("PIL mode 1", png_bytes(Image.fromarray((rng.integers(0, 2, (21, 45)) * 255).astype(np.uint8)).convert("1"))))
+    p = Image.fromarray(smooth_image(rng, 33, 50, 3)).convert("P", palette=Image.ADAPTIVE, colors=12)
+    out.append(("PIL P 4-bit", png_bytes(p, bits=4)))
+    return out
+
+
+def test_png_16bit_and_subbyte_formats(host):
+    rng = np.random.default_rng(21)
+    for name, blob in exotic_pngs(rng):
+        try:
+            ref = np.asarray(Image.open(io.BytesIO(blob)).convert("RGB"))
+        except IndexError:  # Pillow refuses a palette index beyond PLTE; the device decoder writes black
+            continue
+        st, got = _decode(host, blob)
+        assert st == 0, (name, st)
+        assert np.array_equal(got, ref), name
+    g16 = rng.integers(0, 65536, (4, 4)).astype(">u2")
+    blob = build_png(4, 4, 16, 0, [g16[y].tobytes() for y in range(4)], 2)
+    assert _decode(host, blob)[0] == -2  # 16-bit grey ("I;16" saturates in convert("RGB")): host decode, reported as such

@@ -387,9 +387,30 @@ TISE_HD int inflate_zlib(const uint32_t* words, uint32_t stream_bytes, uint8_t* 
 // ---------------------------------------------------------------------------------------------------------
 // What the host parser extracts from a PNG file (offsets are relative to the first byte of the file).
 constexpr int kMaxIdat = 1 << 20;
+TISE_HD int samples_of(int color_type) {
+  return color_type == 0 ? 1 : color_type == 2 ? 3 : color_type == 3 ? 1 : color_type == 4 ? 2 : color_type == 6 ? 4 : 0;
+}
+// bytes of one scanline (without its filter byte) and the filter's "bytes per pixel" unit (PNG spec 9.2)
+TISE_HD int stride_of(int width, int color_type, int bit_depth) {
+  return (int)(((int64_t)width * samples_of(color_type) * bit_depth + 7) >> 3);
+}
+TISE_HD int filter_bpp_of(int color_type, int bit_depth) {
+  const int b = samples_of(color_type) * bit_depth / 8;
+  return b < 1 ? 1 : b;
+}
+// What convert("RGB") of Pillow's decoder is reproduced for: 8-bit everything; 16-bit RGB / RGBA / grey+alpha (Pillow
+// keeps the high byte); 1/2/4-bit grey (scaled to 0..255) and palette.  16-bit grey opens as "I;16", whose conversion
+// to RGB saturates instead of scaling -- left to the host together with Adam7 interlacing.
+TISE_HD bool depth_supported(int color_type, int bit_depth) {
+  if (bit_depth == 8) return samples_of(color_type) > 0;
+  if (bit_depth == 16) return color_type == 2 || color_type == 4 || color_type == 6;
+  if (bit_depth == 1 || bit_depth == 2 || bit_depth == 4) return color_type == 0 || color_type == 3;
+  return false;
+}
+
 struct Header {
   int32_t width, height, bit_depth, color_type, interlace;
-  int32_t channels;  // bytes per pixel of a scanline (bit depth 8)
+  int32_t channels;  // filter unit: bytes per pixel of a scanline, at least 1
   int32_t n_idat;
   int32_t supported;
   int64_t idat_bytes;
@@ -423,17 +444,9 @@ inline int parse(const uint8_t* f, int64_t n, Header* h, F on_idat) {
       h->color_type = f[data + 9];
       const int compression = f[data + 10], filter = f[data + 11];
       h->interlace = f[data + 12];
-      int ch = 0;
-      switch (h->color_type) {
-        case 0: ch = 1; break;
-        case 2: ch = 3; break;
-        case 3: ch = 1; break;
-        case 4: ch = 2; break;
-        case 6: ch = 4; break;
-        default: ch = 0;
-      }
-      h->channels = ch;
-      h->supported = (ch > 0 && h->bit_depth == 8 && h->interlace == 0 && compression == 0 && filter == 0 &&
+      const bool fmt_ok = depth_supported(h->color_type, h->bit_depth);
+      h->channels = fmt_ok ? filter_bpp_of(h->color_type, h->bit_depth) : 0;
+      h->supported = (fmt_ok && h->interlace == 0 && compression == 0 && filter == 0 &&
                       h->width > 0 && h->height > 0 && (int64_t)h->width * h->height <= (int64_t)1 << 28)
                          ? 1
                          : 0;
@@ -482,10 +495,11 @@ TISE_HD uint64_t lanes_sum(uint64_t v) { return v; }
 #endif
 
 template <int LANES>
-TISE_HD int unfilter_to_rgb(const uint8_t* raw, int width, int height, int channels, int color_type,
+TISE_HD int unfilter_to_rgb(const uint8_t* raw, int width, int height, int bit_depth, int color_type,
                             const uint8_t* palette, int palette_entries, uint8_t* rows, uint8_t* out,
                             uint32_t expect_adler, int lane) {
-  const int stride = width * channels, bpp = channels;
+  const int stride = stride_of(width, color_type, bit_depth), bpp = filter_bpp_of(color_type, bit_depth);
+  const int samples = samples_of(color_type);
   uint8_t* cur = rows;
   uint8_t* prev = rows + stride;
   for (int i = lane; i < stride; i += LANES) prev[i] = 0;
@@ -558,17 +572,26 @@ TISE_HD int unfilter_to_rgb(const uint8_t* raw, int width, int height, int chann
     }
     TISE_SYNCWARP();
     uint8_t* o = out + (size_t)y * width * 3;
-    if (color_type == 2) {
+    if (color_type == 2 && bit_depth == 8) {
       for (int i = lane; i < stride; i += LANES) o[i] = cur[i];
+    } else if (bit_depth < 8) {  // 1 / 2 / 4-bit grey (scaled to 0..255) or palette indices, packed MSB first
+      const int mask = (1 << bit_depth) - 1, mul = 255 / mask;
+      for (int i = lane; i < width * 3; i += LANES) {
+        const int p = i / 3, k = i - p * 3, bit = p * bit_depth;
+        const int v = (cur[bit >> 3] >> (8 - bit_depth - (bit & 7))) & mask;
+        o[i] = color_type == 3 ? (v < palette_entries ? palette[v * 3 + k] : (uint8_t)0) : (uint8_t)(v * mul);
+      }
     } else if (color_type == 3) {
       for (int i = lane; i < width * 3; i += LANES) {
         const int p = i / 3, k = i - p * 3, idx = cur[p];
         o[i] = idx < palette_entries ? palette[idx * 3 + k] : (uint8_t)0;
       }
-    } else {  // grey (0), grey + alpha (4): replicate; RGBA (6): drop alpha -- what PIL's convert("RGB") does
+    } else {  // grey (0), grey + alpha (4): replicate; RGB(A) (2, 6): first three samples; 16-bit: the high byte --
+              // what Pillow's decoder + convert("RGB") produce
+      const int sb = bit_depth >> 3;  // bytes per sample
       for (int i = lane; i < width * 3; i += LANES) {
         const int p = i / 3, k = i - p * 3;
-        o[i] = color_type == 6 ? cur[p * 4 + k] : cur[p * channels];
+        o[i] = cur[(p * samples + (samples >= 3 ? k : 0)) * sb];
       }
     }
     uint8_t* t = cur;
