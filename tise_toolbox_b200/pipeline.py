@@ -112,6 +112,36 @@ class RealismJob:
             start_copy(next_pinned, self._slot)
         return out
 
+    def read_partials_async(self):
+        """Device -> host read of the running IS partial sums as they stand after the steps issued so far, without
+        stalling the GPU: the sums are snapshotted on the compute stream (a 4 KB device copy), the snapshot crosses PCIe
+        on a side stream into pinned memory, and the returned handle's ``wait()`` blocks the host only -- call it after
+        the NEXT step has been issued and the GPU never idles between steps."""
+        assert self.parts is not None
+        dev = self.e.device
+        if not hasattr(self, "_rb_stream"):
+            self._rb_stream = torch.cuda.Stream(device=dev)
+            self._rb_slots = [(torch.empty_like(self.parts.f), torch.empty(self.parts.f.numel(), dtype=torch.float64).pin_memory())
+                              for _ in range(2)]
+            self._rb_next = 0
+        snap, host = self._rb_slots[self._rb_next]
+        self._rb_next = 1 - self._rb_next
+        snap.copy_(self.parts.f)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        self._rb_stream.wait_event(ready)
+        with torch.cuda.stream(self._rb_stream):
+            host.copy_(snap, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._rb_stream)
+
+        class _Handle:
+            def wait(_self):
+                done.synchronize()
+                return host
+
+        return _Handle()
+
     def finish(self, group=None) -> Dict[str, object]:
         """All-reduce (if ``group`` / torch.distributed is initialised) and finalise on every rank."""
         import torch.distributed as dist
