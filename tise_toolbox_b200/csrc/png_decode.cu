@@ -5,8 +5,10 @@
 // Host: walk the chunk list of every file (IHDR, PLTE, IDAT segments) -- a few dozen bytes touched per file.
 // Device, three kernels per batch:
 //   png_gather_kernel    IDAT payloads -> one contiguous, word-aligned zlib stream per image        (HBM copy)
-//   png_inflate_kernel   one warp per image: warp-uniform Huffman decode in registers, lane 0 stores
-//                        literals, 32 lanes copy LZ77 matches and build the lookup tables          (latency bound)
+//   png_inflate_kernel   one warp per image: warp-uniform bit reader + Huffman decoder in registers; literal runs
+//                        are decoded 32 candidate bit positions at a time (one table look-up per lane, the chain of
+//                        code boundaries followed through a 64-byte shared-memory window, literals stored side by
+//                        side); 32 lanes copy LZ77 matches and build the lookup tables  (latency / issue bound)
 //   png_unfilter_kernel  one warp per image: scanline rows staged in shared memory, Sub/Avg/Paeth run as one
 //                        sequential chain per byte lane, Up/None and the RGB conversion across the warp;
 //                        the Adler-32 of the inflated bytes is checked on the way                  (shared memory)
