@@ -60,6 +60,29 @@ def install(net, mode):
         hi = w.half().float(); lo = (w - hi).half().float(); first.weight.data = hi + lo
         first.register_forward_pre_hook(lambda m, inp: (inp[0].half().float(),))
         mode = "f16a"
+    if mode in ("f16a_lo8", "f16a_lo8e4"):
+        # candidate for the next round: W_hi pass in fp16 as now, W_lo pass as kind::f8f6f4 -- activations as e5m2 (the
+        # top byte of the fp16 value) or e4m3, W_lo (|lo| <= 1 after the per-channel power-of-two scaling) as e4m3
+        act8 = torch.float8_e5m2 if mode == "f16a_lo8" else torch.float8_e4m3fn
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.Conv2d) and mod is not first:
+                w = mod.weight.data
+                amax = w.abs().flatten(1).max(1).values.clamp_min(1e-30)
+                e = torch.floor(torch.log2(4095.0 / amax))
+                sc = torch.pow(2.0, e).view(-1, 1, 1, 1)
+                ws = w * sc
+                hi = ws.half().float()
+                lo8 = (ws - hi).to(torch.float8_e4m3fn).float()
+                mod.w_hi = hi / sc
+                mod.w_lo = lo8 / sc
+
+                def fwd(x, m=mod):
+                    a16 = x.half().float()
+                    a8 = a16.to(act8).float()
+                    return (torch.nn.functional.conv2d(a16, m.w_hi, None, m.stride, m.padding) +
+                            torch.nn.functional.conv2d(a8, m.w_lo, None, m.stride, m.padding))
+                mod.forward = fwd
+        return
     for mod in net.modules():
         if isinstance(mod, torch.nn.Conv2d) and mod is not first:
             w = mod.weight.data
