@@ -405,7 +405,9 @@ def ingest_throughput(eng, pool, pk, n=4096, unique=128):
 
     from tise_toolbox_b200.img_data import DeviceImageLoader
 
-    tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    shm_ok = os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 2 * n * 200000
+    tmp = tempfile.mkdtemp(dir="/dev/shm" if shm_ok else None)
+    seen, files_s = 0, float("nan")
     try:
         names = []
         for i, b in enumerate(batch):
@@ -418,6 +420,8 @@ def ingest_throughput(eng, pool, pk, n=4096, unique=128):
             seen += len(pack)
         torch.cuda.synchronize()
         files_s = time.perf_counter() - t0
+    except OSError as e:  # (no space for the 620 MB of files: the rest of the line is still valid)
+        print("ingest: from-files measurement skipped: %s" % e, file=sys.stderr)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     t0 = time.perf_counter()
@@ -428,7 +432,7 @@ def ingest_throughput(eng, pool, pk, n=4096, unique=128):
     algo_bytes = n * (2 * file_bytes + 2 * (IMG_BYTES + 256) + 2 * IMG_BYTES)  # gather r+w, inflate w + unfilter r, unfilter w (+ in)
     return {"files": n, "unique": unique, "image": "256x256x3 PNG, Pillow default compression", "file_bytes_mean": file_bytes,
             "device_images_per_s": n / (dev_ms / 1e3), "device_ms": dev_ms, "e2e_images_per_s": n / e2e_s,
-            "from_files_images_per_s": seen / files_s,
+            "from_files_images_per_s": (seen / files_s) if seen else None,
             "pil_images_per_s_one_core": pil, "host_cores": os.cpu_count(), "bit_exact": ok,
             "hbm_frac": algo_bytes / (dev_ms / 1e3) / 1e9 / pk["hbm_gbs"], "kernels_per_call": 3}
 
