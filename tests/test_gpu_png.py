@@ -110,3 +110,31 @@ def test_device_image_loader_order_and_drop_last(tmp_path, engine):
             seen += 1
     assert seen == 20
     assert sum(len(b) for b in img_data.DeviceImageLoader(names, engine, 5, drop_last=False)) == 23
+
+
+def test_shard_loader_matches_the_png_folder(tmp_path, engine, state_dict):
+    """Raw uint8 shard ingest (shards.py): same images, same order, same statistics as the PNG folder path."""
+    from tise_toolbox_b200 import fid_score, shards
+    from tise_toolbox_b200.inception import InceptionV3
+
+    imgs = [im.numpy() for im in synth.images(3, 0, 40, 21)] + [synth.images(5, 1, 7, 1, 90, 140)[0].numpy()]
+    folder = tmp_path / "pngs"
+    folder.mkdir()
+    for i, a in enumerate(imgs):
+        Image.fromarray(a).save(str(folder / ("img_%05d.png" % i)))
+    shard = str(tmp_path / "set.shard")
+    _, n = shards.pack_folder(str(folder), shard)
+    assert n == 22
+    names = img_data.Dataset(str(folder)).file_names
+    loader = shards.ShardLoader(shard, engine, batch_size=5, drop_last=True, group=10)
+    assert len(loader) == 4
+    k = 0
+    for batch in loader:
+        for j in range(len(batch)):
+            assert np.array_equal(batch[j].cpu().numpy(), np.asarray(Image.open(names[k]).convert("RGB"))), k
+            k += 1
+    assert k == 20
+    model = InceptionV3([3], state_dict=state_dict, micro_batch=32)
+    m1, s1 = fid_score._compute_statistics_of_path(str(folder), model, 5, 2048, "0")
+    m2, s2 = fid_score._compute_statistics_of_path(shard, model, 5, 2048, "0")
+    assert np.abs(m1 - m2).max() <= 1e-12 * np.abs(m1).max() and np.abs(s1 - s2).max() <= 1e-10 * np.abs(s1).max()

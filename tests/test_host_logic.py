@@ -143,3 +143,31 @@ def test_shard_batches_partition_is_exactly_the_drop_last_set():
         for (lo, hi), (lo2, _) in zip(ranges, ranges[1:]):
             assert hi == lo2
         assert all((hi - lo) % b == 0 and hi >= lo for lo, hi in ranges)
+
+
+def test_shard_format_round_trip_and_validation(tmp_path):
+    from tise_toolbox_b200 import shards, synth
+
+    imgs = [synth.images(3, 0, i, 1, h, w)[0].numpy() for i, (h, w) in enumerate([(256, 256), (1, 1), (17, 333), (64, 48)])]
+    p = str(tmp_path / "a.shard")
+    nbytes = shards.write_shard(p, imgs)
+    assert nbytes == os.path.getsize(p)
+    offs, hw, size = shards.read_index(p)
+    assert hw.tolist() == [[256, 256], [1, 1], [17, 333], [64, 48]] and not (offs % 16).any() and size == nbytes
+    back = shards.read_images(p)
+    assert all(np.array_equal(a, b) for a, b in zip(imgs, back))
+    assert np.array_equal(shards.read_images(p, [2])[0], imgs[2])
+    shards.write_shard(str(tmp_path / "empty.shard"), [])
+    assert len(shards.read_index(str(tmp_path / "empty.shard"))[0]) == 0
+    with pytest.raises(ValueError):
+        shards.write_shard(str(tmp_path / "bad.shard"), [np.zeros((4, 4), np.uint8)])
+    with open(p, "rb") as f:
+        blob = bytearray(f.read())
+    with open(str(tmp_path / "trunc.shard"), "wb") as f:
+        f.write(blob[:len(blob) // 2])
+    with pytest.raises(ValueError):
+        shards.read_index(str(tmp_path / "trunc.shard"))
+    with open(str(tmp_path / "magic.shard"), "wb") as f:
+        f.write(b"NOTASHARD" + blob[9:])
+    with pytest.raises(ValueError):
+        shards.read_index(str(tmp_path / "magic.shard"))

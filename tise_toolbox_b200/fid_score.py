@@ -118,6 +118,13 @@ def _compute_statistics_of_path(path, model, batch_size, dims, cuda):
         f = np.load(path, allow_pickle=True)  # fid_score.py:200-203
         m, s = f["mu"][:], f["sigma"][:]
         f.close()
+    elif path.endswith(".shard") and os.path.isfile(path):
+        # raw uint8 shard (tise_toolbox_b200/shards.py): file -> pinned memory -> HBM, no codec anywhere
+        from .shards import ShardLoader
+
+        mom = _accumulate_moments(ShardLoader(path, model.engine, batch_size, drop_last=True), model, batch_size, dims)
+        print(" done")
+        m, s = mom.finalize()
     else:
         # fid_score.py:206-217 with decode, Resize and ToTensor moved onto the GPU: host threads only read bytes.
         # TISE_GPU_DECODE=0 keeps PIL decode on DataLoader workers (resize / ToTensor still on the GPU).
