@@ -109,6 +109,27 @@ int tise_png_decode(tise_ctx* ctx, const uint8_t* h_files, const uint8_t* d_file
                     const int64_t* h_file_bytes, int n, uint8_t* d_out, const int64_t* h_out_off,
                     int32_t* d_status, void* d_ws, size_t ws_bytes, tise_stream stream);
 
+/* Baseline JPEG files, same contract as the PNG entry points above: bit-identical to Pillow's
+ * Image.open(f).convert("RGB"), i.e. to libjpeg-turbo with its defaults (jpeg_idct_islow, fancy h2v1 / h2v2
+ * upsampling, 16-bit fixed-point YCbCr -> RGB).  Handled: 8-bit SOF0 / SOF1 Huffman files with one interleaved scan,
+ * grey or YCbCr, chroma 4:4:4 / 4:2:2 / 4:2:0, restart intervals.  Progressive, arithmetic-coded, CMYK and
+ * RGB-tagged files are reported with supported = 0 and stay with the caller.  d_status[i]: 0 ok, 21..24 a corrupt
+ * entropy-coded segment (csrc/jpeg_core.h), -1 not reached. */
+typedef struct {
+  int32_t width, height;
+  int32_t components;       /* 1 (grey) or 3 (YCbCr) */
+  int32_t chroma_mode;      /* 0 grey, 1 4:4:4, 2 4:2:2 (h2v1), 3 4:2:0 (h2v2) */
+  int32_t restart_interval; /* MCUs between RSTn markers, 0 = none */
+  int32_t supported;        /* 1: tise_jpeg_decode handles this file */
+  int64_t scan_bytes;       /* bytes from the first entropy-coded byte to the end of the file */
+  int64_t blocks;           /* 8 x 8 blocks of all components (whole MCUs) */
+} tise_jpeg_info;
+int tise_jpeg_probe(const uint8_t* h_file, int64_t file_bytes, tise_jpeg_info* info);
+size_t tise_jpeg_decode_workspace_bytes(const tise_jpeg_info* infos, int n);
+int tise_jpeg_decode(tise_ctx* ctx, const uint8_t* h_files, const uint8_t* d_files, const int64_t* h_file_off,
+                     const int64_t* h_file_bytes, int n, uint8_t* d_out, const int64_t* h_out_off,
+                     int32_t* d_status, void* d_ws, size_t ws_bytes, tise_stream stream);
+
 /* ---- A2: Pillow-exact bilinear resize to 299x299 ---------------------------------------- */
 /* transforms.Resize((299,299)) at fid_score.py:210 / object_centric_inception_score.py:89 and
  * scipy.misc.imresize at inception_score_star_coco.py:118, inception_score_star_bird.py:67:

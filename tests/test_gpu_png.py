@@ -35,8 +35,8 @@ def test_decode_mixed_batch_bit_exact(engine):
                 im = Image.fromarray(a, mode)
             blobs.append(png_bytes(im, compress_level=int(rng.integers(0, 10))))
     jpg = io.BytesIO()
-    Image.fromarray(smooth_image(rng, 40, 50, 3)).save(jpg, "JPEG")
-    blobs.append(jpg.getvalue())  # not a PNG: decoded by PIL like the reference does, uploaded into the same pack
+    Image.fromarray(smooth_image(rng, 40, 50, 3)).save(jpg, "JPEG", progressive=True)
+    blobs.append(jpg.getvalue())  # progressive JPEG: decoded by PIL like the reference does, uploaded into the same pack
     blobs.append(png_bytes(Image.fromarray(rng.integers(0, 65536, (20, 20)).astype(np.uint16))))  # 16-bit: host
     exotic = [b for _, b in exotic_pngs(rng)]  # 16-bit RGB(A) / GA, 1 / 2 / 4-bit grey and palette, all filter types
     usable = []
@@ -138,3 +138,27 @@ def test_shard_loader_matches_the_png_folder(tmp_path, engine, state_dict):
     m1, s1 = fid_score._compute_statistics_of_path(str(folder), model, 5, 2048, "0")
     m2, s2 = fid_score._compute_statistics_of_path(shard, model, 5, 2048, "0")
     assert np.abs(m1 - m2).max() <= 1e-12 * np.abs(m1).max() and np.abs(s1 - s2).max() <= 1e-10 * np.abs(s1).max()
+
+
+def test_jpeg_decode_bit_exact(engine):
+    """Baseline JPEGs on the device (tise_jpeg_decode) == Pillow / libjpeg-turbo, mixed with PNGs in one call."""
+    from test_jpeg_host import jpeg_cases
+
+    rng = np.random.default_rng(0)
+    cases = jpeg_cases(rng, sizes=[(256, 256), (64, 48), (17, 33), (1, 1), (2, 3), (500, 375), (15, 17)])
+    blobs = [b for _, b in cases] + [png_bytes(smooth_image(rng, 33, 44, 3))]
+    packed = engine.decode_images(blobs, host_fallback=False)
+    for i, b in enumerate(blobs):
+        assert np.array_equal(packed[i].cpu().numpy(), _pil(b)), cases[i][0] if i < len(cases) else "png"
+    # a damaged entropy-coded segment is reported, not decoded into garbage silently when the stream breaks a code
+    good = cases[0][1]
+    bad = bytearray(good)
+    sos = good.find(b"\xff\xda")
+    for k in range(sos + 20, sos + 60):
+        bad[k] = 0xFF if k % 2 else 0x00 ^ bad[k]
+    try:
+        out = engine.decode_images([bytes(bad)], host_fallback=False)
+        assert tuple(out[0].shape) == (256, 256, 3)
+    except ImageDecodeError:
+        pass
+    assert np.array_equal(engine.decode_images([good])[0].cpu().numpy(), _pil(good))

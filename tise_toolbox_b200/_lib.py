@@ -23,6 +23,12 @@ class PngInfo(C.Structure):
                 ("idat_bytes", C.c_int64)]
 
 
+class JpegInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("components", C.c_int32), ("chroma_mode", C.c_int32),
+                ("restart_interval", C.c_int32), ("supported", C.c_int32), ("scan_bytes", C.c_int64),
+                ("blocks", C.c_int64)]
+
+
 class TiseError(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__("libtise_b200: %s (status %d)" % (message, status))
@@ -48,6 +54,10 @@ _SIGNATURES = {
     "tise_png_decode_workspace_bytes": (C.c_size_t, [C.POINTER(PngInfo), C.c_int]),
     "tise_png_decode": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
+    "tise_jpeg_probe": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(JpegInfo)]),
+    "tise_jpeg_decode_workspace_bytes": (C.c_size_t, [C.POINTER(JpegInfo), C.c_int]),
+    "tise_jpeg_decode": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
     "tise_set_input_lut": (C.c_int, [c_ctx_p, C.c_void_p]),
     "tise_inception_workspace_bytes": (C.c_size_t, [c_ctx_p, C.c_int]),
     "tise_inception_features": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -102,6 +102,7 @@ class Engine:
         self._u8: Optional[torch.Tensor] = None
         self._fr_ws: Optional[torch.Tensor] = None
         self._png_ws: Optional[torch.Tensor] = None
+        self._jpg_ws: Optional[torch.Tensor] = None
         self.num_classes = 0
         self.variant = None
         self.set_conv_mode(conv_impl, passes)
@@ -191,15 +192,26 @@ class Engine:
         return self._pin[k]
 
     def _probe_staged(self, pinned: torch.Tensor, f_off: np.ndarray, sizes: np.ndarray) -> dict:
+        """Chunk / marker walk of every staged file on the host: kind 1 = PNG, 2 = JPEG the device decoders handle,
+        0 = anything else (decoded by the caller's host decoder)."""
         m = int(sizes.shape[0])
         infos = (_lib.PngInfo * max(m, 1))()
+        jinfos = (_lib.JpegInfo * max(m, 1))()
         base = pinned.data_ptr()
-        supported = np.zeros(m, dtype=bool)
+        kind = np.zeros(m, dtype=np.int8)
+        hw = np.zeros((m, 2), dtype=np.int32)
+        use_jpeg = os.environ.get("TISE_GPU_JPEG", "1") != "0"
         for i in range(m):
-            rc = self.lib.tise_png_probe(base + int(f_off[i]), int(sizes[i]), C.byref(infos[i]))
-            supported[i] = rc == 0 and bool(infos[i].supported)
-        return {"pinned": pinned, "f_off": f_off, "sizes": sizes, "infos": infos, "supported": supported, "n": m,
-                "total": int(f_off[-1] + sizes[-1]) + 16 if m else 16}
+            ptr, nb = base + int(f_off[i]), int(sizes[i])
+            if self.lib.tise_png_probe(ptr, nb, C.byref(infos[i])) == 0:
+                if infos[i].supported:
+                    kind[i] = 1
+                    hw[i] = (infos[i].height, infos[i].width)
+            elif use_jpeg and self.lib.tise_jpeg_probe(ptr, nb, C.byref(jinfos[i])) == 0 and jinfos[i].supported:
+                kind[i] = 2
+                hw[i] = (jinfos[i].height, jinfos[i].width)
+        return {"pinned": pinned, "f_off": f_off, "sizes": sizes, "infos": infos, "jinfos": jinfos, "kind": kind, "hw": hw,
+                "supported": kind != 0, "n": m, "total": int(f_off[-1] + sizes[-1]) + 16 if m else 16}
 
     @staticmethod
     def _layout(sizes: np.ndarray):
@@ -262,34 +274,40 @@ class Engine:
         return self._probe_staged(pinned, f_off, sizes)
 
     def decode_staged_png(self, staged: dict, d_files: torch.Tensor, index: np.ndarray, out: torch.Tensor,
-                          out_off: np.ndarray) -> torch.Tensor:
-        """tise_png_decode on the staged files ``index`` (already uploaded as ``d_files``) -> images at
-        ``out[out_off[k]:]``; returns the device status vector (asynchronous: nothing is read back here)."""
+                          out_off: np.ndarray, jpeg: bool = False) -> torch.Tensor:
+        """tise_png_decode (or tise_jpeg_decode with ``jpeg``) on the staged files ``index`` (already uploaded as
+        ``d_files``) -> images at ``out[out_off[k]:]``; returns the device status vector (asynchronous: nothing is read
+        back here)."""
         m = int(index.shape[0])
-        infos = (_lib.PngInfo * m)(*[staged["infos"][int(i)] for i in index])
+        if jpeg:
+            infos = (_lib.JpegInfo * m)(*[staged["jinfos"][int(i)] for i in index])
+            ws_bytes, decode, ws_name = self.lib.tise_jpeg_decode_workspace_bytes, self.lib.tise_jpeg_decode, "_jpg_ws"
+        else:
+            infos = (_lib.PngInfo * m)(*[staged["infos"][int(i)] for i in index])
+            ws_bytes, decode, ws_name = self.lib.tise_png_decode_workspace_bytes, self.lib.tise_png_decode, "_png_ws"
         f_off = np.ascontiguousarray(staged["f_off"][index])
         sizes = np.ascontiguousarray(staged["sizes"][index])
         out_off = np.ascontiguousarray(out_off, dtype=np.int64)
-        ws = self._buf("_png_ws", int(self.lib.tise_png_decode_workspace_bytes(infos, m)))
+        ws = self._buf(ws_name, int(ws_bytes(infos, m)))
         status = torch.empty(m, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
-            self._check(self.lib.tise_png_decode(self.ctx, staged["pinned"].data_ptr(), d_files.data_ptr(),
-                                                 f_off.ctypes.data, sizes.ctypes.data, m, out.data_ptr(),
-                                                 out_off.ctypes.data, status.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                 _stream()))
+            self._check(decode(self.ctx, staged["pinned"].data_ptr(), d_files.data_ptr(), f_off.ctypes.data,
+                               sizes.ctypes.data, m, out.data_ptr(), out_off.ctypes.data, status.data_ptr(), ws.data_ptr(),
+                               ws.numel(), _stream()))
         return status
 
     def decode_staged(self, staged: dict, host_fallback: bool = True, host_decoder=None) -> PackedImages:
         """Staged files -> RGB8 HWC images in HBM (what ``PIL.Image.open(f).convert("RGB")`` returns, img_data.py:21).
-        8-bit non-interlaced PNGs are inflated / unfiltered on the device (tise_png_decode); any other format (JPEG,
-        16-bit or interlaced PNG) is outside the device decoder and, with ``host_fallback``, is decoded by PIL exactly
-        like the reference does and uploaded into the same pack.  ``host_decoder`` (bytes -> HWC uint8 array) replaces
+        Non-interlaced PNGs are inflated / unfiltered on the device (tise_png_decode), baseline JPEGs entropy-decoded,
+        inverse-transformed and colour-converted there (tise_jpeg_decode); any other file (progressive JPEG, interlaced
+        PNG, other formats) is outside the device decoders and, with ``host_fallback``, is decoded by PIL exactly like
+        the reference does and uploaded into the same pack.  ``host_decoder`` (bytes -> HWC uint8 array) replaces
         that PIL call for callers whose reference decodes differently (the IS* scripts, inception_score_star.py)."""
         n = staged["n"]
-        on_dev = np.nonzero(staged["supported"])[0]
-        on_host = np.nonzero(~staged["supported"])[0]
+        kind = np.where(staged["supported"], staged["kind"], 0)  # (callers may veto files by clearing "supported")
+        on_png, on_jpg, on_host = np.nonzero(kind == 1)[0], np.nonzero(kind == 2)[0], np.nonzero(kind == 0)[0]
         if len(on_host) and not host_fallback:
-            raise ValueError("decode: file %d is not an 8-bit non-interlaced PNG" % int(on_host[0]))
+            raise ValueError("decode: file %d is neither a PNG nor a baseline JPEG the device decoders handle" % int(on_host[0]))
         hbuf = staged["pinned"].numpy()
         host_imgs = {}
         if len(on_host):
@@ -302,22 +320,24 @@ class Engine:
                 blob = hbuf[o:o + sz].tobytes()
                 host_imgs[int(i)] = (np.ascontiguousarray(host_decoder(blob), dtype=np.uint8) if host_decoder else
                                      np.array(Image.open(io.BytesIO(blob)).convert("RGB"), dtype=np.uint8))
-        hw = np.zeros((n, 2), dtype=np.int32)
-        for i in range(n):
-            hw[i] = host_imgs[i].shape[:2] if i in host_imgs else (staged["infos"][i].height, staged["infos"][i].width)
+        hw = staged["hw"].copy()
+        for i, a in host_imgs.items():
+            hw[i] = a.shape[:2]
         nbytes = hw[:, 0].astype(np.int64) * hw[:, 1] * 3
         out_off = np.zeros(n, dtype=np.int64)
         if n:
             out_off[1:] = np.cumsum((nbytes + 15) // 16 * 16)[:-1]
         total = int(out_off[-1] + nbytes[-1]) if n else 0
         out = torch.empty(max(total, 16), dtype=torch.uint8, device=self.device)
-        if len(on_dev):
+        if len(on_png) or len(on_jpg):
             d_files = staged["pinned"][:staged["total"]].to(self.device, non_blocking=True)
-            status = self.decode_staged_png(staged, d_files, on_dev, out, out_off[on_dev])
-            st = status.cpu().numpy()  # synchronises: the pinned staging buffer may be reused afterwards
-            if st.any():
-                k = int(np.nonzero(st)[0][0])
-                raise ImageDecodeError("corrupt PNG stream in file %d (decoder status %d)" % (int(on_dev[k]), int(st[k])))
+            runs = [(idx, self.decode_staged_png(staged, d_files, idx, out, out_off[idx], jpeg=j), "JPEG" if j else "PNG")
+                    for idx, j in ((on_png, False), (on_jpg, True)) if len(idx)]
+            for idx, status, what in runs:
+                st = status.cpu().numpy()  # synchronises: the pinned staging buffer may be reused afterwards
+                if st.any():
+                    k = int(np.nonzero(st)[0][0])
+                    raise ImageDecodeError("corrupt %s stream in file %d (decoder status %d)" % (what, int(idx[k]), int(st[k])))
         for i, a in host_imgs.items():
             o = int(out_off[i])
             out[o:o + a.size].copy_(torch.from_numpy(a.reshape(-1)))

@@ -83,7 +83,7 @@ def get_inception_score(images, splits=10, variant="coco", engine=None, state_di
         order = order[:n]
     parts = ISPartials(engine, engine.num_classes - off, splits)
     if n and all(isinstance(images[i], str) for i in order) and os.environ.get("TISE_GPU_DECODE", "1") != "0":
-        # file paths (coco): bytes go file -> pinned memory -> HBM and 8-bit RGB / RGBA PNGs are decoded on the device,
+        # file paths (coco): bytes go file -> pinned memory -> HBM; RGB / RGBA PNGs and YCbCr JPEGs are decoded on the device,
         # 4096 files per call (the split of an image depends on its global index only, so the batching is free).
         # scipy.misc.imread keeps the file's own mode, and the scripts' grey -> RGB step is np.resize (a tiling quirk,
         # :116-117), so every other kind of file takes exactly that host path.
@@ -98,8 +98,10 @@ def get_inception_score(images, splits=10, variant="coco", engine=None, state_di
             for start in range(0, n, group):
                 paths = [images[i] for i in order[start:start + group]]
                 staged = engine.stage_files(paths, readers)
-                for k in range(staged["n"]):
-                    if staged["supported"][k] and staged["infos"][k].color_type not in (2, 6):
+                for k in range(staged["n"]):  # only files whose own mode is RGB / RGBA may skip the scripts' host path
+                    if staged["kind"][k] == 1 and staged["infos"][k].color_type not in (2, 6):
+                        staged["supported"][k] = False
+                    if staged["kind"][k] == 2 and staged["jinfos"][k].components != 3:
                         staged["supported"][k] = False
                 pack = engine.decode_staged(staged, host_decoder=host_decode)
                 logits = engine.logits(engine.features(pack), use_bias=use_bias)
