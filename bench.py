@@ -428,13 +428,41 @@ def ingest_throughput(eng, pool, pk, n=4096, unique=128):
     for b in blobs[:64]:
         np.asarray(Image.open(io.BytesIO(b)).convert("RGB"))
     pil = 64 / (time.perf_counter() - t0)
+    # the same measurement for baseline JPEG files (quality 90, 4:2:0 -- Pillow's defaults; MS-COCO-like real sets)
+    jblobs = []
+    for im in imgs:
+        b = io.BytesIO()
+        Image.fromarray(im).save(b, "JPEG", quality=90)
+        jblobs.append(b.getvalue())
+    jbatch = [jblobs[i % unique] for i in range(n)]
+    jpacked = eng.decode_images(jbatch, host_fallback=False)
+    jref = np.asarray(Image.open(io.BytesIO(jblobs[(n - 1) % unique])).convert("RGB"))
+    jok = bool(np.array_equal(jpacked[n - 1].cpu().numpy(), jref))
+    jstaged = eng.stage_blobs(jbatch)
+    jd_files = jstaged["pinned"][:jstaged["total"]].to(eng.device)
+    jout = torch.empty_like(jpacked.buf)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        jstatus = eng.decode_staged_png(jstaged, jd_files, index, jout, jpacked.offsets, jpeg=True)
+    e1.record()
+    torch.cuda.synchronize()
+    jdev_ms = e0.elapsed_time(e1) / reps
+    jok = jok and not bool(jstatus.any().item())
+    t0 = time.perf_counter()
+    for b in jblobs[:64]:
+        np.asarray(Image.open(io.BytesIO(b)).convert("RGB"))
+    jpil = 64 / (time.perf_counter() - t0)
+    jpeg = {"files": n, "image": "256x256x3 baseline JPEG, quality 90, 4:2:0", "file_bytes_mean": float(np.mean([len(b) for b in jblobs])),
+            "device_images_per_s": n / (jdev_ms / 1e3), "device_ms": jdev_ms, "pil_images_per_s_one_core": jpil,
+            "bit_exact_vs_pillow": jok, "kernels_per_call": 3}
     file_bytes = float(np.mean([len(b) for b in blobs]))
     algo_bytes = n * (2 * file_bytes + 2 * (IMG_BYTES + 256) + 2 * IMG_BYTES)  # gather r+w, inflate w + unfilter r, unfilter w (+ in)
     return {"files": n, "unique": unique, "image": "256x256x3 PNG, Pillow default compression", "file_bytes_mean": file_bytes,
             "device_images_per_s": n / (dev_ms / 1e3), "device_ms": dev_ms, "e2e_images_per_s": n / e2e_s,
             "from_files_images_per_s": (seen / files_s) if seen else None,
             "pil_images_per_s_one_core": pil, "host_cores": os.cpu_count(), "bit_exact": ok,
-            "hbm_frac": algo_bytes / (dev_ms / 1e3) / 1e9 / pk["hbm_gbs"], "kernels_per_call": 3}
+            "hbm_frac": algo_bytes / (dev_ms / 1e3) / 1e9 / pk["hbm_gbs"], "kernels_per_call": 3, "jpeg": jpeg}
 
 
 def frechet_latency(eng, res, with_cpu):
