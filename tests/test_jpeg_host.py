@@ -125,3 +125,18 @@ def test_c_abi_jpeg_probe():
     blob = jpeg_bytes(a, progressive=True)
     assert lib.tise_jpeg_probe(blob, len(blob), C.byref(info)) == 0 and info.supported == 0
     assert lib.tise_jpeg_probe(b"not a jpeg at all", 17, C.byref(info)) < 0
+
+
+def test_decoders_survive_fuzzing_under_sanitizers():
+    """tools/fuzz_decoders.py: 1200 damaged PNG / JPEG files through the host builds under ASan + UBSan."""
+    import shutil
+    import sys
+
+    if not shutil.which("g++"):
+        pytest.skip("g++ not found")
+    asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan):
+        pytest.skip("libasan not available")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "..", "tools", "fuzz_decoders.py"), "10"], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "no sanitizer reports" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])

@@ -382,20 +382,20 @@ TISE_JHD void idct_islow(const int16_t* in, const uint16_t* q, uint8_t* out, int
   constexpr int CB = 13, P1 = 2;
   constexpr int F0298 = 2446, F0390 = 3196, F0541 = 4433, F0765 = 6270, F0899 = 7373, F1175 = 9633, F1501 = 12299,
                 F1847 = 15137, F1961 = 16069, F2053 = 16819, F2562 = 20995, F3072 = 25172;
-  int ws[64];
+  typedef int64_t L;  // JLONG of jidctint.c: 64-bit, so damaged streams cannot overflow (results identical for valid data)
+  L ws[64];
   for (int c = 0; c < 8; ++c) {
-    const int d0 = in[c] * (int)q[c], d1 = in[8 + c] * (int)q[8 + c], d2 = in[16 + c] * (int)q[16 + c],
-              d3 = in[24 + c] * (int)q[24 + c], d4 = in[32 + c] * (int)q[32 + c], d5 = in[40 + c] * (int)q[40 + c],
-              d6 = in[48 + c] * (int)q[48 + c], d7 = in[56 + c] * (int)q[56 + c];
-    int z2 = d2, z3 = d6;
-    int z1 = (z2 + z3) * F0541;
-    int tmp2 = z1 + z3 * (-F1847);
-    int tmp3 = z1 + z2 * F0765;
+    const L d0 = (L)in[c] * q[c], d1 = (L)in[8 + c] * q[8 + c], d2 = (L)in[16 + c] * q[16 + c], d3 = (L)in[24 + c] * q[24 + c],
+            d4 = (L)in[32 + c] * q[32 + c], d5 = (L)in[40 + c] * q[40 + c], d6 = (L)in[48 + c] * q[48 + c], d7 = (L)in[56 + c] * q[56 + c];
+    L z2 = d2, z3 = d6;
+    L z1 = (z2 + z3) * F0541;
+    L tmp2 = z1 + z3 * (-F1847);
+    L tmp3 = z1 + z2 * F0765;
     z2 = d0;
     z3 = d4;
-    int tmp0 = (int)((unsigned)(z2 + z3) << CB);
-    int tmp1 = (int)((unsigned)(z2 - z3) << CB);
-    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    L tmp0 = (z2 + z3) * (1 << CB);
+    L tmp1 = (z2 - z3) * (1 << CB);
+    const L tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
     tmp0 = d7;
     tmp1 = d5;
     tmp2 = d3;
@@ -403,8 +403,8 @@ TISE_JHD void idct_islow(const int16_t* in, const uint16_t* q, uint8_t* out, int
     z1 = tmp0 + tmp3;
     z2 = tmp1 + tmp2;
     z3 = tmp0 + tmp2;
-    int z4 = tmp1 + tmp3;
-    const int z5 = (z3 + z4) * F1175;
+    L z4 = tmp1 + tmp3;
+    const L z5 = (z3 + z4) * F1175;
     tmp0 *= F0298;
     tmp1 *= F2053;
     tmp2 *= F3072;
@@ -430,14 +430,14 @@ TISE_JHD void idct_islow(const int16_t* in, const uint16_t* q, uint8_t* out, int
     ws[32 + c] = (tmp13 - tmp0 + R) >> S;
   }
   for (int rr = 0; rr < 8; ++rr) {
-    const int* w = ws + rr * 8;
-    int z2 = w[2], z3 = w[6];
-    int z1 = (z2 + z3) * F0541;
-    int tmp2 = z1 + z3 * (-F1847);
-    int tmp3 = z1 + z2 * F0765;
-    int tmp0 = (int)((unsigned)(w[0] + w[4]) << CB);
-    int tmp1 = (int)((unsigned)(w[0] - w[4]) << CB);
-    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    const L* w = ws + rr * 8;
+    L z2 = w[2], z3 = w[6];
+    L z1 = (z2 + z3) * F0541;
+    L tmp2 = z1 + z3 * (-F1847);
+    L tmp3 = z1 + z2 * F0765;
+    L tmp0 = (w[0] + w[4]) * (1 << CB);
+    L tmp1 = (w[0] - w[4]) * (1 << CB);
+    const L tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
     tmp0 = w[7];
     tmp1 = w[5];
     tmp2 = w[3];
@@ -445,8 +445,8 @@ TISE_JHD void idct_islow(const int16_t* in, const uint16_t* q, uint8_t* out, int
     z1 = tmp0 + tmp3;
     z2 = tmp1 + tmp2;
     z3 = tmp0 + tmp2;
-    int z4 = tmp1 + tmp3;
-    const int z5 = (z3 + z4) * F1175;
+    L z4 = tmp1 + tmp3;
+    const L z5 = (z3 + z4) * F1175;
     tmp0 *= F0298;
     tmp1 *= F2053;
     tmp2 *= F3072;
@@ -463,14 +463,14 @@ TISE_JHD void idct_islow(const int16_t* in, const uint16_t* q, uint8_t* out, int
     tmp3 += z1 + z4;
     constexpr int S = CB + P1 + 3, R = 1 << (S - 1);
     uint8_t* o = out + rr * out_stride;
-    o[0] = range_limit((tmp10 + tmp3 + R) >> S);
-    o[7] = range_limit((tmp10 - tmp3 + R) >> S);
-    o[1] = range_limit((tmp11 + tmp2 + R) >> S);
-    o[6] = range_limit((tmp11 - tmp2 + R) >> S);
-    o[2] = range_limit((tmp12 + tmp1 + R) >> S);
-    o[5] = range_limit((tmp12 - tmp1 + R) >> S);
-    o[3] = range_limit((tmp13 + tmp0 + R) >> S);
-    o[4] = range_limit((tmp13 - tmp0 + R) >> S);
+    o[0] = range_limit((int)((tmp10 + tmp3 + R) >> S));
+    o[7] = range_limit((int)((tmp10 - tmp3 + R) >> S));
+    o[1] = range_limit((int)((tmp11 + tmp2 + R) >> S));
+    o[6] = range_limit((int)((tmp11 - tmp2 + R) >> S));
+    o[2] = range_limit((int)((tmp12 + tmp1 + R) >> S));
+    o[5] = range_limit((int)((tmp12 - tmp1 + R) >> S));
+    o[3] = range_limit((int)((tmp13 + tmp0 + R) >> S));
+    o[4] = range_limit((int)((tmp13 - tmp0 + R) >> S));
   }
 }
 

@@ -119,8 +119,11 @@ TISE_HD int huff_build(Huff* h, const uint8_t* lens, int n, int lane) {
     cnt[0] = 0;
     int left = 1, err = kOk;
     for (int l = 1; l < 16; ++l) {
-      left = (left << 1) - (int)cnt[l];
-      if (left < 0) err = kBadCodeLengths;
+      left = left * 2 - (int)cnt[l];
+      if (left < 0) {  // over-subscribed
+        err = kBadCodeLengths;
+        break;
+      }
     }
     uint16_t next_code[16], next_idx[16];
     uint32_t c = 0, idx = 0;
