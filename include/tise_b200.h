@@ -111,16 +111,18 @@ int tise_png_decode(tise_ctx* ctx, const uint8_t* h_files, const uint8_t* d_file
 
 /* Baseline JPEG files, same contract as the PNG entry points above: bit-identical to Pillow's
  * Image.open(f).convert("RGB"), i.e. to libjpeg-turbo with its defaults (jpeg_idct_islow, fancy h2v1 / h2v2
- * upsampling, 16-bit fixed-point YCbCr -> RGB).  Handled: 8-bit SOF0 / SOF1 Huffman files with one interleaved scan,
- * grey or YCbCr, chroma 4:4:4 / 4:2:2 / 4:2:0, restart intervals.  Progressive, arithmetic-coded, CMYK and
+ * upsampling, 16-bit fixed-point YCbCr -> RGB).  Handled: 8-bit Huffman files, sequential (SOF0 / SOF1) or progressive
+ * (SOF2), grey or YCbCr, chroma 4:4:4 / 4:2:2 / 4:2:0, restart intervals.  Arithmetic-coded, CMYK and
  * RGB-tagged files are reported with supported = 0 and stay with the caller.  d_status[i]: 0 ok, 21..24 a corrupt
  * entropy-coded segment (csrc/jpeg_core.h), -1 not reached. */
 typedef struct {
   int32_t width, height;
   int32_t components;       /* 1 (grey) or 3 (YCbCr) */
   int32_t chroma_mode;      /* 0 grey, 1 4:4:4, 2 4:2:2 (h2v1), 3 4:2:0 (h2v2) */
-  int32_t restart_interval; /* MCUs between RSTn markers, 0 = none */
+  int32_t restart_interval; /* MCUs between RSTn markers in the first scan, 0 = none */
   int32_t supported;        /* 1: tise_jpeg_decode handles this file */
+  int32_t progressive;      /* SOF2 */
+  int32_t scans;            /* SOS segments */
   int64_t scan_bytes;       /* bytes from the first entropy-coded byte to the end of the file */
   int64_t blocks;           /* 8 x 8 blocks of all components (whole MCUs) */
 } tise_jpeg_info;

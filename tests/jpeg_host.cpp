@@ -29,19 +29,14 @@ int host_jpeg_decode(const uint8_t* file, int64_t n, uint8_t* out, int64_t out_c
     delete h;
     return -3;
   }
-  DTable* dc = new DTable[4];
-  DTable* ac = new DTable[4];
-  for (int t = 0; t < 4; ++t) {
-    if (h->ht_present[0][t]) build_dtable(h->bits[0][t], h->vals[0][t], dc + t);
-    if (h->ht_present[1][t]) build_dtable(h->bits[1][t], h->vals[1][t], ac + t);
-  }
+  DTable* work = new DTable[6];
   int64_t comp_off[3] = {0, 0, 0}, total = 0;
   for (int c = 0; c < h->ncomp; ++c) {
     comp_off[c] = total;
     total += (int64_t)h->comp[c].blocks_w * h->comp[c].blocks_h * 64;
   }
   std::vector<int16_t> coef(total, 0);
-  int st = decode_scan(h, file + h->scan_off, h->scan_bytes, dc, ac, coef.data(), comp_off, true);
+  int st = decode_image(h, file, work, coef.data(), comp_off);
   if (!st) {
     std::vector<std::vector<uint8_t>> planes(h->ncomp);
     const uint8_t* pl[3] = {nullptr, nullptr, nullptr};
@@ -57,8 +52,7 @@ int host_jpeg_decode(const uint8_t* file, int64_t n, uint8_t* out, int64_t out_c
     for (int y = 0; y < h->height; ++y)
       for (int x = 0; x < h->width; ++x) output_pixel(h, pl, x, y, out + ((int64_t)y * h->width + x) * 3);
   }
-  delete[] dc;
-  delete[] ac;
+  delete[] work;
   delete h;
   return st;
 }

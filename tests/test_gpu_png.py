@@ -35,8 +35,9 @@ def test_decode_mixed_batch_bit_exact(engine):
                 im = Image.fromarray(a, mode)
             blobs.append(png_bytes(im, compress_level=int(rng.integers(0, 10))))
     jpg = io.BytesIO()
-    Image.fromarray(smooth_image(rng, 40, 50, 3)).save(jpg, "JPEG", progressive=True)
-    blobs.append(jpg.getvalue())  # progressive JPEG: decoded by PIL like the reference does, uploaded into the same pack
+    a = smooth_image(rng, 40, 50, 3)
+    Image.fromarray(np.dstack([a, a[..., :1]]), "CMYK").save(jpg, "JPEG")
+    blobs.append(jpg.getvalue())  # CMYK JPEG: decoded by PIL like the reference does, uploaded into the same pack
     blobs.append(png_bytes(Image.fromarray(rng.integers(0, 65536, (20, 20)).astype(np.uint16))))  # 16-bit: host
     exotic = [b for _, b in exotic_pngs(rng)]  # 16-bit RGB(A) / GA, 1 / 2 / 4-bit grey and palette, all filter types
     usable = []

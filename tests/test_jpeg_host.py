@@ -63,6 +63,10 @@ def jpeg_cases(rng, sizes=JPEG_SIZES):
         out.append(("optimised %dx%d" % (h, w), jpeg_bytes(a, quality=80, optimize=True)))
         out.append(("restart rows %dx%d" % (h, w), jpeg_bytes(a, quality=80, restart_marker_rows=1)))
         out.append(("restart blocks %dx%d" % (h, w), jpeg_bytes(a, quality=90, subsampling=0, restart_marker_blocks=3)))
+        for sub in (0, 1, 2):  # progressive: spectral selection + successive approximation, ~10 scans, tables per scan
+            out.append(("progressive %dx%d sub%d" % (h, w, sub), jpeg_bytes(a, quality=[40, 85, 100][sub], subsampling=sub, progressive=True)))
+        out.append(("progressive grey %dx%d" % (h, w), jpeg_bytes(a[..., 1], quality=70, progressive=True)))
+        out.append(("progressive restart %dx%d" % (h, w), jpeg_bytes(a, quality=80, progressive=True, restart_marker_rows=1)))
     return out
 
 
@@ -74,7 +78,7 @@ def test_jpeg_decode_matches_pillow_bit_for_bit(host):
         assert st == 0, (name, st)
         assert np.array_equal(got, _pil(blob)), name
         n += 1
-    assert n > 150
+    assert n > 200
 
 
 def test_jpeg_extreme_content(host):
@@ -91,7 +95,6 @@ def test_jpeg_extreme_content(host):
 def test_jpeg_variants_left_to_the_host(host):
     rng = np.random.default_rng(2)
     a = smooth_image(rng, 64, 64, 3)
-    assert _decode(host, jpeg_bytes(a, progressive=True))[0] == -2
     b = io.BytesIO()
     Image.fromarray(np.dstack([a, a[..., :1]]), "CMYK").save(b, "JPEG")
     assert _decode(host, b.getvalue())[0] == -2
@@ -123,7 +126,10 @@ def test_c_abi_jpeg_probe():
     assert info.blocks == 13 * 19 * 4 + 2 * 13 * 19 and info.scan_bytes > 0
     assert lib.tise_jpeg_decode_workspace_bytes(C.byref(info), 1) >= info.blocks * 192
     blob = jpeg_bytes(a, progressive=True)
-    assert lib.tise_jpeg_probe(blob, len(blob), C.byref(info)) == 0 and info.supported == 0
+    assert lib.tise_jpeg_probe(blob, len(blob), C.byref(info)) == 0 and info.supported == 1 and info.progressive == 1 and info.scans > 3
+    cmyk = io.BytesIO()
+    Image.fromarray(np.dstack([a, a[..., :1]]), "CMYK").save(cmyk, "JPEG")
+    assert lib.tise_jpeg_probe(cmyk.getvalue(), len(cmyk.getvalue()), C.byref(info)) == 0 and info.supported == 0
     assert lib.tise_jpeg_probe(b"not a jpeg at all", 17, C.byref(info)) < 0
 
 

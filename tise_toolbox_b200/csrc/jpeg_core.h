@@ -9,11 +9,13 @@
 //   chroma upsampling  jdsample.c    "fancy" triangle filters h2v1 / h2v2 (edge rows / columns replicated as jdmainct.c
 //                                    does), or none for 4:4:4
 //   colour conversion  jdcolor.c     YCbCr -> RGB with 16-bit fixed-point tables
-// Handled: 8-bit baseline / extended-sequential Huffman JPEGs (SOF0 / SOF1), one interleaved scan, grey or YCbCr with
-// chroma sampling 4:4:4, 4:2:2 (h2v1) or 4:2:0 (h2v2).  Progressive, arithmetic, CMYK / RGB-tagged files and other
+// Handled: 8-bit Huffman JPEGs -- baseline / extended sequential (SOF0 / SOF1, interleaved or one scan per component) and
+// progressive (SOF2: spectral selection + successive approximation, jdphuff.c) -- grey or YCbCr with chroma sampling
+// 4:4:4, 4:2:2 (h2v1) or 4:2:0 (h2v2), restart intervals.  Arithmetic coding, CMYK / RGB-tagged files and other
 // sampling layouts are reported as unsupported by parse() and stay on the host.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define TISE_JHD __host__ __device__ __forceinline__
@@ -34,23 +36,36 @@ enum Status : int32_t {
 };
 
 struct Component {
-  int32_t id, h, v, tq, td, ta;
+  int32_t id, h, v, tq;
   int32_t blocks_w, blocks_h;  // blocks per row / column of this component's plane (whole MCUs)
   int32_t ds_w, ds_h;          // ceil(width * h / hmax), ceil(height * v / vmax): the real samples
 };
 
+constexpr int kMaxScans = 24;   // progressive files written by libjpeg have ~10 scans
+constexpr int kMaxTables = 40;  // every DHT definition met in the file, in order (tables may be redefined between scans)
+
+struct Scan {
+  int32_t ncomp, comp[3];        // indices into Header::comp
+  int32_t dc_tab[3], ac_tab[3];  // indices into the table pool, -1 = none defined
+  int32_t ss, se, ah, al;        // spectral selection / successive approximation (0, 63, 0, 0 for sequential scans)
+  int32_t restart_interval;
+  int32_t pad;
+  int64_t off, bytes;            // entropy-coded segment of this scan, relative to the first byte of the file
+};
+
 struct Header {
   int32_t width, height, ncomp, hmax, vmax;
-  int32_t mcus_x, mcus_y, restart_interval;
+  int32_t mcus_x, mcus_y;
   int32_t supported;
   int32_t chroma_mode;  // 0 grey, 1 4:4:4, 2 h2v1, 3 h2v2
-  int64_t scan_off, scan_bytes;  // entropy-coded segment (from the byte after the SOS header to the end of the file)
+  int32_t progressive, nscans, ntables;
+  int64_t scan_bytes;   // entropy-coded bytes of all scans
   Component comp[3];
-  uint16_t qt[4][64];     // quantisation tables in NATURAL order
+  Scan scans[kMaxScans];
+  uint16_t qt[4][64];   // quantisation tables in NATURAL order
   uint8_t qt_present[4];
-  uint8_t bits[2][4][17];   // [class 0 = DC / 1 = AC][table id][code length] -> number of codes
-  uint8_t vals[2][4][256];
-  uint8_t ht_present[2][4];
+  uint8_t bits[kMaxTables][17];  // code length -> number of codes
+  uint8_t vals[kMaxTables][256];
 };
 
 TISE_JHD int natural_order(int k) {
@@ -67,9 +82,11 @@ inline int parse(const uint8_t* f, int64_t n, Header* h) {
   *h = Header();
   if (n < 4 || f[0] != 0xFF || f[1] != 0xD8) return -1;
   int64_t p = 2;
-  bool have_sof = false, have_sos = false, ok = true;
-  int adobe_transform = -1;
-  while (p + 4 <= n) {
+  bool have_sof = false, ok = true, sequential_done = false;
+  int adobe_transform = -1, restart_interval = 0;
+  int cur[2][4] = {{-1, -1, -1, -1}, {-1, -1, -1, -1}};  // current table of each (class, id) -> pool index
+  bool covered[3] = {false, false, false};
+  while (p + 4 <= n && !sequential_done) {
     if (f[p] != 0xFF) return -1;
     while (p < n && f[p] == 0xFF) ++p;  // fill bytes
     if (p >= n) return -1;
@@ -82,6 +99,7 @@ inline int parse(const uint8_t* f, int64_t n, Header* h) {
     const uint8_t* d = f + p + 2;
     const int dl = len - 2;
     if (m == 0xDB) {  // DQT
+      if (h->nscans) ok = false;  // (libjpeg latches a component's table at its first scan; redefinitions: host)
       int q = 0;
       while (q < dl) {
         const int pq = d[q] >> 4, tq = d[q] & 15;
@@ -101,23 +119,26 @@ inline int parse(const uint8_t* f, int64_t n, Header* h) {
         ++q;
         if (tc > 1 || th > 3 || q + 16 > dl) return -1;
         int total = 0;
-        h->bits[tc][th][0] = 0;
-        for (int i = 1; i <= 16; ++i) {
-          h->bits[tc][th][i] = d[q + i - 1];
-          total += d[q + i - 1];
+        for (int i = 1; i <= 16; ++i) total += d[q + i - 1];
+        if (total > 256 || q + 16 + total > dl) return -1;
+        if (h->ntables >= kMaxTables) {
+          ok = false;
+        } else {
+          const int t = h->ntables++;
+          h->bits[t][0] = 0;
+          for (int i = 1; i <= 16; ++i) h->bits[t][i] = d[q + i - 1];
+          for (int i = 0; i < total; ++i) h->vals[t][i] = d[q + 16 + i];
+          cur[tc][th] = t;
         }
-        q += 16;
-        if (total > 256 || q + total > dl) return -1;
-        for (int i = 0; i < total; ++i) h->vals[tc][th][i] = d[q + i];
-        q += total;
-        h->ht_present[tc][th] = 1;
+        q += 16 + total;
       }
-    } else if (m == 0xC0 || m == 0xC1) {  // SOF0 / SOF1
+    } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {  // SOF0 / SOF1 (sequential), SOF2 (progressive), Huffman
       if (dl < 6 || have_sof) return -1;
       const int prec = d[0];
       h->height = (d[1] << 8) | d[2];
       h->width = (d[3] << 8) | d[4];
       h->ncomp = d[5];
+      h->progressive = m == 0xC2;
       if (prec != 8 || (h->ncomp != 1 && h->ncomp != 3) || dl < 6 + 3 * h->ncomp || h->width <= 0 || h->height <= 0) ok = false;
       for (int c = 0; c < h->ncomp && c < 3 && dl >= 6 + 3 * h->ncomp; ++c) {
         h->comp[c].id = d[6 + 3 * c];
@@ -126,7 +147,7 @@ inline int parse(const uint8_t* f, int64_t n, Header* h) {
         h->comp[c].tq = d[8 + 3 * c];
       }
       have_sof = true;
-    } else if (m >= 0xC2 && m <= 0xCF && m != 0xC8) {  // progressive, lossless, arithmetic ...
+    } else if (m >= 0xC3 && m <= 0xCF && m != 0xC8) {  // lossless, differential, arithmetic ...
       have_sof = true;
       ok = false;
       if (dl >= 6) {
@@ -135,31 +156,92 @@ inline int parse(const uint8_t* f, int64_t n, Header* h) {
       }
     } else if (m == 0xDD) {  // DRI
       if (dl < 2) return -1;
-      h->restart_interval = (d[0] << 8) | d[1];
+      restart_interval = (d[0] << 8) | d[1];
     } else if (m == 0xEE) {  // APP14 "Adobe"
       if (dl >= 12 && d[0] == 'A' && d[1] == 'd' && d[2] == 'o' && d[3] == 'b' && d[4] == 'e') adobe_transform = d[11];
     } else if (m == 0xDA) {  // SOS
       if (!have_sof || dl < 1) return -1;
       const int ns = d[0];
-      if (ns != h->ncomp || dl < 1 + 2 * ns + 3) ok = false;
-      for (int c = 0; c < ns && c < 3 && ok; ++c) {
-        if (d[1 + 2 * c] != h->comp[c].id) ok = false;  // components in frame order
-        h->comp[c].td = d[2 + 2 * c] >> 4;
-        h->comp[c].ta = d[2 + 2 * c] & 15;
+      if (ns < 1 || ns > 4 || dl < 1 + 2 * ns + 3) return -1;
+      if (ns > 3 || ns > h->ncomp) {  // CMYK / YCCK: a JPEG, but not one the device decoder takes
+        ok = false;
+        break;
       }
-      h->scan_off = p + len;
-      h->scan_bytes = n - h->scan_off;
-      have_sos = true;
-      break;
+      const int64_t data = p + len;
+      int64_t end = n;
+      if (h->nscans >= kMaxScans || !ok) {
+        ok = false;
+      } else {
+        Scan& sc = h->scans[h->nscans];
+        sc.ncomp = ns;
+        for (int c = 0; c < ns; ++c) {
+          int ci = -1;
+          for (int k = 0; k < h->ncomp && k < 3; ++k)
+            if (h->comp[k].id == d[1 + 2 * c]) ci = k;
+          if (ci < 0 || (c > 0 && ci <= sc.comp[c - 1])) ok = false;  // unknown id, or not in frame order
+          sc.comp[c] = ci < 0 ? 0 : ci;
+          const int td = d[2 + 2 * c] >> 4, ta = d[2 + 2 * c] & 15;
+          sc.dc_tab[c] = td < 4 ? cur[0][td] : -1;
+          sc.ac_tab[c] = ta < 4 ? cur[1][ta] : -1;
+          if (ci >= 0) covered[ci] = true;
+        }
+        sc.ss = d[1 + 2 * ns];
+        sc.se = d[2 + 2 * ns];
+        sc.ah = d[3 + 2 * ns] >> 4;
+        sc.al = d[3 + 2 * ns] & 15;
+        sc.restart_interval = restart_interval;
+        sc.off = data;
+        if (!h->progressive) {
+          sc.ss = 0;
+          sc.se = 63;
+          sc.ah = sc.al = 0;
+        } else if (sc.ss > sc.se || sc.se > 63 || sc.al > 13 || sc.ah > 13 || (sc.ss == 0 && sc.se != 0) || (sc.ss > 0 && ns != 1)) {
+          ok = false;
+        }
+        // tables this kind of scan reads
+        for (int c = 0; c < ns; ++c) {
+          const bool need_dc = !h->progressive || (sc.ss == 0 && sc.ah == 0);
+          const bool need_ac = !h->progressive || sc.ss > 0;
+          if ((need_dc && sc.dc_tab[c] < 0) || (need_ac && sc.ac_tab[c] < 0)) ok = false;
+        }
+        bool all = true;
+        for (int c = 0; c < h->ncomp && c < 3; ++c) all = all && covered[c];
+        if (!h->progressive && all) {
+          sequential_done = true;  // every component decoded: nothing else can follow but EOI; skip the byte walk
+        } else {
+          int64_t q = data;  // find the marker that ends this scan's entropy-coded segment
+          end = n;
+          while (q + 1 < n) {
+            const uint8_t* ff = (const uint8_t*)memchr(f + q, 0xFF, (size_t)(n - q - 1));
+            if (!ff) break;
+            q = ff - f;
+            const int nx = f[q + 1];
+            if (nx == 0x00 || (nx >= 0xD0 && nx <= 0xD7)) {
+              q += 2;
+            } else if (nx == 0xFF) {
+              q += 1;
+            } else {
+              end = q;
+              break;
+            }
+          }
+        }
+        sc.bytes = end - data;
+        h->scan_bytes += sc.bytes;
+        h->nscans++;
+      }
+      p = end;
+      continue;
     }
     p += len;
   }
-  if (!have_sof || !have_sos) return -1;
+  if (!have_sof) return -1;
+  if (h->nscans == 0) ok = false;
   // what the device decoder handles
   if (ok) {
     for (int c = 0; c < h->ncomp; ++c) {
       const Component& k = h->comp[c];
-      if (k.tq > 3 || !h->qt_present[k.tq] || k.td > 3 || k.ta > 3 || !h->ht_present[0][k.td] || !h->ht_present[1][k.ta]) ok = false;
+      if (k.tq > 3 || !h->qt_present[k.tq] || !covered[c]) ok = false;
     }
   }
   if (ok && h->ncomp == 1) {
@@ -301,73 +383,217 @@ TISE_JHD int huff_decode(const DTable* t, BitReader& r) {  // needs >= 16 buffer
   return t->vals[(code + t->valoffset[l]) & 255];
 }
 
-// Entropy-decodes the whole scan.  coef: per component a plane of blocks (blocks_w x blocks_h) x 64 int16 in natural
-// order, zero-initialised by the caller; comp_off[c] = first int16 of component c.  Every lane may run this with the
-// same arguments (warp-uniform, registers only); stores happen when `store` is true (lane 0).
-TISE_JHD int decode_scan(const Header* h, const uint8_t* scan, int64_t scan_bytes, const DTable* dc, const DTable* ac,
-                         int16_t* coef, const int64_t* comp_off, bool store) {
+// Entropy decoding of all scans of one image (jdhuff.c decode_mcu for sequential files, jdphuff.c decode_mcu_DC_first /
+// DC_refine / AC_first / AC_refine for progressive ones).  coef: per component a plane of blocks (blocks_w x blocks_h)
+// x 64 int16 in natural order, zero-initialised by the caller; comp_off[c] = first int16 of component c.  work: 6
+// tables of scratch (3 DC + 3 AC, rebuilt for every scan).  Runs on ONE thread.
+struct ScanState {
   BitReader r;
-  br_init(r, scan, scan_bytes);
-  int pred[3] = {0, 0, 0};
-  int restarts_left = h->restart_interval, next_rst = 0;
-  for (int my = 0; my < h->mcus_y; ++my) {
-    for (int mx = 0; mx < h->mcus_x; ++mx) {
-      if (h->restart_interval) {
-        if (restarts_left == 0) {
-          // byte align, expect RSTn
-          br_skip(r, r.cnt & 7);
+  int pred[3];
+  int eobrun;
+  int restarts_left, next_rst;
+};
+
+TISE_JHD int scan_restart(ScanState& st, int interval) {
+  BitReader& r = st.r;
+  br_skip(r, r.cnt & 7);
+  br_fill(r);
+  if (r.hit_marker != 0xD0 + st.next_rst) return kBadRestart;
+  r.p += 2;  // the reader stopped AT the marker: step over it and restart the bit buffer
+  r.buf = 0;
+  r.cnt = 0;
+  r.hit_marker = 0;
+  st.next_rst = (st.next_rst + 1) & 7;
+  st.restarts_left = interval;
+  st.pred[0] = st.pred[1] = st.pred[2] = 0;
+  st.eobrun = 0;
+  return kOk;
+}
+
+TISE_JHD int block_sequential(ScanState& st, int c, const DTable* dct, const DTable* act, int16_t* blk) {
+  BitReader& r = st.r;
+  br_fill(r);
+  int s = huff_decode(dct, r);
+  if (s < 0) return kBadHuffmanCode;
+  if (s > 15) return kBadCoefficient;
+  if (s) {
+    br_fill(r);
+    s = huff_extend(br_get(r, s), s);
+  }
+  st.pred[c] += s;
+  blk[0] = (int16_t)st.pred[c];
+  for (int kk = 1; kk < 64; ++kk) {
+    br_fill(r);
+    const int rs = huff_decode(act, r);
+    if (rs < 0) return kBadHuffmanCode;
+    const int run = rs >> 4;
+    s = rs & 15;
+    if (s) {
+      kk += run;
+      if (kk > 63) return kBadCoefficient;
+      blk[natural_order(kk)] = (int16_t)huff_extend(br_get(r, s), s);
+    } else {
+      if (run != 15) break;
+      kk += 15;
+    }
+  }
+  return kOk;
+}
+
+TISE_JHD int block_dc_first(ScanState& st, int c, const DTable* dct, int al, int16_t* blk) {
+  BitReader& r = st.r;
+  br_fill(r);
+  int s = huff_decode(dct, r);
+  if (s < 0) return kBadHuffmanCode;
+  if (s > 15) return kBadCoefficient;
+  if (s) {
+    br_fill(r);
+    s = huff_extend(br_get(r, s), s);
+  }
+  st.pred[c] += s;
+  blk[0] = (int16_t)(st.pred[c] * (1 << al));
+  return kOk;
+}
+
+TISE_JHD int block_ac_first(ScanState& st, const DTable* act, int ss, int se, int al, int16_t* blk) {
+  if (st.eobrun > 0) {
+    st.eobrun--;
+    return kOk;
+  }
+  BitReader& r = st.r;
+  for (int k = ss; k <= se; ++k) {
+    br_fill(r);
+    const int rs = huff_decode(act, r);
+    if (rs < 0) return kBadHuffmanCode;
+    const int run = rs >> 4, s = rs & 15;
+    if (s) {
+      k += run;
+      if (k > 63) return kBadCoefficient;
+      blk[natural_order(k)] = (int16_t)(huff_extend(br_get(r, s), s) * (1 << al));
+    } else if (run == 15) {
+      k += 15;
+    } else {
+      st.eobrun = 1 << run;
+      if (run) st.eobrun += br_get(r, run);
+      st.eobrun--;
+      break;
+    }
+  }
+  return kOk;
+}
+
+TISE_JHD void refine_nonzero(BitReader& r, int16_t* coef, int p1, int m1) {
+  br_fill(r);
+  if (br_get(r, 1)) {
+    if ((*coef & p1) == 0) *coef = (int16_t)(*coef >= 0 ? *coef + p1 : *coef + m1);
+  }
+}
+
+TISE_JHD int block_ac_refine(ScanState& st, const DTable* act, int ss, int se, int al, int16_t* blk) {
+  BitReader& r = st.r;
+  const int p1 = 1 << al, m1 = -(1 << al);
+  int k = ss;
+  if (st.eobrun == 0) {
+    for (; k <= se; ++k) {
+      br_fill(r);
+      const int rs = huff_decode(act, r);
+      if (rs < 0) return kBadHuffmanCode;
+      int run = rs >> 4, s = rs & 15;
+      if (s) {  // a newly non-zero coefficient: its sign follows (size is always 1)
+        br_fill(r);
+        s = br_get(r, 1) ? p1 : m1;
+      } else if (run != 15) {
+        st.eobrun = 1 << run;
+        if (run) {
           br_fill(r);
-          if (r.hit_marker != 0xD0 + next_rst) return kBadRestart;
-          // the reader stopped AT the marker: step over it and restart the bit buffer
-          r.p += 2;
-          r.buf = 0;
-          r.cnt = 0;
-          r.hit_marker = 0;
-          next_rst = (next_rst + 1) & 7;
-          restarts_left = h->restart_interval;
-          pred[0] = pred[1] = pred[2] = 0;
+          st.eobrun += br_get(r, run);
         }
-        --restarts_left;
+        break;  // end of band
       }
-      for (int c = 0; c < h->ncomp; ++c) {
-        const Component& k = h->comp[c];
-        const DTable* dct = dc + k.td;
-        const DTable* act = ac + k.ta;
-        for (int by = 0; by < k.v; ++by)
-          for (int bx = 0; bx < k.h; ++bx) {
-            int16_t* blk = coef + comp_off[c] + ((int64_t)(my * k.v + by) * k.blocks_w + (mx * k.h + bx)) * 64;
-            br_fill(r);
-            int s = huff_decode(dct, r);
-            if (s < 0) return kBadHuffmanCode;
-            if (s > 15) return kBadCoefficient;
-            if (s) {
-              br_fill(r);
-              s = huff_extend(br_get(r, s), s);
-            }
-            pred[c] += s;
-            if (store) blk[0] = (int16_t)pred[c];
-            for (int kk = 1; kk < 64; ++kk) {
-              br_fill(r);
-              int rs = huff_decode(act, r);
-              if (rs < 0) return kBadHuffmanCode;
-              const int run = rs >> 4;
-              s = rs & 15;
-              if (s) {
-                kk += run;
-                if (kk > 63) return kBadCoefficient;
-                const int v = huff_extend(br_get(r, s), s);
-                if (store) blk[natural_order(kk)] = (int16_t)v;
-              } else {
-                if (run != 15) break;
-                kk += 15;
-              }
-            }
-          }
+      // advance over already-non-zero coefficients and `run` still-zero ones, appending correction bits to the former
+      do {
+        int16_t* cf = blk + natural_order(k);
+        if (*cf != 0) {
+          refine_nonzero(r, cf, p1, m1);
+        } else {
+          if (--run < 0) break;
+        }
+        ++k;
+      } while (k <= se);
+      if (s) {
+        if (k > 63) return kBadCoefficient;
+        blk[natural_order(k)] = (int16_t)s;
       }
     }
   }
-  // data that ends before the last MCU shows up as a marker hit with MCUs decoded from zero padding
-  if (r.hit_marker && r.hit_marker != 0xD9 && !(r.hit_marker >= 0xD0 && r.hit_marker <= 0xD7)) return kTruncated;
+  if (st.eobrun > 0) {
+    for (; k <= se; ++k) {
+      int16_t* cf = blk + natural_order(k);
+      if (*cf != 0) refine_nonzero(r, cf, p1, m1);
+    }
+    st.eobrun--;
+  }
+  return kOk;
+}
+
+TISE_JHD int decode_image(const Header* h, const uint8_t* file, DTable* work, int16_t* coef, const int64_t* comp_off) {
+  for (int si = 0; si < h->nscans; ++si) {
+    const Scan& sc = h->scans[si];
+    const bool prog = h->progressive != 0;
+    const bool dc_scan = !prog || sc.ss == 0, ac_scan = !prog || sc.ss > 0;
+    for (int c = 0; c < sc.ncomp; ++c) {
+      if (dc_scan && (!prog || sc.ah == 0)) build_dtable(h->bits[sc.dc_tab[c]], h->vals[sc.dc_tab[c]], work + c);
+      if (ac_scan) build_dtable(h->bits[sc.ac_tab[c]], h->vals[sc.ac_tab[c]], work + 3 + c);
+    }
+    ScanState st;
+    br_init(st.r, file + sc.off, sc.bytes);
+    st.pred[0] = st.pred[1] = st.pred[2] = 0;
+    st.eobrun = 0;
+    st.restarts_left = sc.restart_interval;
+    st.next_rst = 0;
+    // MCU grid of this scan: interleaved scans walk the frame's MCUs, a single-component scan walks that component's own
+    // blocks (ceil(samples / 8): the MCU padding of the frame is not coded)
+    const Component& k0 = h->comp[sc.comp[0]];
+    const int gx = sc.ncomp > 1 ? h->mcus_x : (k0.ds_w + 7) / 8, gy = sc.ncomp > 1 ? h->mcus_y : (k0.ds_h + 7) / 8;
+    for (int my = 0; my < gy; ++my)
+      for (int mx = 0; mx < gx; ++mx) {
+        if (sc.restart_interval) {
+          if (st.restarts_left == 0) {
+            const int e = scan_restart(st, sc.restart_interval);
+            if (e) return e;
+          }
+          --st.restarts_left;
+        }
+        for (int c = 0; c < sc.ncomp; ++c) {
+          const int ci = sc.comp[c];
+          const Component& k = h->comp[ci];
+          const int bh = sc.ncomp > 1 ? k.h : 1, bv = sc.ncomp > 1 ? k.v : 1;
+          for (int by = 0; by < bv; ++by)
+            for (int bx = 0; bx < bh; ++bx) {
+              int16_t* blk = coef + comp_off[ci] + ((int64_t)(my * bv + by) * k.blocks_w + (mx * bh + bx)) * 64;
+              int e;
+              if (!prog) {
+                e = block_sequential(st, ci, work + c, work + 3 + c, blk);
+              } else if (sc.ss == 0) {
+                if (sc.ah == 0) {
+                  e = block_dc_first(st, ci, work + c, sc.al, blk);
+                } else {
+                  br_fill(st.r);
+                  if (br_get(st.r, 1)) blk[0] = (int16_t)(blk[0] | (1 << sc.al));
+                  e = kOk;
+                }
+              } else {
+                e = sc.ah == 0 ? block_ac_first(st, work + 3 + c, sc.ss, sc.se, sc.al, blk)
+                               : block_ac_refine(st, work + 3 + c, sc.ss, sc.se, sc.al, blk);
+              }
+              if (e) return e;
+            }
+        }
+      }
+    const int hm = st.r.hit_marker;  // entropy data that ends early shows up as an unexpected marker before the last MCU
+    if (hm && hm != 0xD9 && hm != 0xDA && hm != 0xC4 && hm != 0xDD && !(hm >= 0xD0 && hm <= 0xD7) && hm != 0xFE && !(hm >= 0xE0 && hm <= 0xEF))
+      return kTruncated;
+  }
   return kOk;
 }
 

@@ -1,9 +1,10 @@
 // A1: baseline JPEG files -> packed RGB8 HWC images in HBM, bit-identical to Pillow's
 // Image.open(f).convert("RGB") (libjpeg-turbo defaults: islow IDCT, fancy upsampling) -- image_realism/FID/img_data.py:21.
 // The algorithms live in jpeg_core.h (also compiled for the host by the CPU test-suite).  Three kernels per batch:
-//   jpeg_entropy_kernel  one warp per image: the lanes build the (up to 8) Huffman look-up tables in shared memory and
-//                        zero the coefficient planes, lane 0 walks the entropy-coded segment (byte-stuffed, MSB first,
-//                        restart intervals) and stores the non-zero coefficients            (latency bound, serial stream)
+//   jpeg_entropy_kernel  one warp per image: the lanes zero the coefficient planes, lane 0 walks the entropy-coded
+//                        segments of all scans (byte-stuffed, MSB first, restart intervals; sequential or progressive
+//                        with spectral selection / successive approximation), rebuilding the Huffman look-up tables
+//                        of each scan in shared memory                                     (latency bound, serial stream)
 //   jpeg_idct_kernel     one thread per 8 x 8 block: dequantise + jpeg_idct_islow into uint8 component planes
 //   jpeg_color_kernel    one thread per output pixel: h2v1 / h2v2 triangle upsampling of Cb / Cr + YCbCr -> RGB
 #include <stdarg.h>
@@ -28,7 +29,7 @@ struct JpegDesc {
 
 constexpr int kJpegWarps = 4;
 struct JpegSmem {
-  jpg::DTable dc[4], ac[4];
+  jpg::DTable work[6];  // 3 DC + 3 AC tables of the scan being decoded
 };
 
 __global__ void __launch_bounds__(kJpegWarps * 32) jpeg_entropy_kernel(const JpegDesc* __restrict__ descs, int n,
@@ -39,18 +40,14 @@ __global__ void __launch_bounds__(kJpegWarps * 32) jpeg_entropy_kernel(const Jpe
   const int img = blockIdx.x * kJpegWarps + warp;
   if (img >= n) return;
   const JpegDesc& d = descs[img];
-  if (lane < 8) {
-    const int cls = lane >> 2, id = lane & 3;
-    if (d.h.ht_present[cls][id]) jpg::build_dtable(d.h.bits[cls][id], d.h.vals[cls][id], cls ? &sm[warp].ac[id] : &sm[warp].dc[id]);
-  }
   uint32_t* z = reinterpret_cast<uint32_t*>(ws + d.coef_off);
   const long long words = d.blocks * 32;  // 64 int16 per block
   for (long long i = lane; i < words; i += 32) z[i] = 0u;
   __syncwarp();
   int st = 0;
   if (lane == 0)
-    st = jpg::decode_scan(&d.h, files + d.file_off + d.h.scan_off, d.h.scan_bytes, sm[warp].dc, sm[warp].ac,
-                          reinterpret_cast<int16_t*>(ws + d.coef_off), reinterpret_cast<const int64_t*>(d.comp_coef), true);
+    st = jpg::decode_image(&d.h, files + d.file_off, sm[warp].work, reinterpret_cast<int16_t*>(ws + d.coef_off),
+                           reinterpret_cast<const int64_t*>(d.comp_coef));
   if (lane == 0) status[img] = st;
 }
 
@@ -102,7 +99,9 @@ static void fill_jpeg_info(const jpg::Header& h, tise_jpeg_info* info) {
   info->height = h.height;
   info->components = h.ncomp;
   info->chroma_mode = h.chroma_mode;
-  info->restart_interval = h.restart_interval;
+  info->restart_interval = h.nscans ? h.scans[0].restart_interval : 0;
+  info->progressive = h.progressive;
+  info->scans = h.nscans;
   info->supported = h.supported;
   info->scan_bytes = h.scan_bytes;
   info->blocks = h.supported ? jpeg_blocks(h) : 0;

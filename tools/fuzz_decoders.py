@@ -44,6 +44,8 @@ def run(trials, libs):
         pb = b.getvalue()
         b = io.BytesIO()
         kw = {"restart_marker_blocks": int(rng.integers(1, 5))} if trial % 3 == 0 else {}
+        if trial % 2:
+            kw["progressive"] = True  # multi-scan files: spectral selection, successive approximation, EOB runs
         Image.fromarray(a).save(b, "JPEG", quality=int(rng.integers(5, 100)), subsampling=int(rng.integers(0, 3)), **kw)
         jb = b.getvalue()
         for blob, f in ((pb, png.host_png_decode), (jb, jpg.host_jpeg_decode)):
