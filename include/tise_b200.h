@@ -123,6 +123,8 @@ typedef struct {
   int32_t supported;        /* 1: tise_jpeg_decode handles this file */
   int32_t progressive;      /* SOF2 */
   int32_t scans;            /* SOS segments */
+  int32_t huffman_tables;   /* DHT definitions in the file */
+  int32_t pad;
   int64_t scan_bytes;       /* bytes from the first entropy-coded byte to the end of the file */
   int64_t blocks;           /* 8 x 8 blocks of all components (whole MCUs) */
 } tise_jpeg_info;

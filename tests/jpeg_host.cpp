@@ -36,7 +36,7 @@ int host_jpeg_decode(const uint8_t* file, int64_t n, uint8_t* out, int64_t out_c
     total += (int64_t)h->comp[c].blocks_w * h->comp[c].blocks_h * 64;
   }
   std::vector<int16_t> coef(total, 0);
-  int st = decode_image(h, file, work, coef.data(), comp_off);
+  int st = decode_image(h, h->scans, h->tables, file, work, coef.data(), comp_off);
   if (!st) {
     std::vector<std::vector<uint8_t>> planes(h->ncomp);
     const uint8_t* pl[3] = {nullptr, nullptr, nullptr};

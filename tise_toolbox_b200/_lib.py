@@ -25,7 +25,7 @@ class PngInfo(C.Structure):
 
 class JpegInfo(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("components", C.c_int32), ("chroma_mode", C.c_int32),
-                ("restart_interval", C.c_int32), ("supported", C.c_int32), ("progressive", C.c_int32), ("scans", C.c_int32),
+                ("restart_interval", C.c_int32), ("supported", C.c_int32), ("progressive", C.c_int32), ("scans", C.c_int32), ("huffman_tables", C.c_int32), ("pad", C.c_int32),
                 ("scan_bytes", C.c_int64),
                 ("blocks", C.c_int64)]
 

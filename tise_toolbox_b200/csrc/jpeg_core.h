@@ -53,7 +53,14 @@ struct Scan {
   int64_t off, bytes;            // entropy-coded segment of this scan, relative to the first byte of the file
 };
 
-struct Header {
+struct HuffDef {
+  uint8_t bits[17];  // code length -> number of codes
+  uint8_t vals[256];
+  uint8_t pad[15];
+};
+
+// What the kernels need of one image (the scans and Huffman definitions travel in pools next to it).
+struct Core {
   int32_t width, height, ncomp, hmax, vmax;
   int32_t mcus_x, mcus_y;
   int32_t supported;
@@ -61,11 +68,14 @@ struct Header {
   int32_t progressive, nscans, ntables;
   int64_t scan_bytes;   // entropy-coded bytes of all scans
   Component comp[3];
-  Scan scans[kMaxScans];
   uint16_t qt[4][64];   // quantisation tables in NATURAL order
   uint8_t qt_present[4];
-  uint8_t bits[kMaxTables][17];  // code length -> number of codes
-  uint8_t vals[kMaxTables][256];
+  uint8_t pad[4];
+};
+
+struct Header : Core {
+  Scan scans[kMaxScans];
+  HuffDef tables[kMaxTables];
 };
 
 TISE_JHD int natural_order(int k) {
@@ -125,9 +135,9 @@ inline int parse(const uint8_t* f, int64_t n, Header* h) {
           ok = false;
         } else {
           const int t = h->ntables++;
-          h->bits[t][0] = 0;
-          for (int i = 1; i <= 16; ++i) h->bits[t][i] = d[q + i - 1];
-          for (int i = 0; i < total; ++i) h->vals[t][i] = d[q + 16 + i];
+          h->tables[t].bits[0] = 0;
+          for (int i = 1; i <= 16; ++i) h->tables[t].bits[i] = d[q + i - 1];
+          for (int i = 0; i < total; ++i) h->tables[t].vals[i] = d[q + 16 + i];
           cur[tc][th] = t;
         }
         q += 16 + total;
@@ -536,14 +546,15 @@ TISE_JHD int block_ac_refine(ScanState& st, const DTable* act, int ss, int se, i
   return kOk;
 }
 
-TISE_JHD int decode_image(const Header* h, const uint8_t* file, DTable* work, int16_t* coef, const int64_t* comp_off) {
+TISE_JHD int decode_image(const Core* h, const Scan* scans, const HuffDef* tables, const uint8_t* file, DTable* work,
+                          int16_t* coef, const int64_t* comp_off) {
   for (int si = 0; si < h->nscans; ++si) {
-    const Scan& sc = h->scans[si];
+    const Scan& sc = scans[si];
     const bool prog = h->progressive != 0;
     const bool dc_scan = !prog || sc.ss == 0, ac_scan = !prog || sc.ss > 0;
     for (int c = 0; c < sc.ncomp; ++c) {
-      if (dc_scan && (!prog || sc.ah == 0)) build_dtable(h->bits[sc.dc_tab[c]], h->vals[sc.dc_tab[c]], work + c);
-      if (ac_scan) build_dtable(h->bits[sc.ac_tab[c]], h->vals[sc.ac_tab[c]], work + 3 + c);
+      if (dc_scan && (!prog || sc.ah == 0)) build_dtable(tables[sc.dc_tab[c]].bits, tables[sc.dc_tab[c]].vals, work + c);
+      if (ac_scan) build_dtable(tables[sc.ac_tab[c]].bits, tables[sc.ac_tab[c]].vals, work + 3 + c);
     }
     ScanState st;
     br_init(st.r, file + sc.off, sc.bytes);
@@ -743,7 +754,7 @@ TISE_JHD void ycc_to_rgb(int y, int cb, int cr, uint8_t* rgb) {
   rgb[2] = (uint8_t)clamp255(y + b_add);
 }
 
-TISE_JHD void output_pixel(const Header* h, const uint8_t* const* planes, int x, int y, uint8_t* rgb) {
+TISE_JHD void output_pixel(const Core* h, const uint8_t* const* planes, int x, int y, uint8_t* rgb) {
   const int py = h->comp[0].blocks_w * 8;
   const int yy = planes[0][(int64_t)y * py + x];
   if (h->ncomp == 1) {

@@ -17,7 +17,9 @@
 namespace tise {
 
 struct JpegDesc {
-  jpg::Header h;
+  jpg::Core h;
+  long long scan_base;    // first entry of this image in the scan pool / the Huffman-definition pool
+  long long table_base;
   long long file_off;     // byte offset of the file in d_files
   long long coef_off;     // byte offset of the int16 coefficient planes in the workspace
   long long plane_off;    // byte offset of the uint8 component planes in the workspace
@@ -33,6 +35,8 @@ struct JpegSmem {
 };
 
 __global__ void __launch_bounds__(kJpegWarps * 32) jpeg_entropy_kernel(const JpegDesc* __restrict__ descs, int n,
+                                                                       const jpg::Scan* __restrict__ scans,
+                                                                       const jpg::HuffDef* __restrict__ tables,
                                                                        const uint8_t* __restrict__ files, uint8_t* ws,
                                                                        int* __restrict__ status) {
   __shared__ JpegSmem sm[kJpegWarps];
@@ -46,7 +50,8 @@ __global__ void __launch_bounds__(kJpegWarps * 32) jpeg_entropy_kernel(const Jpe
   __syncwarp();
   int st = 0;
   if (lane == 0)
-    st = jpg::decode_image(&d.h, files + d.file_off, sm[warp].work, reinterpret_cast<int16_t*>(ws + d.coef_off),
+    st = jpg::decode_image(&d.h, scans + d.scan_base, tables + d.table_base, files + d.file_off, sm[warp].work,
+                           reinterpret_cast<int16_t*>(ws + d.coef_off),
                            reinterpret_cast<const int64_t*>(d.comp_coef));
   if (lane == 0) status[img] = st;
 }
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(256) jpeg_color_kernel(const JpegDesc* __restr
   o[2] = rgb[2];
 }
 
-static long long jpeg_blocks(const jpg::Header& h) {
+static long long jpeg_blocks(const jpg::Core& h) {
   long long b = 0;
   for (int c = 0; c < h.ncomp; ++c) b += (long long)h.comp[c].blocks_w * h.comp[c].blocks_h;
   return b;
@@ -102,6 +107,7 @@ static void fill_jpeg_info(const jpg::Header& h, tise_jpeg_info* info) {
   info->restart_interval = h.nscans ? h.scans[0].restart_interval : 0;
   info->progressive = h.progressive;
   info->scans = h.nscans;
+  info->huffman_tables = h.ntables;
   info->supported = h.supported;
   info->scan_bytes = h.scan_bytes;
   info->blocks = h.supported ? jpeg_blocks(h) : 0;
@@ -127,8 +133,13 @@ extern "C" int tise_jpeg_probe(const uint8_t* h_file, int64_t file_bytes, tise_j
 extern "C" size_t tise_jpeg_decode_workspace_bytes(const tise_jpeg_info* infos, int n) {
   if (!infos || n <= 0) return 0;
   size_t total = align_up(sizeof(JpegDesc) * (size_t)n, 256);
-  for (int i = 0; i < n; ++i) total += align_up((size_t)infos[i].blocks * 128, 256) + align_up((size_t)infos[i].blocks * 64, 256);
-  return total;
+  size_t n_scans = 0, n_tables = 0;
+  for (int i = 0; i < n; ++i) {
+    total += align_up((size_t)infos[i].blocks * 128, 256) + align_up((size_t)infos[i].blocks * 64, 256);
+    n_scans += (size_t)infos[i].scans;
+    n_tables += (size_t)infos[i].huffman_tables;
+  }
+  return total + align_up(sizeof(jpg::Scan) * n_scans, 256) + align_up(sizeof(jpg::HuffDef) * n_tables, 256);
 }
 
 extern "C" int tise_jpeg_decode(tise_ctx* ctx, const uint8_t* h_files, const uint8_t* d_files, const int64_t* h_file_off,
@@ -140,14 +151,23 @@ extern "C" int tise_jpeg_decode(tise_ctx* ctx, const uint8_t* h_files, const uin
     return fail(ctx, TISE_ERR_INVALID, "tise_jpeg_decode: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   std::vector<JpegDesc> descs(n);
-  size_t off = align_up(sizeof(JpegDesc) * (size_t)n, 256);
+  std::vector<jpg::Scan> scans;
+  std::vector<jpg::HuffDef> tables;
+  jpg::Header* hdr = new jpg::Header;
   long long max_blocks = 0, max_pixels = 0;
   for (int i = 0; i < n; ++i) {
     JpegDesc& d = descs[i];
-    const int rc = jpg::parse(h_files + h_file_off[i], h_file_bytes[i], &d.h);
-    if (rc || !d.h.supported)
+    const int rc = jpg::parse(h_files + h_file_off[i], h_file_bytes[i], hdr);
+    if (rc || !hdr->supported) {
+      delete hdr;
       return fail(ctx, TISE_ERR_INVALID, "tise_jpeg_decode: file %d is %s (tise_jpeg_probe reports what the device decoder handles)",
                   i, rc ? "not a JPEG" : "a JPEG variant the device decoder does not handle");
+    }
+    d.h = *static_cast<const jpg::Core*>(hdr);
+    d.scan_base = (long long)scans.size();
+    d.table_base = (long long)tables.size();
+    scans.insert(scans.end(), hdr->scans, hdr->scans + hdr->nscans);
+    tables.insert(tables.end(), hdr->tables, hdr->tables + hdr->ntables);
     d.file_off = h_file_off[i];
     d.out_off = h_out_off[i];
     d.blocks = jpeg_blocks(d.h);
@@ -161,23 +181,38 @@ extern "C" int tise_jpeg_decode(tise_ctx* ctx, const uint8_t* h_files, const uin
         pi += nb * 64;
       }
     }
-    d.coef_off = (long long)off;
-    off += align_up((size_t)d.blocks * 128, 256);
-    d.plane_off = (long long)off;
-    off += align_up((size_t)d.blocks * 64, 256);
     max_blocks = d.blocks > max_blocks ? d.blocks : max_blocks;
     const long long px = (long long)d.h.width * d.h.height;
     max_pixels = px > max_pixels ? px : max_pixels;
   }
+  delete hdr;
+  // workspace: [descs][scan pool][Huffman-definition pool][per image: coefficients, planes]
+  size_t off = align_up(sizeof(JpegDesc) * (size_t)n, 256);
+  const size_t off_scans = off;
+  off += align_up(sizeof(jpg::Scan) * scans.size(), 256);
+  const size_t off_tables = off;
+  off += align_up(sizeof(jpg::HuffDef) * tables.size(), 256);
+  for (int i = 0; i < n; ++i) {
+    JpegDesc& d = descs[i];
+    d.coef_off = (long long)off;
+    off += align_up((size_t)d.blocks * 128, 256);
+    d.plane_off = (long long)off;
+    off += align_up((size_t)d.blocks * 64, 256);
+  }
   if (ws_bytes < off) return fail(ctx, TISE_ERR_WORKSPACE, "tise_jpeg_decode: workspace %zu < %zu bytes", ws_bytes, off);
   uint8_t* ws = (uint8_t*)d_ws;
   JpegDesc* d_descs = (JpegDesc*)ws;
+  jpg::Scan* d_scans = (jpg::Scan*)(ws + off_scans);
+  jpg::HuffDef* d_tables = (jpg::HuffDef*)(ws + off_tables);
+  // (pageable host memory: cudaMemcpyAsync has staged it before returning)
   TISE_CUDA(ctx, cudaMemcpyAsync(d_descs, descs.data(), sizeof(JpegDesc) * n, cudaMemcpyHostToDevice, st));
+  TISE_CUDA(ctx, cudaMemcpyAsync(d_scans, scans.data(), sizeof(jpg::Scan) * scans.size(), cudaMemcpyHostToDevice, st));
+  TISE_CUDA(ctx, cudaMemcpyAsync(d_tables, tables.data(), sizeof(jpg::HuffDef) * tables.size(), cudaMemcpyHostToDevice, st));
   TISE_CUDA(ctx, cudaMemsetAsync(d_status, 0xff, sizeof(int32_t) * n, st));
-  // (descs is pageable host memory: cudaMemcpyAsync has staged it before returning)
   for (int i0 = 0; i0 < n; i0 += 32768) {  // gridDim.y <= 65535
     const int cnt = n - i0 < 32768 ? n - i0 : 32768;
-    jpeg_entropy_kernel<<<cdiv(cnt, kJpegWarps), kJpegWarps * 32, 0, st>>>(d_descs + i0, cnt, d_files, ws, d_status + i0);
+    jpeg_entropy_kernel<<<cdiv(cnt, kJpegWarps), kJpegWarps * 32, 0, st>>>(d_descs + i0, cnt, d_scans, d_tables, d_files, ws,
+                                                                           d_status + i0);
     TISE_LAUNCH_CHECK(ctx);
     jpeg_idct_kernel<<<dim3((unsigned)cdiv(max_blocks, 256), cnt), 256, 0, st>>>(d_descs + i0, ws, d_status + i0);
     TISE_LAUNCH_CHECK(ctx);
