@@ -83,10 +83,10 @@ int tise_load_inception(tise_ctx* ctx, const tise_weight_desc* tensors, int n_te
  * (image_realism/FID/img_data.py:19-25, object_centric_inception_score.py:100-102) for PNG files:
  * zlib inflate, scanline unfiltering and conversion to RGB run on the device, one warp per image,
  * and the result is the packed uint8 HWC layout tise_resize_u8 / tise_crop_resize_u8 read.
- * Handled (non-interlaced): bit depth 8 for colour types 0 (grey), 2 (RGB), 3 (palette), 4 (grey+alpha), 6 (RGBA);
- * bit depth 16 for types 2, 4, 6 (the high byte, as Pillow keeps it); bit depths 1 / 2 / 4 for grey (scaled to
- * 0..255) and palette.  Alpha / tRNS are dropped exactly as convert("RGB") drops them.  Everything else
- * (16-bit grey, Adam7, JPEG) is reported with supported = 0 and stays with the caller. */
+ * Handled (plain or Adam7-interlaced): bit depth 8 for colour types 0 (grey), 2 (RGB), 3 (palette), 4 (grey+alpha),
+ * 6 (RGBA); bit depth 16 for types 2, 4, 6 (the high byte, as Pillow keeps it); bit depths 1 / 2 / 4 for grey
+ * (scaled to 0..255) and palette.  Alpha / tRNS are dropped exactly as convert("RGB") drops them.  16-bit grey
+ * ("I;16" in Pillow) is reported with supported = 0 and stays with the caller. */
 typedef struct {
   int32_t width, height;
   int32_t bit_depth, color_type, interlace;

@@ -38,14 +38,14 @@ int host_png_decode(const uint8_t* file, int64_t n, uint8_t* out, int64_t out_ca
   if (!h.supported) return -2;
   if ((int64_t)h.width * h.height * 3 > out_cap) return -3;
   const int stride = stride_of(h.width, h.color_type, h.bit_depth);
-  const uint32_t raw_bytes = (uint32_t)h.height * (uint32_t)(stride + 1);
+  const uint32_t raw_bytes = (uint32_t)raw_bytes_of(h.width, h.height, h.color_type, h.bit_depth, h.interlace);
   std::vector<uint8_t> raw(raw_bytes + 16);
   uint32_t out_len = 0, adler = 0;
   int st = host_inflate(stream.data(), (uint32_t)stream.size(), raw.data(), raw_bytes, &out_len, &adler);
   if (st) return st;
   if (out_len != raw_bytes) return kSizeMismatch;
   std::vector<uint8_t> rows(2 * (size_t)stride + 16);
-  return unfilter_to_rgb<1>(raw.data(), h.width, h.height, h.bit_depth, h.color_type,
+  return unfilter_to_rgb<1>(raw.data(), h.width, h.height, h.bit_depth, h.color_type, h.interlace,
                             h.plte_off >= 0 ? file + h.plte_off : nullptr, h.plte_entries, rows.data(), out, adler, 0);
 }
 

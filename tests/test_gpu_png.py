@@ -12,7 +12,7 @@ from oracle import restate
 from tise_toolbox_b200 import img_data, synth
 from tise_toolbox_b200.engine import ImageDecodeError
 
-from test_png_host import MODES, SIZES, exotic_pngs, png_bytes, smooth_image
+from test_png_host import MODES, SIZES, exotic_pngs, interlaced_pngs, png_bytes, smooth_image
 
 pytestmark = pytest.mark.gpu
 
@@ -40,6 +40,7 @@ def test_decode_mixed_batch_bit_exact(engine):
     blobs.append(jpg.getvalue())  # CMYK JPEG: decoded by PIL like the reference does, uploaded into the same pack
     blobs.append(png_bytes(Image.fromarray(rng.integers(0, 65536, (20, 20)).astype(np.uint16))))  # 16-bit: host
     exotic = [b for _, b in exotic_pngs(rng)]  # 16-bit RGB(A) / GA, 1 / 2 / 4-bit grey and palette, all filter types
+    exotic += [b for _, b in interlaced_pngs(rng, sizes=((1, 1), (3, 5), (9, 17), (33, 70)))]  # Adam7
     usable = []
     for b in exotic:
         try:

@@ -311,3 +311,52 @@ def test_png_16bit_and_subbyte_formats(host):
     g16 = rng.integers(0, 65536, (4, 4)).astype(">u2")
     blob = build_png(4, 4, 16, 0, [g16[y].tobytes() for y in range(4)], 2)
     assert _decode(host, blob)[0] == -2  # 16-bit grey ("I;16" saturates in convert("RGB")): host decode, reported as such
+
+
+def build_adam7_png(a, depth, ctype, row_bytes, bpp, plte=None):
+    """Interlaced (Adam7) PNG of array a: the seven sub-images are filtered and concatenated as the spec prescribes."""
+    import struct
+
+    h, w = a.shape[:2]
+    xst, yst = [0, 4, 0, 2, 0, 1, 0], [0, 0, 4, 0, 2, 0, 1]
+    xsp, ysp = [8, 8, 4, 4, 2, 2, 1], [8, 8, 8, 4, 4, 2, 2]
+    raw = b""
+    for p in range(7):
+        sub = a[yst[p]::ysp[p], xst[p]::xsp[p]]
+        if sub.shape[0] and sub.shape[1]:
+            raw += _filter_rows([row_bytes(sub[y]) for y in range(sub.shape[0])], bpp, (0, 1, 2, 3, 4))
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+
+    blob = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 1))
+    if plte is not None:
+        blob += chunk(b"PLTE", plte)
+    return blob + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b"")
+
+
+def interlaced_pngs(rng, sizes=((1, 1), (2, 2), (3, 5), (8, 8), (9, 17), (33, 70), (64, 48), (5, 1), (1, 9))):
+    def pack4(r):
+        bits = "".join(format(int(v), "04b") for v in r)
+        bits += "0" * ((-len(bits)) % 8)
+        return bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8))
+
+    out = []
+    for (h, w) in sizes:
+        a = smooth_image(rng, h, w, 4)
+        out.append(("adam7 rgb8 %dx%d" % (h, w), build_adam7_png(a[..., :3], 8, 2, lambda r: r.tobytes(), 3)))
+        out.append(("adam7 rgba8 %dx%d" % (h, w), build_adam7_png(a, 8, 6, lambda r: r.tobytes(), 4)))
+        out.append(("adam7 grey8 %dx%d" % (h, w), build_adam7_png(a[..., 0], 8, 0, lambda r: r.tobytes(), 1)))
+        out.append(("adam7 rgb16 %dx%d" % (h, w), build_adam7_png(a[..., :3].astype(">u2") * 257, 16, 2, lambda r: r.tobytes(), 6)))
+        out.append(("adam7 grey4 %dx%d" % (h, w), build_adam7_png(a[..., 0] >> 4, 4, 0, pack4, 1)))
+        pal = rng.integers(0, 256, 48, dtype=np.uint8).tobytes()
+        out.append(("adam7 pal4 %dx%d" % (h, w), build_adam7_png(a[..., 0] >> 4, 4, 3, pack4, 1, pal)))
+    return out
+
+
+def test_png_adam7_interlaced(host):
+    rng = np.random.default_rng(8)
+    for name, blob in interlaced_pngs(rng):
+        st, got = _decode(host, blob)
+        assert st == 0, (name, st)
+        assert np.array_equal(got, np.asarray(Image.open(io.BytesIO(blob)).convert("RGB"))), name

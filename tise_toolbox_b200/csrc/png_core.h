@@ -7,8 +7,8 @@
 // the library itself never decodes on the host.
 //
 // Replaces PIL.Image.open(f).convert("RGB") at image_realism/FID/img_data.py:21,
-// object_fidelity/O-IS/object_centric_inception_score.py:101 for PNG files (8-bit, non-interlaced,
-// colour types 0/2/3/4/6); anything else is reported as unsupported by png_parse and stays on the host.
+// object_fidelity/O-IS/object_centric_inception_score.py:101 for PNG files (every colour type; 8-bit, 16-bit except grey,
+// 1/2/4-bit grey and palette; plain or Adam7); anything else is reported as unsupported by parse() and stays on the host.
 #pragma once
 #include <stdint.h>
 
@@ -449,7 +449,7 @@ inline int parse(const uint8_t* f, int64_t n, Header* h, F on_idat) {
       h->interlace = f[data + 12];
       const bool fmt_ok = depth_supported(h->color_type, h->bit_depth);
       h->channels = fmt_ok ? filter_bpp_of(h->color_type, h->bit_depth) : 0;
-      h->supported = (fmt_ok && h->interlace == 0 && compression == 0 && filter == 0 &&
+      h->supported = (fmt_ok && h->interlace <= 1 && compression == 0 && filter == 0 &&
                       h->width > 0 && h->height > 0 && (int64_t)h->width * h->height <= (int64_t)1 << 28)
                          ? 1
                          : 0;
@@ -497,19 +497,21 @@ TISE_HD uint64_t lanes_sum(uint64_t v) {
 TISE_HD uint64_t lanes_sum(uint64_t v) { return v; }
 #endif
 
+// One pass of scanlines (the whole image, or one of the seven Adam7 sub-images): unfilter row by row and write pixel
+// (r, c) of the pass to image position (y0 + r * ys, x0 + c * xs).  A / B carry the Adler-32 state across passes.
 template <int LANES>
-TISE_HD int unfilter_to_rgb(const uint8_t* raw, int width, int height, int bit_depth, int color_type,
-                            const uint8_t* palette, int palette_entries, uint8_t* rows, uint8_t* out,
-                            uint32_t expect_adler, int lane) {
-  const int stride = stride_of(width, color_type, bit_depth), bpp = filter_bpp_of(color_type, bit_depth);
+TISE_HD int unfilter_pass(const uint8_t* raw, int pw, int ph, int bit_depth, int color_type, const uint8_t* palette,
+                          int palette_entries, uint8_t* rows, uint8_t* out, int out_width, int x0, int xs, int y0, int ys,
+                          uint64_t& A, uint64_t& B, int lane) {
+  const int stride = stride_of(pw, color_type, bit_depth), bpp = filter_bpp_of(color_type, bit_depth);
   const int samples = samples_of(color_type);
   uint8_t* cur = rows;
   uint8_t* prev = rows + stride;
+  TISE_SYNCWARP();
   for (int i = lane; i < stride; i += LANES) prev[i] = 0;
-  uint64_t A = 1, B = 0;  // Adler-32 state, reduced once per row
   const uint64_t m = (uint64_t)stride + 1;
   int status = kOk;
-  for (int y = 0; y < height; ++y) {
+  for (int y = 0; y < ph; ++y) {
     const uint8_t* src = raw + (size_t)y * (stride + 1);
     const int ft = src[0];
     uint64_t s1 = 0, s2 = 0;
@@ -574,32 +576,82 @@ TISE_HD int unfilter_to_rgb(const uint8_t* raw, int width, int height, int bit_d
       }
     }
     TISE_SYNCWARP();
-    uint8_t* o = out + (size_t)y * width * 3;
-    if (color_type == 2 && bit_depth == 8) {
+    uint8_t* o = out + ((size_t)(y0 + y * ys) * out_width + x0) * 3;
+    const int ostep = xs * 3;  // bytes between consecutive pixels of this pass in the output row
+    if (color_type == 2 && bit_depth == 8 && xs == 1) {
       for (int i = lane; i < stride; i += LANES) o[i] = cur[i];
     } else if (bit_depth < 8) {  // 1 / 2 / 4-bit grey (scaled to 0..255) or palette indices, packed MSB first
       const int mask = (1 << bit_depth) - 1, mul = 255 / mask;
-      for (int i = lane; i < width * 3; i += LANES) {
+      for (int i = lane; i < pw * 3; i += LANES) {
         const int p = i / 3, k = i - p * 3, bit = p * bit_depth;
         const int v = (cur[bit >> 3] >> (8 - bit_depth - (bit & 7))) & mask;
-        o[i] = color_type == 3 ? (v < palette_entries ? palette[v * 3 + k] : (uint8_t)0) : (uint8_t)(v * mul);
+        o[p * ostep + k] = color_type == 3 ? (v < palette_entries ? palette[v * 3 + k] : (uint8_t)0) : (uint8_t)(v * mul);
       }
     } else if (color_type == 3) {
-      for (int i = lane; i < width * 3; i += LANES) {
+      for (int i = lane; i < pw * 3; i += LANES) {
         const int p = i / 3, k = i - p * 3, idx = cur[p];
-        o[i] = idx < palette_entries ? palette[idx * 3 + k] : (uint8_t)0;
+        o[p * ostep + k] = idx < palette_entries ? palette[idx * 3 + k] : (uint8_t)0;
       }
     } else {  // grey (0), grey + alpha (4): replicate; RGB(A) (2, 6): first three samples; 16-bit: the high byte --
               // what Pillow's decoder + convert("RGB") produce
       const int sb = bit_depth >> 3;  // bytes per sample
-      for (int i = lane; i < width * 3; i += LANES) {
+      for (int i = lane; i < pw * 3; i += LANES) {
         const int p = i / 3, k = i - p * 3;
-        o[i] = cur[(p * samples + (samples >= 3 ? k : 0)) * sb];
+        o[p * ostep + k] = cur[(p * samples + (samples >= 3 ? k : 0)) * sb];
       }
     }
     uint8_t* t = cur;
     cur = prev;
     prev = t;
+  }
+  return status;
+}
+
+// Adam7 (PNG spec 8.2): pass p holds the pixels (ystart + r * ystep, xstart + c * xstep)
+TISE_HD void adam7_pass(int p, int width, int height, int* x0, int* xs, int* y0, int* ys, int* pw, int* ph) {
+  const int xst[7] = {0, 4, 0, 2, 0, 1, 0}, yst[7] = {0, 0, 4, 0, 2, 0, 1};
+  const int xsp[7] = {8, 8, 4, 4, 2, 2, 1}, ysp[7] = {8, 8, 8, 4, 4, 2, 2};
+  *x0 = xst[p];
+  *y0 = yst[p];
+  *xs = xsp[p];
+  *ys = ysp[p];
+  *pw = (width - xst[p] + xsp[p] - 1) / xsp[p];
+  *ph = (height - yst[p] + ysp[p] - 1) / ysp[p];
+  if (*pw < 0) *pw = 0;
+  if (*ph < 0) *ph = 0;
+}
+
+// bytes of the inflated stream: filter byte + scanline per row, per pass when interlaced (empty passes are absent)
+TISE_HD int64_t raw_bytes_of(int width, int height, int color_type, int bit_depth, int interlace) {
+  if (!interlace) return (int64_t)height * (1 + (int64_t)stride_of(width, color_type, bit_depth));
+  int64_t total = 0;
+  for (int p = 0; p < 7; ++p) {
+    int x0, xs, y0, ys, pw, ph;
+    adam7_pass(p, width, height, &x0, &xs, &y0, &ys, &pw, &ph);
+    if (pw > 0 && ph > 0) total += (int64_t)ph * (1 + (int64_t)stride_of(pw, color_type, bit_depth));
+  }
+  return total;
+}
+
+template <int LANES>
+TISE_HD int unfilter_to_rgb(const uint8_t* raw, int width, int height, int bit_depth, int color_type, int interlace,
+                            const uint8_t* palette, int palette_entries, uint8_t* rows, uint8_t* out,
+                            uint32_t expect_adler, int lane) {
+  uint64_t A = 1, B = 0;  // Adler-32 state, reduced once per row
+  int status = kOk;
+  if (!interlace) {
+    status = unfilter_pass<LANES>(raw, width, height, bit_depth, color_type, palette, palette_entries, rows, out, width, 0, 1, 0,
+                                  1, A, B, lane);
+  } else {
+    for (int p = 0; p < 7; ++p) {
+      int x0, xs, y0, ys, pw, ph;
+      adam7_pass(p, width, height, &x0, &xs, &y0, &ys, &pw, &ph);
+      if (pw <= 0 || ph <= 0) continue;
+      const int e = unfilter_pass<LANES>(raw, pw, ph, bit_depth, color_type, palette, palette_entries, rows, out, width, x0, xs,
+                                         y0, ys, A, B, lane);
+      if (e) status = e;
+      raw += (size_t)ph * (1 + (size_t)stride_of(pw, color_type, bit_depth));
+    }
   }
   if (status) return status;
   const uint32_t adler = (uint32_t)((B << 16) | A);

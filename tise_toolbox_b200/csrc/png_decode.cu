@@ -28,7 +28,7 @@ struct PngDesc {
   long long out_off;     // byte offset of the RGB8 image in d_out
   long long plte_off;    // absolute byte offset of the PLTE data in d_files, -1: none
   int stream_bytes, raw_bytes;
-  int width, height, bit_depth, color_type, plte_entries;
+  int width, height, bit_depth, color_type, plte_entries, interlace, pad;
   unsigned adler;        // written by the inflate kernel
 };
 struct PngSeg {
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(32) png_unfilter_kernel(const PngDesc* __restr
   const int img = blockIdx.x, lane = threadIdx.x;
   if (status[img] != png::kOk) return;  // inflate failed: leave its status
   const PngDesc d = descs[img];
-  const int st = png::unfilter_to_rgb<32>(ws + d.raw_off, d.width, d.height, d.bit_depth, d.color_type,
+  const int st = png::unfilter_to_rgb<32>(ws + d.raw_off, d.width, d.height, d.bit_depth, d.color_type, d.interlace,
                                           d.plte_off >= 0 ? files + d.plte_off : nullptr, d.plte_entries, rows,
                                           out + d.out_off, d.adler, lane);
   if (lane == 0 && st != png::kOk) status[img] = st;
@@ -151,7 +151,7 @@ extern "C" size_t tise_png_decode_workspace_bytes(const tise_png_info* infos, in
   for (int i = 0; i < n; ++i) {
     n_seg += infos[i].n_idat;
     sb += pad_stream(infos[i].idat_bytes);
-    rb += pad_raw((long long)infos[i].height * (1 + (long long)png::stride_of(infos[i].width, infos[i].color_type, infos[i].bit_depth)));
+    rb += pad_raw(png::raw_bytes_of(infos[i].width, infos[i].height, infos[i].color_type, infos[i].bit_depth, infos[i].interlace));
   }
   return png_ws_layout(n, n_seg, sb, rb).total;
 }
@@ -194,7 +194,7 @@ extern "C" int tise_png_decode(tise_ctx* ctx, const uint8_t* h_files, const uint
     d.stream_bytes = (int)h.idat_bytes;
     d.raw_off = raw_total;
     const int stride = png::stride_of(h.width, h.color_type, h.bit_depth);
-    const long long raw = (long long)h.height * (1 + (long long)stride);
+    const long long raw = png::raw_bytes_of(h.width, h.height, h.color_type, h.bit_depth, h.interlace);
     if (raw > 0x7fffffffLL) return fail(ctx, TISE_ERR_INVALID, "tise_png_decode: file %d is too large", i);
     d.raw_bytes = (int)raw;
     d.out_off = h_out_off[i];
@@ -203,6 +203,8 @@ extern "C" int tise_png_decode(tise_ctx* ctx, const uint8_t* h_files, const uint
     d.width = h.width;
     d.height = h.height;
     d.bit_depth = h.bit_depth;
+    d.interlace = h.interlace;
+    d.pad = 0;
     d.color_type = h.color_type;
     d.adler = 0;
     stream_total += pad_stream(h.idat_bytes);
