@@ -158,6 +158,13 @@ int tise_crop_resize_u8(tise_ctx* ctx, const uint8_t* d_imgs, const int64_t* h_o
                         const int32_t* h_box, int n, uint8_t* d_out, void* d_ws, size_t ws_bytes,
                         tise_stream stream);
 
+/* Float bilinear resampling of n x c x h x w (contiguous NCHW) to n x c x 299 x 299 for callers that hand the
+ * reference-facing modules float tensors of another size: F.upsample(..., align_corners=True) at
+ * image_realism/FID/inception.py:117-118 (align_corners = 1) and nn.Upsample(size=(299, 299), mode="bilinear") at
+ * object_centric_inception_score.py:49 (align_corners = 0).  Same source-index arithmetic as ATen (float). */
+int tise_upsample_bilinear_f32(tise_ctx* ctx, const float* d_in, int n, int c, int h, int w, int align_corners,
+                               float* d_out, tise_stream stream);
+
 /* ---- A3/A4: uint8 level -> network input ------------------------------------------------ */
 /* lut[c*256 + v] = float fed to Conv2d_1a_3x3 for channel c and uint8 level v; covers ToTensor
  * (fid_score.py:211) + the affine at image_realism/FID/inception.py:120-124, or

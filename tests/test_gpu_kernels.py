@@ -177,3 +177,19 @@ def test_inception_score_partials(engine, variant, n, c):
     rmean, rstd = _is_reference(logits, variant, 10)
     assert abs(mean - rmean) <= 1e-5 * rmean, (mean, rmean)
     assert abs(std - rstd) <= 1e-4 * max(rstd, 1e-3), (std, rstd)
+
+
+@pytest.mark.parametrize("align", [True, False])
+def test_upsample_float_matches_aten(engine, align):
+    """tise_upsample_bilinear_f32 vs torch's CPU upsample_bilinear2d (the op behind F.upsample / nn.Upsample in the
+    reference, inception.py:117-118 align_corners=True, object_centric_inception_score.py:49 align_corners=False).
+    Tolerance: one float32 rounding of the blend (ATen may contract the products into FMAs), inputs in [0, 1]."""
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(3)
+    for (h, w) in [(64, 48), (300, 511), (299, 299), (1, 1), (17, 333), (256, 256)]:
+        x = torch.rand(2, 3, h, w, generator=g)
+        ref = F.interpolate(x, size=(299, 299), mode="bilinear", align_corners=align)
+        got = engine.upsample_float(x, align_corners=align).cpu()
+        assert float((got - ref).abs().max()) <= 2e-6, (h, w, align)
+    assert tuple(engine.upsample_float(torch.empty(0, 3, 8, 8), align_corners=align).shape) == (0, 3, 299, 299)

@@ -71,3 +71,18 @@ def test_micro_batching_is_invisible(engine, batch):
     finally:
         engine.micro_batch = keep
     assert np.array_equal(full, part)
+
+
+def test_forward_resizes_float_inputs_of_other_sizes(state_dict):
+    """Quirk 3 of SURVEY.md §9: a caller that bypasses the Dataset and feeds non-299 float tensors gets the reference's
+    F.upsample(align_corners=True) (inception.py:117-118) -- here a libtise kernel -- before the trunk."""
+    import torch.nn.functional as F
+
+    from tise_toolbox_b200.inception import InceptionV3
+
+    model = InceptionV3([3], state_dict=state_dict, micro_batch=8)
+    x = synth.images(1, 0, 0, 4).permute(0, 3, 1, 2).float().div(255)  # 256 x 256 floats in [0, 1]
+    a = model(x)[0].reshape(4, -1).cpu().numpy()
+    b = model(F.interpolate(x, size=(299, 299), mode="bilinear", align_corners=True))[0].reshape(4, -1).cpu().numpy()
+    assert a.shape == (4, 2048)
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) <= 1e-4

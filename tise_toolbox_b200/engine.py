@@ -428,6 +428,18 @@ class Engine:
                                                      _stream()))
         return out
 
+    def upsample_float(self, x: torch.Tensor, align_corners: bool) -> torch.Tensor:
+        """float32 [n, c, h, w] -> [n, c, 299, 299], bilinear (the reference's F.upsample / nn.Upsample on float
+        inputs of another size, inception.py:117-118 / object_centric_inception_score.py:49)."""
+        assert x.dtype == torch.float32 and x.dim() == 4
+        x = x.to(self.device).contiguous()
+        n, c, h, w = (int(v) for v in x.shape)
+        out = torch.empty((n, c, 299, 299), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.tise_upsample_bilinear_f32(self.ctx, x.data_ptr(), n, c, h, w, int(bool(align_corners)),
+                                                            out.data_ptr(), _stream()))
+        return out
+
     # ------------------------------------------------------------------ A5 trunk
     def _trunk(self, u8: Optional[torch.Tensor], f32: Optional[torch.Tensor], n: int, tap: int, feat: torch.Tensor):
         need = int(self.lib.tise_inception_workspace_bytes(self.ctx, self.micro_batch))

@@ -13,7 +13,6 @@ import os
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .engine import Engine, PackedImages
 
@@ -64,7 +63,7 @@ class InceptionV3(nn.Module):
         x = inp.to(self.engine.device, torch.float32)
         if self.resize_input and tuple(x.shape[2:]) != (299, 299):
             # identity at 299x299 (the Dataset already resized with Pillow); live only for odd callers
-            x = F.interpolate(x, size=(299, 299), mode="bilinear", align_corners=True)
+            x = self.engine.upsample_float(x, align_corners=True)
         if self.normalize_input:
             x = x.clone()  # inception.py:119-124, torchvision's transform_input applied to [0,1] data
             x[:, 0] = x[:, 0] * (0.229 / 0.5) + (0.485 - 0.5) / 0.5

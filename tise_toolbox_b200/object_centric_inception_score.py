@@ -11,7 +11,6 @@ import numpy as np
 import torch
 import torch.utils.data
 from PIL import Image
-from torch.nn import functional as F
 
 from . import inception_score as _is
 from .engine import Engine, ISPartials
@@ -51,7 +50,7 @@ def inception_score(imgs, cuda=True, batch_size=32, resize=False, splits=1, stat
         else:
             x = batch.to(engine.device, torch.float32)
             if resize:  # nn.Upsample(size=(299, 299), mode="bilinear"), :49
-                x = F.interpolate(x, size=(299, 299), mode="bilinear")
+                x = engine.upsample_float(x, align_corners=False)
             feat = engine.features_from_float(x)
         logits = engine.logits(feat, use_bias=True)
         _is.update_from_logits(engine, parts, logits, "ois", N, start)
