@@ -183,7 +183,9 @@ def test_inception_score_partials(engine, variant, n, c):
 def test_upsample_float_matches_aten(engine, align):
     """tise_upsample_bilinear_f32 vs torch's CPU upsample_bilinear2d (the op behind F.upsample / nn.Upsample in the
     reference, inception.py:117-118 align_corners=True, object_centric_inception_score.py:49 align_corners=False).
-    Tolerance: one float32 rounding of the blend (ATen may contract the products into FMAs), inputs in [0, 1]."""
+    Tolerance, inputs in [0, 1]: align_corners=True agrees to one float32 rounding (1.2e-7 measured); for
+    align_corners=False ATen's CPU kernel rounds the source index / weights in a slightly different sequence than its CUDA
+    kernel, whose float arithmetic this kernel follows: up to 3.4e-6 on these sizes, far below anything the score sees."""
     import torch.nn.functional as F
 
     g = torch.Generator().manual_seed(3)
@@ -191,5 +193,5 @@ def test_upsample_float_matches_aten(engine, align):
         x = torch.rand(2, 3, h, w, generator=g)
         ref = F.interpolate(x, size=(299, 299), mode="bilinear", align_corners=align)
         got = engine.upsample_float(x, align_corners=align).cpu()
-        assert float((got - ref).abs().max()) <= 2e-6, (h, w, align)
+        assert float((got - ref).abs().max()) <= (5e-7 if align else 1e-5), (h, w, align)
     assert tuple(engine.upsample_float(torch.empty(0, 3, 8, 8), align_corners=align).shape) == (0, 3, 299, 299)
