@@ -207,3 +207,25 @@ def test_ragged_crops_path(state_dict):
 def test_empty_batch(engine):
     f = engine.features(torch.empty((0, 64, 64, 3), dtype=torch.uint8, device="cuda"))
     assert tuple(f.shape) == (0, 2048)
+
+
+def test_ois_folder_path_on_device_matches_float_path(tmp_path):
+    """O-IS through a folder of crop files: IgnoreLabelDataset(raw_u8=True) -> DeviceImageLoader (PNG decode, resize and
+    normalisation on the GPU, whole decode groups) against the reference's own pipeline on the same files
+    (IgnoreLabelDataset: PIL resize + ToTensor + Normalize on the host, object_centric_inception_score.py:84-104)."""
+    from PIL import Image
+
+    from tise_toolbox_b200 import object_centric_inception_score as ois
+
+    sd80 = synth.inception_state_dict(3, num_classes=80)
+    head = np.load(os.path.join(GOLD, "ois_head.npy"))
+    sd80["fc.weight"] = torch.from_numpy(head[:, :2048].copy())
+    sd80["fc.bias"] = torch.from_numpy(head[:, 2048].copy())
+    sizes = synth.crop_sizes(8, 0, 26, lo=24, hi=320)
+    for i, (h, w) in enumerate(sizes):
+        Image.fromarray(synth.images(5, i % 2, i, 1, h, w)[0].numpy()).save(str(tmp_path / ("crop_%03d.png" % i)))
+    eng = Engine(sd80, device="cuda:0", variant="ois", micro_batch=16)
+    dev = ois.inception_score(ois.IgnoreLabelDataset(str(tmp_path), raw_u8=True), batch_size=8, splits=2, engine=eng)
+    ref = ois.inception_score(ois.IgnoreLabelDataset(str(tmp_path)), batch_size=8, splits=2, engine=eng)
+    assert ref[0] > 1.2, ref
+    assert abs(dev[0] - ref[0]) <= 1e-3 * ref[0] and abs(dev[1] - ref[1]) <= 2e-2 * ref[1] + 1e-4, (dev, ref)
