@@ -12,4 +12,8 @@ path, so the oracle is pinned by (1) ``oracle/reference_shim.py`` -- the referen
 inputs by ``tools/make_golden.py``, which also writes the committed fixtures under
 ``tests/golden/``; (2) the one transferable known-answer of the reference's result files,
 ``FID(X, X) ~ 0`` (``object_fidelity/results/O-FID/real_images.txt``).
+For the rows added around the path the checker is the routine the reference itself calls: Pillow's
+PNG / JPEG decoders and ``Image.crop`` (bit-exact comparisons in ``tests/``), and the reference's own
+``temperature_scaling.py`` / ``ranking_score.py`` run by ``tools/make_golden_calibration.py`` into
+``tests/golden/calibration.json``.
 """

@@ -171,3 +171,39 @@ def test_shard_format_round_trip_and_validation(tmp_path):
         f.write(b"NOTASHARD" + blob[9:])
     with pytest.raises(ValueError):
         shards.read_index(str(tmp_path / "magic.shard"))
+
+
+def test_device_image_loader_grouping_with_a_stub_engine(tmp_path):
+    """Host logic of img_data.DeviceImageLoader without a GPU: order, drop_last, decode groups that are whole numbers of
+    consumer batches, batch slices of a group."""
+    from tise_toolbox_b200 import img_data
+    from tise_toolbox_b200.engine import PackedImages
+
+    class StubEngine:
+        def __init__(self):
+            self.staged_groups = []
+
+        def stage_files(self, paths, pool=None):
+            self.staged_groups.append(list(paths))
+            return {"paths": list(paths)}
+
+        def decode_staged(self, staged):
+            n = len(staged["paths"])
+            ids = np.array([int(os.path.basename(p)[1:-4]) for p in staged["paths"]], dtype=np.int64)
+            return PackedImages(torch.zeros(16, dtype=torch.uint8), ids * 48, np.tile(np.array([[4, 4]], np.int32), (n, 1)))
+
+    names = [str(tmp_path / ("f%04d.png" % i)) for i in range(103)]
+    eng = StubEngine()
+    loader = img_data.DeviceImageLoader(names, eng, batch_size=10, drop_last=True, decode_batch=35)
+    assert len(loader) == 10 and loader.group == 30
+    seen = []
+    for batch in loader:
+        assert len(batch) == 10
+        seen += (batch.offsets // 48).tolist()
+    assert seen == list(range(100))  # the last 3 files are dropped, order kept
+    assert [len(g) for g in eng.staged_groups] == [30, 30, 30, 10]
+    eng = StubEngine()
+    loader = img_data.DeviceImageLoader(names, eng, batch_size=10, drop_last=False, decode_batch=1000)
+    sizes = [len(b) for b in loader]
+    assert sizes == [10] * 10 + [3] and len(loader) == 11
+    assert sum(len(g) for g in img_data.DeviceImageLoader(names[:7], StubEngine(), 10, drop_last=True).groups()) == 0
