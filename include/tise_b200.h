@@ -60,6 +60,9 @@ const char* tise_last_error(const tise_ctx* ctx);
 /* conv engine (default TISE_CONV_UMMA) and operand passes: 2 = fp16 activations x (hi+lo) fp16
  * weights, fp32 TMEM accumulation (default; FID within 1e-4 of fp32), 1 = single fp16 pass. */
 int tise_set_conv_mode(tise_ctx* ctx, int impl, int passes);
+/* mixed operand policy: with passes = 2, convolutions whose INPUT map is at most `single_pass_max_hw`
+ * pixels high (0 = none, the default) skip the W_lo pass.  Measured trade-off: DESIGN.md section 2. */
+int tise_set_pass_policy(tise_ctx* ctx, int single_pass_max_hw);
 
 /* ---- weights -------------------------------------------------------------------------- */
 /* One tensor of a torchvision Inception3 state_dict (fp32, host, contiguous), e.g.

@@ -1,7 +1,8 @@
 """Runs the reference's OWN source files (unmodified, from /root/reference) on the CPU.
 
-TEST INFRASTRUCTURE ONLY, and only usable in the build container: /root/reference does not exist on
-the GPU box.  ``tools/make_golden.py`` uses this module to (a) validate ``oracle/restate.py`` against
+TEST INFRASTRUCTURE ONLY.  In the build container the files are read from /root/reference; on the GPU
+box (where that tree does not exist) from the unmodified copies under git-ignored ``oracle/_ref/``
+(``oracle/build_ref.py``, run by ``__graft_entry__.build()``).  ``tools/make_golden.py`` uses this module to (a) validate ``oracle/restate.py`` against
 the real reference and (b) write the committed fixtures under ``tests/golden/``.
 
 Shims -- none of them touches the arithmetic of the path:
@@ -20,7 +21,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("TISE_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    """The reference tree: $TISE_REFERENCE_ROOT, else /root/reference (build container), else the unmodified copies
+    of the path's nine files that ``oracle/build_ref.py`` placed under git-ignored ``oracle/_ref/`` (GPU box)."""
+    for cand in (os.environ.get("TISE_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "image_realism", "FID")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:

@@ -6,6 +6,7 @@ import re
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 from PIL import Image
@@ -46,3 +47,31 @@ def test_fid_cli_two_ranks_equals_one(tmp_path):
     assert abs(a - b) <= 1e-6 * abs(a), (a, b)
     assert open(str(tmp_path / "fid.txt")).read() == "FID: %s" % re.findall(r"^FID: (\S+)$", two.stdout, flags=re.M)[-1]
     assert two.stdout.count("FID: ") == 1  # rank 0 alone reports
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_engines_on_two_devices_in_one_process():
+    """Kernel attributes (opt-in shared memory) are per device and tise_ctx_create must not move the caller's current
+    device: a second Engine on cuda:1 in the same process gives the same features as the one on cuda:0."""
+    from tise_toolbox_b200.engine import Engine, Moments
+
+    sd = synth.inception_state_dict(0, num_classes=1000)
+    imgs = synth.images(1, 0, 0, 24)
+    torch.cuda.set_device(0)
+    e0 = Engine(sd, device="cuda:0", micro_batch=16)
+    f0 = e0.features(imgs.to("cuda:0"))
+    e1 = Engine(sd, device="cuda:1", micro_batch=16)
+    assert torch.cuda.current_device() == 0  # ctx creation left torch's device alone
+    f1 = e1.features(imgs.to("cuda:1"))
+    assert torch.equal(f0.cpu(), f1.cpu())
+    st = []
+    for e, f in ((e0, f0), (e1, f1)):
+        m = Moments(e)
+        m.update(f)
+        st.append(m.finalize())
+    assert np.array_equal(st[0][1], st[1][1])
+    v1, _ = e1.frechet(st[1][0], st[1][1], st[1][0] + 0.01, st[1][1] * 1.1)  # 64 KB dynamic smem kernels on device 1
+    v0, _ = e0.frechet(st[0][0], st[0][1], st[0][0] + 0.01, st[0][1] * 1.1)
+    assert v0 == v1
+    e1.close()
+    assert torch.cuda.current_device() == 0

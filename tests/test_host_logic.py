@@ -104,6 +104,40 @@ def test_two_rank_moment_exchange_over_gloo(tmp_path):
     assert np.allclose(r["sigma"].numpy(), np.cov(x, rowvar=False), rtol=1e-9, atol=1e-13)
 
 
+def _pack_worker(rank, world, port, out):
+    """StatsPack.allreduce over gloo with a stub engine (device = cpu): the packing / counter round trip is host logic."""
+    from types import SimpleNamespace
+
+    from tise_toolbox_b200.engine import StatsPack
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = SimpleNamespace(device=torch.device("cpu"))
+    pack = StatsPack(eng, d=8, is_classes=5, is_splits=3)
+    assert pack.buf.numel() == 1 + 8 + 64 + 3 + 15 + 3 + 1
+    pack.moments.count = 10 + rank
+    pack.moments.sum.add_(float(rank + 1))
+    pack.moments.sxx.add_(0.5)
+    pack.parts.f.add_(float(rank + 2))
+    pack.parts.i.add_(torch.tensor([1, 2, 3, rank], dtype=torch.int64) * (rank + 1))
+    pack.allreduce()
+    if rank == 0:
+        torch.save({"count": pack.moments.count, "sum": pack.moments.sum.clone(), "sxx": pack.moments.sxx.clone(),
+                    "f": pack.parts.f.clone(), "i": pack.parts.i.clone()}, out)
+    dist.destroy_process_group()
+
+
+def test_stats_pack_single_allreduce_over_gloo(tmp_path):
+    out = str(tmp_path / "p.pt")
+    mp.spawn(_pack_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["count"] == 21
+    assert torch.equal(r["sum"], torch.full((8,), 3.0, dtype=torch.float64))
+    assert torch.equal(r["sxx"], torch.full((64,), 1.0, dtype=torch.float64))
+    assert torch.equal(r["f"], torch.full((18,), 5.0, dtype=torch.float64))
+    assert r["i"].tolist() == [3, 6, 9, 2]
+
+
 def test_result_file_formats(tmp_path):
     assert pipeline.format_result("fid", 26.581254719518654) == "FID: 26.581254719518654"
     assert pipeline.format_result("ofid", -2.6147972675971687e-12) == "O-FID: -2.6147972675971687e-12"
@@ -171,6 +205,15 @@ def test_shard_format_round_trip_and_validation(tmp_path):
         f.write(b"NOTASHARD" + blob[9:])
     with pytest.raises(ValueError):
         shards.read_index(str(tmp_path / "magic.shard"))
+    # entries out of file order (index rows 0 and 2 swapped): every entry is in bounds, but the loader's span
+    # arithmetic would address outside the uploaded bytes
+    swapped = bytearray(blob)
+    e0, e2 = bytes(swapped[16:32]), bytes(swapped[48:64])
+    swapped[16:32], swapped[48:64] = e2, e0
+    with open(str(tmp_path / "order.shard"), "wb") as f:
+        f.write(swapped)
+    with pytest.raises(ValueError):
+        shards.read_index(str(tmp_path / "order.shard"))
 
 
 def test_device_image_loader_grouping_with_a_stub_engine(tmp_path):

@@ -31,6 +31,7 @@ extern "C" int tise_ctx_create(int device, tise_ctx** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TISE_ERR_CUDA;
   if (prop.major != 10) return TISE_ERR_CUDA;  // sm_100a only: no other code path exists in this library
+  DeviceRestore restore;  // the caller's current device is left as it was
   if (cudaSetDevice(device) != cudaSuccess) return TISE_ERR_CUDA;
   tise_ctx* ctx = new tise_ctx();
   ctx->device = device;
@@ -46,6 +47,7 @@ extern "C" int tise_ctx_create(int device, tise_ctx** out) {
 
 extern "C" void tise_ctx_destroy(tise_ctx* ctx) {
   if (!ctx) return;
+  DeviceRestore restore;
   cudaSetDevice(ctx->device);
   net_free(ctx);
   if (ctx->d_lut) cudaFree(ctx->d_lut);
@@ -62,6 +64,13 @@ extern "C" int tise_set_conv_mode(tise_ctx* ctx, int impl, int passes) {
     return fail(ctx, TISE_ERR_INVALID, "tise_set_conv_mode: impl %d passes %d", impl, passes);
   ctx->conv_impl = impl;
   ctx->passes = passes;
+  return TISE_OK;
+}
+
+extern "C" int tise_set_pass_policy(tise_ctx* ctx, int single_pass_max_hw) {
+  if (!ctx) return TISE_ERR_INVALID;
+  if (single_pass_max_hw < 0) return fail(ctx, TISE_ERR_INVALID, "tise_set_pass_policy: %d", single_pass_max_hw);
+  ctx->pass1_max_hw = single_pass_max_hw;
   return TISE_OK;
 }
 

@@ -28,6 +28,7 @@ struct tise_ctx {
   long long launches = 0;
   int conv_impl = TISE_CONV_UMMA;
   int passes = 2;
+  int pass1_max_hw = 0;  // layers whose input map is at most this many pixels high run one MMA pass (0: none)
   float* d_lut = nullptr;  // 768 floats
   bool lut_set = false;
   tise::Net* net = nullptr;
@@ -62,6 +63,28 @@ int fail(tise_ctx* ctx, int status, const char* fmt, ...);
       return tise::fail(ctx, TISE_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__,         \
                         __LINE__, cudaGetErrorString(e__));                                        \
   } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: a process that drives several
+// GPUs (one tise_ctx each) must opt in on every one of them.  Each launch site keeps one of these instead of a bool.
+struct PerDeviceFlag {
+  int value[64] = {0};
+  bool is(const tise_ctx* ctx, int want) const { return ctx->device >= 0 && ctx->device < 64 && value[ctx->device] == want; }
+  void set(const tise_ctx* ctx, int v) {
+    if (ctx->device >= 0 && ctx->device < 64) value[ctx->device] = v;
+  }
+};
+
+// Saves the caller's current device and restores it on scope exit (tise_ctx_create / tise_ctx_destroy select the
+// context's device; the caller -- e.g. torch -- must not see its current device change behind its back).
+struct DeviceRestore {
+  int prev = -1;
+  DeviceRestore() {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+  }
+  ~DeviceRestore() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -354,12 +354,12 @@ int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const
   p.num_tiles = cdiv(p.total, kBlockM);
   p.relu = a.relu;
 
-  static int configured = 0;
+  static PerDeviceFlag configured;
   const int smem_limit = ctx->smem_optin > 0 ? ctx->smem_optin : 232448;
-  if (configured != smem_limit) {
+  if (!configured.is(ctx, smem_limit)) {
     TISE_CUDA(ctx, cudaFuncSetAttribute(conv_flat_kernel<3, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
     TISE_CUDA(ctx, cudaFuncSetAttribute(conv_flat_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
-    configured = smem_limit;
+    configured.set(ctx, smem_limit);
   }
   const int fixed = 1024 + (int)align_up((size_t)L.R * L.S * p.wtile_bytes, 1024) + 4 * kFlatEpiBuf + 2 * 128 * 4 +
                     8 * (2 * kFlatMaxStages + 6) + 16;

@@ -716,16 +716,16 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
     p.dbg_out = d_dbg;
   }
 
-  static int configured_smem = 0;
+  static PerDeviceFlag configured_smem;
   const int smem_limit = ctx->smem_optin > 0 ? ctx->smem_optin : 232448;
-  if (configured_smem != smem_limit) {
+  if (!configured_smem.is(ctx, smem_limit)) {
     const void* kernels[8] = {(const void*)conv_umma_kernel<false, false, false>, (const void*)conv_umma_kernel<true, false, false>,
                               (const void*)conv_umma_kernel<false, true, false>,  (const void*)conv_umma_kernel<true, true, false>,
                               (const void*)conv_umma_kernel<false, false, true>,  (const void*)conv_umma_kernel<true, false, true>,
                               (const void*)conv_umma_kernel<false, true, true>,   (const void*)conv_umma_kernel<true, true, true>};
     for (int i = 0; i < 8; ++i)
       TISE_CUDA(ctx, cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
-    configured_smem = smem_limit;
+    configured_smem.set(ctx, smem_limit);
   }
   const int reserve = 1024 /*alignment*/ + 4 * kEpiBufBytes + 2 * kMaxCout * 4 + 8 * (2 * kMaxStages + 4) + 16 + 16 * kMaxKb;
   const int budget = smem_limit - reserve;

@@ -756,12 +756,12 @@ extern "C" int tise_frechet(tise_ctx* ctx, const double* d_mu1, const double* d_
   if (ws_bytes < fr_layout(d).total)
     return fail(ctx, TISE_ERR_WORKSPACE, "tise_frechet: workspace %zu < %zu bytes", ws_bytes, fr_layout(d).total);
   cudaStream_t st = (cudaStream_t)stream;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  if (!configured.is(ctx, 1)) {
     TISE_CUDA(ctx, cudaFuncSetAttribute(tri_rank2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
     TISE_CUDA(ctx, cudaFuncSetAttribute(tri_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 32));
     TISE_CUDA(ctx, cudaFuncSetAttribute(sturm_sqrt_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
-    configured = true;
+    configured.set(ctx, 1);
   }
   double scal[FR_NSLOTS];
   int flags = 0;

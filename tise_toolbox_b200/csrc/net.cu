@@ -626,7 +626,8 @@ int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, i
       case STEP_CONV:
         if (ctx->conv_impl == TISE_CONV_UMMA) {
           if (!s.umma.valid && (rc = build_umma_plan(ctx, *s.layer, s.conv, &s.umma))) break;
-          rc = launch_conv_umma(ctx, *s.layer, s.conv, s.umma, ctx->passes, st);
+          rc = launch_conv_umma(ctx, *s.layer, s.conv, s.umma,
+                                (ctx->passes == 2 && s.conv.h <= ctx->pass1_max_hw) ? 1 : ctx->passes, st);
         } else {
           rc = launch_conv_simt(ctx, *s.layer, s.conv, st);
         }

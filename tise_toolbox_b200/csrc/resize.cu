@@ -332,10 +332,10 @@ static int resize_impl(tise_ctx* ctx, const char* who, const uint8_t* d_imgs, co
     static int fused_env = -1;
     if (fused_env < 0) fused_env = getenv("TISE_RESIZE_FUSED") ? atoi(getenv("TISE_RESIZE_FUSED")) : 1;
     if (fused_env && need <= (size_t)kFusedSmem) {
-      static bool configured = false;
-      if (!configured) {
+      static PerDeviceFlag configured;
+      if (!configured.is(ctx, 1)) {
         TISE_CUDA(ctx, cudaFuncSetAttribute(resize_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmem));
-        configured = true;
+        configured.set(ctx, 1);
       }
       for (int i0 = 0; i0 < n; i0 += 32768) {
         const int cnt = n - i0 < 32768 ? n - i0 : 32768;

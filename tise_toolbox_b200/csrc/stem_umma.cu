@@ -284,10 +284,10 @@ void pack_stem_umma(const float* w_k_major /*[27][32]*/, float* scale /*[32], in
 
 int launch_stem_umma(tise_ctx* ctx, const uint8_t* d_u8, int n, const __half* d_w16, const float* d_scale,
                      const float* d_shift, __half* d_out, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceFlag configured;
+  if (!configured.is(ctx, 1)) {
     TISE_CUDA(ctx, cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSuSmem));
-    configured = true;
+    configured.set(ctx, 1);
   }
   StemUmmaParams p;
   p.u8 = d_u8;

@@ -129,6 +129,11 @@ class Engine:
         self._check(self.lib.tise_set_conv_mode(self.ctx, {"umma": 0, "simt": 1}[conv_impl], int(passes)))
         self.conv_impl, self.passes = conv_impl, int(passes)
 
+    def set_pass_policy(self, single_pass_max_hw: int = 0):
+        """Convolutions whose input map is at most this many pixels high skip the W_lo pass (0: none)."""
+        self._check(self.lib.tise_set_pass_policy(self.ctx, int(single_pass_max_hw)))
+        self.pass1_max_hw = int(single_pass_max_hw)
+
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor]):
         keep, descs = [], []
         for name, t in state_dict.items():
@@ -512,12 +517,20 @@ def default_engine(device: Union[int, str, torch.device, None] = None) -> Engine
 
 class Moments:
     """Running sum_i x_i and sum_i x_i x_i^T (fp64, on the device) -> (mu, sigma) of np.mean / np.cov
-    (fid_score.py:194-195).  Additive across batches and across ranks."""
+    (fid_score.py:194-195).  Additive across batches and across ranks.  ``buf`` (1 + d + d*d float64, zeroed) lets a
+    caller place the sums inside a larger packed buffer (:class:`StatsPack`: one all-reduce for everything)."""
 
-    def __init__(self, engine: Engine, d: int = 2048):
+    def __init__(self, engine: Engine, d: int = 2048, buf: Optional[torch.Tensor] = None):
         self.e, self.d = engine, d
-        self.buf = torch.zeros(1 + d + d * d, dtype=torch.float64, device=engine.device)  # [count | sum | sxx]
+        if buf is None:
+            buf = torch.zeros(1 + d + d * d, dtype=torch.float64, device=engine.device)  # [count | sum | sxx]
+        assert buf.dtype == torch.float64 and buf.numel() == 1 + d + d * d and buf.is_contiguous()
+        self.buf = buf
         self.count = 0
+
+    @staticmethod
+    def numel(d: int = 2048) -> int:
+        return 1 + d + d * d
 
     @property
     def sum(self):
@@ -536,13 +549,19 @@ class Moments:
                                                          self.sxx.data_ptr(), _stream()))
         self.count += n
 
+    def before_reduce(self):
+        self.buf[0] = float(self.count)
+
+    def after_reduce(self):
+        self.count = int(round(float(self.buf[0].item())))
+
     def allreduce(self, group=None):
         """The path's one exchange step: sum the packed moments over all ranks."""
         import torch.distributed as dist
 
-        self.buf[0] = float(self.count)
+        self.before_reduce()
         dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=group)
-        self.count = int(round(float(self.buf[0].item())))
+        self.after_reduce()
 
     def finalize_device(self) -> Tuple[torch.Tensor, torch.Tensor]:
         mu = torch.empty(self.d, dtype=torch.float64, device=self.e.device)
@@ -560,13 +579,24 @@ class Moments:
 
 class ISPartials:
     """Per-split partial sums of the inception score: sum_i sum_c p log p, sum_i p (marginal), count.
-    mean_i KL(p_i || m) = S / n - sum_c m_c log m_c with m = marg / n  (one-pass form)."""
+    mean_i KL(p_i || m) = S / n - sum_c m_c log m_c with m = marg / n  (one-pass form).
+    ``fbuf`` (``numel(C, S)`` float64, zeroed) places the sums -- and, for the exchange step, a float64 copy of the
+    integer counters -- inside a larger packed buffer (:class:`StatsPack`)."""
 
-    def __init__(self, engine: Engine, n_classes: int, n_splits: int):
+    def __init__(self, engine: Engine, n_classes: int, n_splits: int, fbuf: Optional[torch.Tensor] = None):
         self.e, self.cs, self.s = engine, n_classes, n_splits
-        # [splogp S | marg S*Cs | cnt S | zeros 1] -- all float64 except the two int64 tails viewed below
-        self.f = torch.zeros(n_splits + n_splits * n_classes, dtype=torch.float64, device=engine.device)
-        self.i = torch.zeros(n_splits + 1, dtype=torch.int64, device=engine.device)
+        nf = n_splits + n_splits * n_classes
+        if fbuf is None:
+            fbuf = torch.zeros(self.numel(n_classes, n_splits), dtype=torch.float64, device=engine.device)
+        assert fbuf.dtype == torch.float64 and fbuf.numel() == self.numel(n_classes, n_splits) and fbuf.is_contiguous()
+        self.fbuf = fbuf
+        self.f = fbuf[:nf]            # [splogp S | marg S*Cs]
+        self.icopy = fbuf[nf:]        # [cnt S | zeros 1] as float64, only meaningful around the all-reduce
+        self.i = torch.zeros(n_splits + 1, dtype=torch.int64, device=engine.device)  # the kernel's integer counters
+
+    @staticmethod
+    def numel(n_classes: int, n_splits: int) -> int:
+        return n_splits + n_splits * n_classes + n_splits + 1
 
     def update(self, logits: torch.Tensor, split_id: torch.Tensor, class_offset: int, temperature: float):
         assert logits.dtype == torch.float32 and split_id.dtype == torch.int32
@@ -580,11 +610,18 @@ class ISPartials:
                                           self.f[self.s:].data_ptr(), self.i.data_ptr(), self.i[self.s:].data_ptr(),
                                           _stream()))
 
+    def before_reduce(self):
+        self.icopy.copy_(self.i)  # counts < 2^53: exact in float64
+
+    def after_reduce(self):
+        self.i.copy_(self.icopy.round())
+
     def allreduce(self, group=None):
         import torch.distributed as dist
 
-        dist.all_reduce(self.f, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(self.i, op=dist.ReduceOp.SUM, group=group)
+        self.before_reduce()
+        dist.all_reduce(self.fbuf, op=dist.ReduceOp.SUM, group=group)
+        self.after_reduce()
 
     def finalize(self, nan_on_zero: bool = False) -> Tuple[float, float, np.ndarray]:
         """(mean, std (ddof=0), per-split scores).  ``nan_on_zero`` reproduces the IS* scripts' explicit
@@ -604,3 +641,41 @@ class ISPartials:
         if nan_on_zero and zeros > 0:
             scores[:] = np.nan
         return float(np.mean(scores)), float(np.std(scores)), scores
+
+
+class StatsPack:
+    """ONE contiguous fp64 device buffer ``[count | sum x | sum x x^T | IS sums | IS counters]`` holding every additive
+    statistic of a set, so that the path's single exchange step is a single ``all_reduce`` of
+    33.6 MB instead of one collective per statistic."""
+
+    def __init__(self, engine: Engine, d: int = 2048, is_classes: int = 0, is_splits: int = 0, want_moments: bool = True):
+        nm = Moments.numel(d) if want_moments else 0
+        ni = ISPartials.numel(is_classes, is_splits) if is_classes > 0 else 0
+        self.buf = torch.zeros(max(nm + ni, 1), dtype=torch.float64, device=engine.device)
+        self.moments = Moments(engine, d, self.buf[:nm]) if want_moments else None
+        self.parts = ISPartials(engine, is_classes, is_splits, self.buf[nm:nm + ni]) if is_classes > 0 else None
+
+    def allreduce(self, group=None):
+        import torch.distributed as dist
+
+        for st in (self.moments, self.parts):
+            if st is not None:
+                st.before_reduce()
+        dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=group)
+        for st in (self.moments, self.parts):
+            if st is not None:
+                st.after_reduce()
+
+
+def warm_collective(device, numel: int = 1 + 2048 + 2048 * 2048, group=None):
+    """First use of a NCCL communicator at a given message size costs tens of milliseconds (channel set-up, buffer
+    registration: 24.6 ms at 8 ranks in round 1).  Evaluation jobs call this once during set-up, next to the weight
+    upload, so that the end-of-run exchange step costs what the wire costs."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    t = torch.zeros(numel, dtype=torch.float64, device=device)
+    for _ in range(2):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    torch.cuda.synchronize(device)

@@ -122,7 +122,11 @@ def _compute_statistics_of_path(path, model, batch_size, dims, cuda):
         # raw uint8 shard (tise_toolbox_b200/shards.py): file -> pinned memory -> HBM, no codec anywhere
         from .shards import ShardLoader
 
-        mom = _accumulate_moments(ShardLoader(path, model.engine, batch_size, drop_last=True), model, batch_size, dims)
+        rank, world = _world()
+        mom = _accumulate_moments(ShardLoader(path, model.engine, batch_size, drop_last=True, rank=rank, world=world),
+                                  model, batch_size, dims)
+        if world > 1:
+            mom.allreduce()
         print(" done")
         m, s = mom.finalize()
     else:
@@ -178,6 +182,9 @@ def main(argv=None):
         torch.cuda.set_device(local)
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from .engine import warm_collective
+
+        warm_collective(torch.device("cuda", local))  # the end-of-run exchange then costs what the wire costs
     elif args.gpu != "":
         os.environ["CUDA_VISIBLE_DEVICES"] = args.gpu
     if args.weights:

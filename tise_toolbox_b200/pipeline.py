@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import inception_score as _is
-from .engine import Engine, ISPartials, Moments
+from .engine import Engine, ISPartials, Moments, StatsPack
 
 
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
@@ -56,11 +56,13 @@ class RealismJob:
         self.n_total, self.pos = int(n_total), int(start)
         self.is_variant = is_variant
         self.input_variant = input_variant
-        self.moments = Moments(engine, 2048) if want_moments else None
-        self.parts = None
+        cls = 0
         if is_variant is not None:
             _, off, _, _ = _is.VARIANTS[is_variant]
-            self.parts = ISPartials(engine, engine.num_classes - off, splits)
+            cls = engine.num_classes - off
+        # every additive statistic of the set lives in ONE packed fp64 buffer: the exchange step is one all-reduce
+        self.pack = StatsPack(engine, 2048, cls, splits if cls else 0, want_moments)
+        self.moments, self.parts = self.pack.moments, self.pack.parts
 
     def step(self, images: Union[torch.Tensor, Sequence[torch.Tensor]]) -> torch.Tensor:
         """One batch (device uint8 [B,H,W,3] or list of [H,W,3]); returns the batch's pool3 features."""
@@ -148,14 +150,12 @@ class RealismJob:
 
         use_dist = dist.is_available() and dist.is_initialized()
         out: Dict[str, object] = {}
+        if use_dist:
+            self.pack.allreduce(group)
         if self.moments is not None:
-            if use_dist:
-                self.moments.allreduce(group)
             out["count"] = self.moments.count
             out["mu"], out["sigma"] = self.moments.finalize_device()
         if self.parts is not None:
-            if use_dist:
-                self.parts.allreduce(group)
             _, _, _, nan_on_zero = _is.VARIANTS[self.is_variant]
             m, s, scores = self.parts.finalize(nan_on_zero=nan_on_zero)
             out["is_mean"], out["is_std"], out["is_scores"] = m, s, scores

@@ -68,6 +68,10 @@ def read_index(path):
     ends = offs + hw[:, 0].astype(np.int64) * hw[:, 1] * 3
     if n and (ends.max() > size or (offs % 16).any() or (hw <= 0).any() or offs.min() < 16 + n * _ENTRY.size):
         raise ValueError("%s: corrupt index" % path)
+    # ShardLoader uploads [offs[g0], ends[g1 - 1]) and addresses the images relative to offs[g0]: entries must be in
+    # file order and must not overlap, or the device would read outside the uploaded span
+    if n > 1 and (ends[:-1] > offs[1:]).any():
+        raise ValueError("%s: corrupt index (entries out of order or overlapping)" % path)
     return offs, hw, size
 
 
@@ -89,10 +93,15 @@ class ShardLoader:
     DataLoader (fid_score.py:214-217).  ``groups()`` yields ``group`` images per H2D copy for the batch-invariant
     consumers, exactly like :class:`~tise_toolbox_b200.img_data.DeviceImageLoader`."""
 
-    def __init__(self, path, engine, batch_size, drop_last=True, group=4096):
+    def __init__(self, path, engine, batch_size, drop_last=True, group=4096, rank=0, world=1):
         self.path, self.engine = path, engine
         self.batch_size, self.drop_last = int(batch_size), bool(drop_last)
         self.offsets, self.hw, self.size = read_index(path)
+        if world > 1:  # one process per GPU: a contiguous run of whole batches each, like the folder branch
+            from .pipeline import shard_batches
+
+            lo, hi = shard_batches(len(self.offsets), self.batch_size, rank, world)
+            self.offsets, self.hw = self.offsets[lo:hi], self.hw[lo:hi]
         self.group = max(1, int(group) // self.batch_size) * self.batch_size
 
     def __len__(self):
