@@ -209,10 +209,12 @@ def test_empty_batch(engine):
     assert tuple(f.shape) == (0, 2048)
 
 
-def test_ois_folder_path_on_device_matches_float_path(tmp_path):
+def test_ois_folder_path_on_device_matches_reference_pipeline(tmp_path):
     """O-IS through a folder of crop files: IgnoreLabelDataset(raw_u8=True) -> DeviceImageLoader (PNG decode, resize and
-    normalisation on the GPU, whole decode groups) against the reference's own pipeline on the same files
-    (IgnoreLabelDataset: PIL resize + ToTensor + Normalize on the host, object_centric_inception_score.py:84-104)."""
+    normalisation on the GPU, whole decode groups) against the REFERENCE's pipeline restated on the host for the same
+    files in the same os.listdir order: PIL open + Resize + ToTensor + Normalize (object_centric_inception_score.py:
+    84-104), torchvision Inception3 fp32 with the 80-way fc, softmax(logits / T) and scipy.stats.entropy over the
+    splits (:54-57, :69-81) -- oracle/restate.py's ois_preds / ois_inception_score."""
     from PIL import Image
 
     from tise_toolbox_b200 import object_centric_inception_score as ois
@@ -225,7 +227,16 @@ def test_ois_folder_path_on_device_matches_float_path(tmp_path):
     for i, (h, w) in enumerate(sizes):
         Image.fromarray(synth.images(5, i % 2, i, 1, h, w)[0].numpy()).save(str(tmp_path / ("crop_%03d.png" % i)))
     eng = Engine(sd80, device="cuda:0", variant="ois", micro_batch=16)
-    dev = ois.inception_score(ois.IgnoreLabelDataset(str(tmp_path), raw_u8=True), batch_size=8, splits=2, engine=eng)
-    ref = ois.inception_score(ois.IgnoreLabelDataset(str(tmp_path)), batch_size=8, splits=2, engine=eng)
+    ds = ois.IgnoreLabelDataset(str(tmp_path), raw_u8=True)
+    dev = ois.inception_score(ds, batch_size=8, splits=2, engine=eng)
+    # the host pipeline, file by file in the dataset's own order
+    names = [os.path.join(str(tmp_path), n) for n in ds.namelist]  # os.listdir order, as the reference walks it
+    ims = [np.asarray(Image.open(n).convert("RGB")) for n in names]
+    trunk = restate.Trunk(sd80, num_classes=80)
+    logits = trunk.logits(restate.preprocess(ims, "ois"))
+    ref = restate.ois_inception_score(restate.ois_preds(logits), 2)
     assert ref[0] > 1.2, ref
     assert abs(dev[0] - ref[0]) <= 1e-3 * ref[0] and abs(dev[1] - ref[1]) <= 2e-2 * ref[1] + 1e-4, (dev, ref)
+    # and the float path of the drop-in (host PIL resize + ToTensor + Normalize, trunk on the GPU) agrees with both
+    flt = ois.inception_score(ois.IgnoreLabelDataset(str(tmp_path)), batch_size=8, splits=2, engine=eng)
+    assert abs(flt[0] - ref[0]) <= 1e-3 * ref[0], (flt, ref)

@@ -79,6 +79,40 @@ def calculate_frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
     return np.float64(value)
 
 
+def _prefetched(images, device):
+    """Iterates ``images`` one batch ahead: host tensors (uint8 HWC batches or the reference's float batches) are
+    uploaded on a private copy stream while the previous batch is still in the trunk, so the PCIe transfer hides
+    behind the compute instead of serialising with it.  Ragged lists / device-resident packs pass through untouched."""
+    copy_stream = torch.cuda.Stream(device=device)
+    main = torch.cuda.current_stream(device)
+
+    def upload(batch):
+        if torch.is_tensor(batch) and not batch.is_cuda:
+            with torch.cuda.stream(copy_stream):
+                dev = batch.to(device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return dev, ev
+        return batch, None
+
+    it = iter(images)
+    try:
+        cur = upload(next(it))
+    except StopIteration:
+        return
+    while cur is not None:
+        try:
+            nxt = upload(next(it))
+        except StopIteration:
+            nxt = None
+        batch, ev = cur
+        if ev is not None:
+            main.wait_event(ev)
+            batch.record_stream(main)  # allocated on the copy stream, consumed on the compute stream
+        yield batch
+        cur = nxt
+
+
 def _accumulate_moments(images, model, batch_size, dims):
     model.eval()
     mom = Moments(model.engine, dims)
@@ -88,7 +122,7 @@ def _accumulate_moments(images, model, batch_size, dims):
         for pack in images.groups():
             mom.update(_batch_features(pack, model, dims))
         return mom
-    for batch in images:
+    for batch in _prefetched(images, model.engine.device):
         if len(batch) != batch_size:
             raise ValueError("calculate_activation_statistics: batch of %d, expected %d (drop_last=True, "
                              "fid_score.py:216)" % (len(batch), batch_size))

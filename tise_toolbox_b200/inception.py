@@ -33,7 +33,7 @@ class InceptionV3(nn.Module):
     BLOCK_INDEX_BY_DIM = {64: 0, 192: 1, 768: 2, 2048: 3}
 
     def __init__(self, output_blocks=[DEFAULT_BLOCK_INDEX], resize_input=True, normalize_input=True,
-                 requires_grad=False, state_dict=None, weights_path=None, device=None, micro_batch=512):
+                 requires_grad=False, state_dict=None, weights_path=None, device=None, micro_batch=512, engine=None):
         super(InceptionV3, self).__init__()
         self.resize_input = resize_input
         self.normalize_input = normalize_input
@@ -42,6 +42,9 @@ class InceptionV3(nn.Module):
         assert self.last_needed_block <= 3, "Last possible output block index is 3"
         if requires_grad:
             raise NotImplementedError("libtise_b200 is an inference path: requires_grad=True is not supported")
+        if engine is not None:  # share an existing context (weights already on the device)
+            self.engine = engine
+            return
         if state_dict is None:
             weights_path = weights_path or os.environ.get("TISE_INCEPTION_WEIGHTS")
             if not weights_path:
