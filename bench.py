@@ -44,6 +44,7 @@ def parse():
     p.add_argument("--crops", type=int, default=100000, help="cfg4: number of ragged crops")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--passes", type=int, default=2)
+    p.add_argument("--strict", action="store_true", help="two MMA passes in every layer (default: mixed operand policy)")
     p.add_argument("--cpu-sample", type=int, default=500, help="images of the CPU reference leg (two sets of half)")
     p.add_argument("--ref-step", type=int, default=200, help="--impl reference: images per step")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -382,7 +383,8 @@ def main():
 
     # ---- setup (untimed): weights, resident image pool, calibrated IS head, real-set statistics, warm communicator
     sd = synth.inception_state_dict(0, num_classes=51)
-    eng = Engine(sd, device=dev, variant="bird", micro_batch=args.micro_batch, passes=args.passes)
+    eng = Engine(sd, device=dev, variant="bird", micro_batch=args.micro_batch, passes=args.passes,
+                 single_pass_max_hw=0 if args.strict else None)
     pool = torch.cat([synth.images(1, 0, rank * args.pool + i, min(256, args.pool - i), device=dev)
                       for i in range(0, args.pool, 256)])
     calib = eng.features(pool[:64])
@@ -475,6 +477,19 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * B * K / (float(e2e_ms.item()) / 1e3)
 
+    # ---- what the PCIe link of this box delivers for the same pinned buffer, GPU otherwise idle (e2e cannot exceed
+    # h2d_gbs / bytes-per-image whatever the kernels do)
+    torch.cuda.synchronize()
+    stg = torch.empty_like(host[:B], device=dev)
+    stg.copy_(host[:B], non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        stg.copy_(host[:B], non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * B * IMG_BYTES / (time.perf_counter() - t0) / 1e9
+    del stg
+
     # ---- end-to-end through the reference-facing drop-in function itself: fid_score.calculate_activation_statistics on
     # an iterable of uint8 HOST batches (what a DataLoader(collate_u8) yields), (mu, sigma) returned as numpy arrays
     class HostBatches(list):
@@ -545,20 +560,30 @@ def main():
                 "algorithmic_gflop_per_image": conv_flops / (2 * B) / 1e9,
                 "share_of_trunk_time": conv_ms / trunk_ms if trunk_ms else None,
                 "other_kernels_ms_per_step": {k: v[0] / 2 for k, v in prof.items() if k != "conv"},
-                "note": "two MMA passes (W_hi, W_lo) per algorithmic FLOP: frac <= 0.5 x tensor-pipe utilisation",
+                "note": "algorithmic FLOPs; layers on maps > 17 px issue two MMA passes (W_hi, W_lo) per FLOP, the others "
+                        "one (strict policy: two everywhere)",
                 "how": "cudaEvent pairs on the launch stream around each launch, summed over 2 steps after the timed region"}
 
     line = {"metric": "FID/IS* images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 x (f16 hi + f16 lo) operands, f32 accumulate" if args.passes == 2 else "f16, f32 accumulate",
+            "dtype": (("f16 x (f16 hi + f16 lo) operands, f32 accumulate" if eng.pass1_max_hw == 0 else
+                       "f16 x (f16 hi + f16 lo) operands (maps > %d px) / f16 x f16 (maps <= %d px), f32 accumulate"
+                       % (eng.pass1_max_hw, eng.pass1_max_hw)) if args.passes == 2 else "f16, f32 accumulate"),
             "data": "synthetic",
             "config": {"workload": ("cfg2: IS* (bird head, T=0.598, 10 splits) + FID moments" if world == 1 else
                                     "cfg3: FID + IS* sharded over %d GPUs, one all-reduce at the end" % world),
                        "image": "256x256x3 uint8", "images_per_step_per_gpu": B, "micro_batch": args.micro_batch,
                        "resident_pool_images": args.pool, "l2": "inputs (%.0f MB/step) larger than L2" % (B * IMG_BYTES / 1e6),
-                       "random_init": "seeded He-normal Inception3, calibrated 51-way head"},
+                       "random_init": "seeded He-normal Inception3, calibrated 51-way head",
+                       "operand_policy": ("strict: two MMA passes (W_hi, W_lo) in every layer" if eng.pass1_max_hw == 0 else
+                                          "mixed (default): W_lo pass skipped in layers whose input map is <= %d px "
+                                          "(DESIGN.md section 2; parity at BASELINE sizes: tests/test_gpu_parity_baseline.py)"
+                                          % eng.pass1_max_hw)},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * IMG_BYTES,
                     "d2h_bytes_per_step": int(d2h.numel() * 8),
+                    "h2d_link_gbs": h2d_gbs, "h2d_link_images_per_s": h2d_gbs * 1e9 / IMG_BYTES,
+                    "h2d_link_note": "pinned-memory H2D copy of one step's batch with the GPU idle: the ceiling of any "
+                                     "end-to-end number that ships raw uint8 images over this link",
                     "through_dropin": {"value": dropin_value, "unit": "images/s", "steps": kd,
                                        "call": "fid_score.calculate_activation_statistics(uint8 host batches, model, "
                                                "batch_size=%d) -> (mu, sigma) numpy: H2D of every batch (prefetched one "
@@ -571,13 +596,20 @@ def main():
             import shutil
             import tempfile
 
+            # the CPU leg is the reference's FID module, whose input map is the FID affine: give both sides a head
+            # calibrated for THAT feature distribution (the bird-calibrated head makes IS* ~ 1.3 there: a vacuous target)
+            eng.set_variant("fid")
+            sd_par = synth.calibrate_head(sd, eng.features(pool[:64]).cpu(), T_BIRD, class_offset=1)
+            eng.load_state_dict(sd_par)
             tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
             try:
-                rec, cpu = cpu_leg(sd, args.cpu_sample, tmp)
+                rec, cpu = cpu_leg(sd_par, args.cpu_sample, tmp)
             finally:
                 shutil.rmtree(tmp, ignore_errors=True)
             line["cpu_baseline"] = rec
             line["parity"] = gpu_parity(eng, cpu)
+            line["parity"]["operand_policy"] = "strict" if eng.pass1_max_hw == 0 else "mixed (maps <= %d px: one pass)" % eng.pass1_max_hw
+            eng.load_state_dict(sd)
             eng.set_variant("bird")
         if not args.no_frechet:
             line["frechet"] = frechet_latency(eng, res, world == 1 and not args.no_cpu_baseline)
@@ -608,7 +640,8 @@ def run_cfg4(args, rank, world, dev):
         torch.cuda.synchronize()
 
     sd = synth.inception_state_dict(3, num_classes=80)
-    eng = Engine(sd, device=dev, variant="ois", micro_batch=args.micro_batch, passes=args.passes)
+    eng = Engine(sd, device=dev, variant="ois", micro_batch=args.micro_batch, passes=args.passes,
+                 single_pass_max_hw=0 if args.strict else None)
     sizes = synth.crop_sizes(8, rank * U, U)
     src = synth.images(5, 1, rank * 8, 8, 480, 480, device=dev)
     hw = np.array(sizes, dtype=np.int32)

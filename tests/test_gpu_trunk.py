@@ -45,6 +45,25 @@ def test_pool3_parity(engine, batch, oracle_blocks, impl, passes):
     assert err <= POOL3_REL_L2[passes], "pool3 rel L2 %.3e" % err
 
 
+def test_pool3_parity_mixed_policy(engine, batch, oracle_blocks):
+    """The default operand policy (layers on maps <= 17 x 17 skip the W_lo pass): TF32-class pool3 bound, strictly
+    between the strict two-pass error and the single-pass one; blocks up to Mixed_6a are untouched by it."""
+    from tise_toolbox_b200.engine import DEFAULT_SINGLE_PASS_MAX_HW, POOL3_REL_L2_BOUND
+
+    engine.set_variant("fid")
+    strict = engine.features(batch.cuda()).cpu().numpy()
+    engine.set_pass_policy(DEFAULT_SINGLE_PASS_MAX_HW)
+    try:
+        mixed = engine.features(batch.cuda()).cpu().numpy()
+        tap192 = engine.features(batch.cuda(), dims=192).cpu().numpy()
+    finally:
+        engine.set_pass_policy(0)
+    ref = oracle_blocks[1][3].reshape(len(batch), -1).numpy()
+    assert _rel_l2(mixed, ref) <= POOL3_REL_L2_BOUND["mixed"]
+    assert _rel_l2(strict, ref) <= POOL3_REL_L2_BOUND["strict"]
+    assert np.array_equal(tap192, engine.features(batch.cuda(), dims=192).cpu().numpy())  # 73 x 73 / 71 x 71 layers: same bits
+
+
 @pytest.mark.parametrize("dims,block", [(64, 0), (192, 1), (768, 2)])
 def test_block_taps(engine, batch, oracle_blocks, dims, block):
     got = engine.features(batch.cuda(), dims=dims).cpu().numpy()
@@ -80,7 +99,7 @@ def test_forward_resizes_float_inputs_of_other_sizes(state_dict):
 
     from tise_toolbox_b200.inception import InceptionV3
 
-    model = InceptionV3([3], state_dict=state_dict, micro_batch=8)
+    model = InceptionV3([3], state_dict=state_dict, micro_batch=8, single_pass_max_hw=0)
     x = synth.images(1, 0, 0, 4).permute(0, 3, 1, 2).float().div(255)  # 256 x 256 floats in [0, 1]
     a = model(x)[0].reshape(4, -1).cpu().numpy()
     b = model(F.interpolate(x, size=(299, 299), mode="bilinear", align_corners=True))[0].reshape(4, -1).cpu().numpy()

@@ -130,6 +130,8 @@ struct ConvArgs {
   const __half* in = nullptr;  // base of the input tensor (channel 0 of the view)
   int n = 0, h = 0, w = 0;     // input spatial dims
   int in_stride = 0;           // elements per input pixel (>= cin)
+  int in_row_pitch = 0;        // pixels per physical input row (0: w).  Row-folded layers (net.cu: conv_folded) read a
+                               // window of S pixels as ONE pixel of S * cin channels, so their logical width is wo
   ConvSeg segs[kMaxSegs];
   int n_segs = 0;
   int out_f32 = 0;  // all segments fp32 (Mixed_7c) or all fp16

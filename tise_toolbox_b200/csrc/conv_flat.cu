@@ -7,11 +7,14 @@
 //
 //     out[v] = sum_{r,s} in[v + r * Wp + s] . W[r,s]        v = (n * Hp + y) * Wp + x
 //
-// so every filter tap is the SAME run of pixels shifted by r * Wp + s rows.  Per 128-pixel tile the producer
-// issues R plain 2D TMA loads (one run of 128 + S - 1 pixels per filter row) into ONE pipeline stage, the MMA
-// warp issues all R * S * (C / 16) MMAs of the tile against shifted views of those runs (the shared-memory
-// descriptor's start address moves by whole pixel rows), and the weights of all taps stay resident in shared
-// memory for the lifetime of the CTA.  Outputs that fall outside the valid region (x >= Wo or y >= Ho: the
+// so every filter tap is the SAME run of pixels shifted by r * Wp + s rows.  A work item is T consecutive
+// 128-pixel tiles (T * 128 flat positions): the producer brings ONE contiguous run of T * 128 + (R - 1) * Wp + S - 1
+// pixels into a pipeline stage (a few plain 2D TMA boxes), the MMA warp issues all T * R * S * (C / 16) MMAs of the item
+// against shifted views of that run (the shared-memory descriptor's start address moves by whole pixel rows:
+// t * 128 + r * Wp + s), and the weights of all taps stay resident in shared memory for the lifetime of the CTA.
+// With T = 3 a 3x3 layer loads 232 rows per 128 outputs instead of the 390 of one run per (tile, filter row): the
+// rows of the three filter rows overlap, and so do the runs of neighbouring tiles (measured: these 32-channel layers
+// were bound by the ~2 cycles the TMA unit needs per row, and Conv2d_2a by HBM at 43 % of its peak).  Outputs that fall outside the valid region (x >= Wo or y >= Ho: the
 // wrap-around columns / rows of the padded grid) are written as zeros, so the output tensor is itself a correctly
 // zero-padded input grid for the next flat layer (written at a constant flat offset `out_shift`).
 //
@@ -43,7 +46,8 @@ struct FlatParams {
   int row_bytes;        // cin * 2: 64 (SWIZZLE_64B) or 128 (SWIZZLE_128B)
   int swz_type, sbo;
   int nt;               // cout (<= 128); MMA N = 2 * nt
-  int run_rows, run_bytes;  // pixels per run (128 + S - 1) and its shared-memory footprint
+  int tsub;                 // 128-pixel tiles per work item (their accumulators sit side by side in one TMEM stage)
+  int n_boxes, box_rows;    // the run of a work item arrives as n_boxes TMA boxes of box_rows pixels
   int wtile_bytes;          // one tap's weights: 2 * nt rows
   int stages, stage_bytes, num_tiles, relu;
   int pdl;  // launched with programmatic stream serialization
@@ -58,7 +62,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int taps = p.R * p.S;
-  // layout: [weights taps x wtile][stages x R runs][2 staged output boxes][scale | shift][barriers][tmem slot]
+  // layout: [weights taps x wtile][stages x run of the item][2 staged output boxes][scale | shift][barriers][tmem slot]
   const uint32_t w_base = smem_base;
   const uint32_t st_base = (w_base + (uint32_t)(taps * p.wtile_bytes) + 1023u) & ~1023u;
   const uint32_t epi_base = st_base + (uint32_t)p.stages * (uint32_t)p.stage_bytes;
@@ -101,9 +105,10 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    const int R = p.R, wp = p.wp, n_stages = p.stages;
-    const uint32_t run_bytes = (uint32_t)p.run_bytes, stage_bytes = (uint32_t)p.stage_bytes;
-    const uint32_t tx = (uint32_t)(p.R * p.run_rows * p.row_bytes);
+    const int n_stages = p.stages, n_boxes = p.n_boxes, box_rows = p.box_rows;
+    const uint32_t stage_bytes = (uint32_t)p.stage_bytes, box_bytes = (uint32_t)(p.box_rows * p.row_bytes);
+    const uint32_t tx = (uint32_t)p.n_boxes * box_bytes;
+    const long long item_pos = (long long)p.tsub * kBlockM;
     if (elect_one()) {  // all weights, once
       mbar_expect_tx(wfull_bar, (uint32_t)(taps * p.wtile_bytes));
       for (int t = 0; t < taps; ++t) tma_load_2d(&tm_w, w_base + (uint32_t)(t * p.wtile_bytes), wfull_bar, t * (p.ksteps * 16), 0);
@@ -111,14 +116,14 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const long long v0 = (long long)tile * kBlockM;
+    for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
+      const long long v0 = (long long)item * item_pos;
       mbar_wait(empty_bar(stage), phase ^ 1u);
       const uint32_t sa = st_base + (uint32_t)stage * stage_bytes;
       const uint32_t fb = full_bar(stage);
       if (elect_one()) {
-        mbar_expect_tx(fb, tx);
-        for (int r = 0; r < R; ++r) tma_load_2d(&tm_a, sa + (uint32_t)r * run_bytes, fb, 0, (int)(v0 + (long long)r * wp));
+        mbar_expect_tx(fb, tx);  // boxes that reach past the end of the tensor are zero-filled and still count in full
+        for (int b = 0; b < n_boxes; ++b) tma_load_2d(&tm_a, sa + (uint32_t)b * box_bytes, fb, 0, (int)(v0 + (long long)b * box_rows));
       }
       if (++stage == n_stages) {
         stage = 0;
@@ -129,48 +134,54 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ===================================================================== MMA issuer
     const uint32_t idesc = make_instr_desc(2 * p.nt);
     const uint64_t dhi = smem_desc_hi(p.swz_type, p.sbo);
-    const int R = TR ? TR : p.R, S = TS ? TS : p.S, ksteps = TK ? TK : p.ksteps, n_stages = p.stages;
-    const uint32_t run_bytes = (uint32_t)p.run_bytes, stage_bytes = (uint32_t)p.stage_bytes, row_bytes = (uint32_t)p.row_bytes,
-                   wtile_bytes = (uint32_t)p.wtile_bytes;
+    const int R = TR ? TR : p.R, S = TS ? TS : p.S, ksteps = TK ? TK : p.ksteps, n_stages = p.stages, tsub = p.tsub;
+    const uint32_t stage_bytes = (uint32_t)p.stage_bytes, row_bytes = (uint32_t)p.row_bytes, wtile_bytes = (uint32_t)p.wtile_bytes;
     // Descriptor start-address fields (>> 4).  The swizzle of both TMA and tcgen05 is a function of the absolute
     // shared-memory address bits, so a view shifted by whole pixel rows needs nothing but the new start address (the
     // descriptor's base-offset field stays 0; setting it to (addr >> 7) & 7 gives wrong results -- measured).
     const uint64_t wdesc0 = make_smem_desc(w_base, dhi);
+    const uint32_t tile_step = ((uint32_t)kBlockM * row_bytes) >> 4;  // next 128-pixel tile of the item
+    const uint32_t frow_step = ((uint32_t)p.wp * row_bytes) >> 4;     // next filter row: Wp pixels further
+    const uint32_t pix_step = row_bytes >> 4;                        // next filter column: one pixel further
+    const uint32_t acc_cols = 2u * (uint32_t)p.nt;
     mbar_wait(wfull_bar, 0);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < p.num_tiles; item += gridDim.x) {
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       mbar_wait(full_bar(stage), phase);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
       const uint64_t adesc0 = make_smem_desc(st_base + (uint32_t)stage * stage_bytes, dhi);
       if (elect_one()) {
-        if (TR && TS && TK) {
+        for (int t = 0; t < tsub; ++t) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256) + (uint32_t)t * acc_cols;
+          const uint64_t at = adesc0 + (uint64_t)((uint32_t)t * tile_step);
+          if (TR && TS && TK) {
 #pragma unroll
-          for (int r = 0; r < TR; ++r)
+            for (int r = 0; r < TR; ++r)
 #pragma unroll
-            for (int s2 = 0; s2 < TS; ++s2)
+              for (int s2 = 0; s2 < TS; ++s2)
 #pragma unroll
-              for (int k = 0; k < TK; ++k) {
-                const uint64_t ad = adesc0 + (uint64_t)(((uint32_t)r * run_bytes + (uint32_t)s2 * row_bytes) >> 4) + (uint64_t)(2 * k);
-                const uint64_t bd = wdesc0 + (uint64_t)(((uint32_t)(r * TS + s2) * wtile_bytes) >> 4) + (uint64_t)(2 * k);
-                umma_f16(d_tmem, ad, bd, idesc, (r | s2 | k) ? 1u : 0u);
+                for (int k = 0; k < TK; ++k) {
+                  const uint64_t ad = at + (uint64_t)((uint32_t)r * frow_step + (uint32_t)s2 * pix_step) + (uint64_t)(2 * k);
+                  const uint64_t bd = wdesc0 + (uint64_t)(((uint32_t)(r * TS + s2) * wtile_bytes) >> 4) + (uint64_t)(2 * k);
+                  umma_f16(d_tmem, ad, bd, idesc, (r | s2 | k) ? 1u : 0u);
+                }
+          } else {
+            uint32_t first = 0;
+            uint64_t bd = wdesc0;
+            for (int r = 0; r < R; ++r)
+              for (int s2 = 0; s2 < S; ++s2) {
+                const uint64_t ad = at + (uint64_t)((uint32_t)r * frow_step + (uint32_t)s2 * pix_step);
+                for (int k = 0; k < ksteps; ++k) {
+                  umma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, first);
+                  first = 1u;
+                }
+                bd += (uint64_t)(wtile_bytes >> 4);
               }
-        } else {
-          uint32_t first = 0;
-          uint64_t bd = wdesc0;
-          for (int r = 0; r < R; ++r)
-            for (int s2 = 0; s2 < S; ++s2) {
-              const uint64_t ad = adesc0 + (uint64_t)(((uint32_t)r * run_bytes + (uint32_t)s2 * row_bytes) >> 4);
-              for (int k = 0; k < ksteps; ++k) {
-                umma_f16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, first);
-                first = 1u;
-              }
-              bd += (uint64_t)(wtile_bytes >> 4);
-            }
+          }
         }
         umma_commit(empty_bar(stage));
         umma_commit(tfull_bar(as));
@@ -208,65 +219,69 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int as = grp;
     uint32_t aphase = 0;
     uint32_t box_it = 0;
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x) {
-      const long long v0 = (long long)tile * kBlockM;
-      // is this thread's output position a real output or a wrap-around cell of the padded grid (written as 0)?
-      const long long v = v0 + row;
-      const int rem = (int)(v % hpwp);
-      const int y = rem / wp, x = rem - y * wp;
-      const bool valid = v < p.total && y < ho && x < wo;
+    const int tsub = p.tsub;
+    const long long item_pos = (long long)tsub * kBlockM;
+    for (int item = blockIdx.x + grp * gridDim.x; item < p.num_tiles; item += 2 * gridDim.x) {
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 256);
-      for (int c0 = 0; c0 < nt; c0 += 32, ++box_it) {
-        const uint32_t buf = my_epi + (box_it & 1u) * kFlatEpiBuf;
-        float f[32];
-        {
-          uint32_t a[32], b[32];
-          tmem_ld32(taddr + (uint32_t)c0, a);
-          tmem_ld32(taddr + (uint32_t)(nt + c0), b);  // W_lo products
-          tmem_ld_wait();
+      for (int t = 0; t < tsub; ++t) {
+        const long long v0 = (long long)item * item_pos + (long long)t * kBlockM;
+        // is this thread's output position a real output or a wrap-around cell of the padded grid (written as 0)?
+        const long long v = v0 + row;
+        const int rem = (int)(v % hpwp);
+        const int y = rem / wp, x = rem - y * wp;
+        const bool valid = v < p.total && y < ho && x < wo;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 256 + t * 2 * nt);
+        for (int c0 = 0; c0 < nt; c0 += 32, ++box_it) {
+          const uint32_t buf = my_epi + (box_it & 1u) * kFlatEpiBuf;
+          float f[32];
+          {
+            uint32_t a[32], b[32];
+            tmem_ld32(taddr + (uint32_t)c0, a);
+            tmem_ld32(taddr + (uint32_t)(nt + c0), b);  // W_lo products
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
-        }
-        if (c0 + 32 >= nt) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(as));
-        }
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
+          }
+          if (c0 + 32 >= nt && t == tsub - 1) {  // all accumulators of the item read: hand the stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+          }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * q);
-          const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + 4 * q);
-          float* yv = f + 4 * q;
-          yv[0] = fmaf(yv[0], sc.x, sh.x);
-          yv[1] = fmaf(yv[1], sc.y, sh.y);
-          yv[2] = fmaf(yv[2], sc.z, sh.z);
-          yv[3] = fmaf(yv[3], sc.w, sh.w);
-          if (!valid) yv[0] = yv[1] = yv[2] = yv[3] = 0.f;
-        }
+          for (int q = 0; q < 8; ++q) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * q);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + 4 * q);
+            float* yv = f + 4 * q;
+            yv[0] = fmaf(yv[0], sc.x, sh.x);
+            yv[1] = fmaf(yv[1], sc.y, sh.y);
+            yv[2] = fmaf(yv[2], sc.z, sh.z);
+            yv[3] = fmaf(yv[3], sc.w, sh.w);
+            if (!valid) yv[0] = yv[1] = yv[2] = yv[3] = 0.f;
+          }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {  // ReLU and saturation are part of the conversion
-          const uint32_t dst = buf + wr_off + (((uint32_t)j ^ wr_swz) << 4);
-          if (relu)
-            st_shared_v4(dst, pack_h2_sat<true>(f[8 * j], f[8 * j + 1]), pack_h2_sat<true>(f[8 * j + 2], f[8 * j + 3]),
-                         pack_h2_sat<true>(f[8 * j + 4], f[8 * j + 5]), pack_h2_sat<true>(f[8 * j + 6], f[8 * j + 7]));
-          else
-            st_shared_v4(dst, pack_h2_sat<false>(f[8 * j], f[8 * j + 1]), pack_h2_sat<false>(f[8 * j + 2], f[8 * j + 3]),
-                         pack_h2_sat<false>(f[8 * j + 4], f[8 * j + 5]), pack_h2_sat<false>(f[8 * j + 6], f[8 * j + 7]));
-        }
-        epi_bar(1 + grp);
-        const int ccol = c0 + st_chunk * 8;
-        if (ccol < nt) {
-          char* obase = reinterpret_cast<char*>(p.out) + (size_t)ccol * 2;
-          const size_t pitch = (size_t)p.out_stride * 2;
+          for (int j = 0; j < 4; ++j) {  // ReLU and saturation are part of the conversion
+            const uint32_t dst = buf + wr_off + (((uint32_t)j ^ wr_swz) << 4);
+            if (relu)
+              st_shared_v4(dst, pack_h2_sat<true>(f[8 * j], f[8 * j + 1]), pack_h2_sat<true>(f[8 * j + 2], f[8 * j + 3]),
+                           pack_h2_sat<true>(f[8 * j + 4], f[8 * j + 5]), pack_h2_sat<true>(f[8 * j + 6], f[8 * j + 7]));
+            else
+              st_shared_v4(dst, pack_h2_sat<false>(f[8 * j], f[8 * j + 1]), pack_h2_sat<false>(f[8 * j + 2], f[8 * j + 3]),
+                           pack_h2_sat<false>(f[8 * j + 4], f[8 * j + 5]), pack_h2_sat<false>(f[8 * j + 6], f[8 * j + 7]));
+          }
+          epi_bar(1 + grp);
+          const int ccol = c0 + st_chunk * 8;
+          if (ccol < nt) {
+            char* obase = reinterpret_cast<char*>(p.out) + (size_t)ccol * 2;
+            const size_t pitch = (size_t)p.out_stride * 2;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = st_row0 + 32 * i;
-            const long long mo = v0 + r + p.out_shift;
-            if (mo < p.out_total && v0 + r < p.total) {
-              const uint4 val = ld_shared_v4(buf + (uint32_t)r * 64u + (((uint32_t)st_chunk ^ (uint32_t)((r >> 1) & 3)) << 4));
-              *reinterpret_cast<uint4*>(obase + (size_t)mo * pitch) = val;
+            for (int i = 0; i < 4; ++i) {
+              const int r = st_row0 + 32 * i;
+              const long long mo = v0 + r + p.out_shift;
+              if (mo < p.out_total && v0 + r < p.total) {
+                const uint4 val = ld_shared_v4(buf + (uint32_t)r * 64u + (((uint32_t)st_chunk ^ (uint32_t)((r >> 1) & 3)) << 4));
+                *reinterpret_cast<uint4*>(obase + (size_t)mo * pitch) = val;
+              }
             }
           }
         }
@@ -291,6 +306,36 @@ bool conv_flat_supported(const ConvLayer& L) {
          L.nt == L.cout && L.S <= 7 && L.R <= 7;
 }
 
+// Work-item geometry: T tiles of 128 positions share one contiguous run of T * 128 + (R - 1) * Wp + S - 1 pixels, which
+// arrives as n_boxes TMA boxes (<= 256 rows each, a multiple of 8 so that every box starts on a swizzle atom).  T is
+// limited by the 256 TMEM columns of an accumulator stage (2 * nt per tile) and by shared memory (>= 3 pipeline stages
+// next to the resident weights).
+struct FlatGeom {
+  int tsub, n_boxes, box_rows, stage_bytes, stages;
+};
+static FlatGeom flat_geometry(const ConvLayer& L, int wp, int smem_limit) {
+  const int row_bytes = L.cin * 2;
+  const int fixed = 1024 + (int)align_up((size_t)L.R * L.S * 2 * L.nt * row_bytes, 1024) + 4 * kFlatEpiBuf + 2 * 128 * 4 +
+                    8 * (2 * kFlatMaxStages + 6) + 16;
+  static int t_env = -1;
+  if (t_env < 0) t_env = getenv("TISE_FLAT_T") ? atoi(getenv("TISE_FLAT_T")) : 0;
+  int tmax = 256 / (2 * L.nt);
+  if (tmax > 4) tmax = 4;
+  if (t_env > 0 && t_env < tmax) tmax = t_env;
+  FlatGeom g{1, 1, 0, 0, 0};
+  for (int t = tmax; t >= 1; --t) {
+    const int run_rows = t * kBlockM + (L.R - 1) * wp + L.S - 1;
+    const int n_boxes = (run_rows + 255) / 256;
+    const int box_rows = ((run_rows + n_boxes - 1) / n_boxes + 7) / 8 * 8;
+    const int stage_bytes = (int)align_up((size_t)n_boxes * box_rows * row_bytes, 1024);
+    int stages = (smem_limit - fixed) / stage_bytes;
+    if (stages > kFlatMaxStages) stages = kFlatMaxStages;
+    g = FlatGeom{t, n_boxes, box_rows, stage_bytes, stages};
+    if (stages >= 3 || (t == 1 && stages >= 2)) break;
+  }
+  return g;
+}
+
 int build_flat_plan(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, FlatPlan* plan) {
   if (!conv_flat_supported(L)) return fail(ctx, TISE_ERR_INVALID, "flat conv: unsupported layer");
   if (!g_flat_encode) {
@@ -302,10 +347,12 @@ int build_flat_plan(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, FlatPl
   }
   const CUtensorMapSwizzle swz = L.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const long long total = (long long)a.n * a.hp * a.wp;
+  const FlatGeom g = flat_geometry(L, a.wp, ctx->smem_optin > 0 ? ctx->smem_optin : 232448);
+  if (g.stages < 2) return fail(ctx, TISE_ERR_INVALID, "flat conv: does not fit shared memory");
   {
     cuuint64_t dims[2] = {(cuuint64_t)L.cin, (cuuint64_t)total};
     cuuint64_t strides[1] = {(cuuint64_t)L.cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)L.kc, (cuuint32_t)(kBlockM + L.S - 1)};
+    cuuint32_t box[2] = {(cuuint32_t)L.kc, (cuuint32_t)g.box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_flat_encode(&plan->tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)a.in, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -347,11 +394,7 @@ int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const
   p.swz_type = L.kc == 64 ? 2 : 4;
   p.sbo = 8 * p.row_bytes;
   p.nt = L.cout;
-  p.run_rows = kBlockM + L.S - 1;
-  p.run_bytes = (int)align_up((size_t)p.run_rows * p.row_bytes, 1024);
   p.wtile_bytes = 2 * L.nt * p.row_bytes;
-  p.stage_bytes = L.R * p.run_bytes;
-  p.num_tiles = cdiv(p.total, kBlockM);
   p.relu = a.relu;
 
   static PerDeviceFlag configured;
@@ -361,12 +404,14 @@ int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const
     TISE_CUDA(ctx, cudaFuncSetAttribute(conv_flat_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
     configured.set(ctx, smem_limit);
   }
-  const int fixed = 1024 + (int)align_up((size_t)L.R * L.S * p.wtile_bytes, 1024) + 4 * kFlatEpiBuf + 2 * 128 * 4 +
-                    8 * (2 * kFlatMaxStages + 6) + 16;
-  int stages = (smem_limit - fixed) / p.stage_bytes;
-  if (stages > kFlatMaxStages) stages = kFlatMaxStages;
-  if (stages < 2) return fail(ctx, TISE_ERR_INVALID, "flat conv: does not fit shared memory");
-  p.stages = stages;
+  const FlatGeom g = flat_geometry(L, a.wp, smem_limit);  // the same geometry the plan's input box was built for
+  if (g.stages < 2) return fail(ctx, TISE_ERR_INVALID, "flat conv: does not fit shared memory");
+  p.tsub = g.tsub;
+  p.n_boxes = g.n_boxes;
+  p.box_rows = g.box_rows;
+  p.stage_bytes = g.stage_bytes;
+  p.stages = g.stages;
+  p.num_tiles = cdiv(p.total, (long long)g.tsub * kBlockM);  // work items
   const int grid = p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);

@@ -15,7 +15,7 @@ struct SimtParams {
   const float* shift;
   void* seg_out[kMaxSegs];
   int seg_end[kMaxSegs], seg_stride[kMaxSegs], seg_relu[kMaxSegs];
-  int n, h, w, in_stride, cin, cin_pad, ktot, nt;
+  int n, h, w, pitch_w, in_stride, cin, cin_pad, ktot, nt;
   int cout, R, S, stride, pad_h, pad_w, ho, wo, out_f32, passes;
   long long M;
 };
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(SimtParams p) {
     for (int s = 0; s < p.S; ++s) {
       const int iy = loy * p.stride - p.pad_h + r, ix = lox * p.stride - p.pad_w + s;
       const bool inb = lvalid && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
-      const __half* arow = inb ? p.in + (((size_t)limg * p.h + iy) * p.w + ix) * p.in_stride : p.in;
+      const __half* arow = inb ? p.in + (((size_t)limg * p.h + iy) * p.pitch_w + ix) * p.in_stride : p.in;
       const size_t whi = ((size_t)(lco / p.nt) * 2 * p.nt + lco % p.nt) * p.ktot + (size_t)(r * p.S + s) * p.cin_pad;
       const size_t wlo = whi + (size_t)p.nt * p.ktot;
       for (int c0 = 0; c0 < p.cin; c0 += SBK) {
@@ -125,6 +125,7 @@ int launch_conv_simt(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, cudaS
   p.n = a.n;
   p.h = a.h;
   p.w = a.w;
+  p.pitch_w = a.in_row_pitch ? a.in_row_pitch : a.w;
   p.in_stride = a.in_stride;
   p.cin = L.cin;
   p.cin_pad = L.cin_pad;

@@ -585,8 +585,9 @@ int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPl
   // ---- A: im2col map over the NHWC input view, dims (C, W, H, N), box = kc channels x 128 pixels
   {
     cuuint64_t dims[4] = {(cuuint64_t)L.cin, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)a.n};
-    cuuint64_t strides[3] = {(cuuint64_t)a.in_stride * 2, (cuuint64_t)a.in_stride * 2 * a.w,
-                             (cuuint64_t)a.in_stride * 2 * a.w * a.h};
+    const cuuint64_t pitch_w = (cuuint64_t)(a.in_row_pitch ? a.in_row_pitch : a.w);  // physical pixels per row
+    cuuint64_t strides[3] = {(cuuint64_t)a.in_stride * 2, (cuuint64_t)a.in_stride * 2 * pitch_w,
+                             (cuuint64_t)a.in_stride * 2 * pitch_w * a.h};
     int lower[2] = {-L.pad_w, -L.pad_h};
     int upper[2] = {L.pad_w - (L.S - 1), L.pad_h - (L.R - 1)};
     cuuint32_t estr[4] = {1, (cuuint32_t)L.stride, (cuuint32_t)L.stride, 1};
@@ -601,7 +602,7 @@ int build_umma_plan(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, UmmaPl
     // (cute/atom/copy_traits_sm90_im2col.hpp) clears bit 21 of the second 64-bit word in that case.
     int drv = 0;
     cudaDriverGetVersion(&drv);
-    const size_t bytes = (size_t)a.n * a.h * a.w * a.in_stride * 2;
+    const size_t bytes = (size_t)a.n * a.h * pitch_w * a.in_stride * 2;
     if (drv <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(&plan->tm_a)[1] &= ~(1ull << 21);
   }
   // ---- B: packed weights [2 cout][ktot]; boxes of kc x nt rows (one plane) and kc x 2 nt rows (hi + lo)

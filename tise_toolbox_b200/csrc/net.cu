@@ -184,8 +184,11 @@ struct Builder {
   };
 
   // Creates (once) the packed layer holding the members' output channels back to back.
+  // fold_s: the S taps of a filter row become channels (cin' = S * cin, S' = 1): for stride-1, unpadded layers a
+  // window of S neighbouring NHWC pixels IS one contiguous run of S * cin channels, so e.g. Conv2d_4a (cin = 80:
+  // 9 taps x 2 chunks of which the second holds 16 channels) walks 3 x 4 K blocks instead of 18.
   const ConvLayer* layer(const std::string& key, const std::vector<Member>& ms, int cin, int R, int S, int stride, int ph,
-                         int pw, int force_kc = 0) {
+                         int pw, int force_kc = 0, bool fold_s = false) {
     auto it = net->convs.find(key);
     if (it != net->convs.end()) return &it->second;
     const int taps = R * S;
@@ -225,6 +228,17 @@ struct Builder {
     L.stride = stride;
     L.pad_h = ph;
     L.pad_w = pw;
+    if (fold_s) {  // w[co][ci][r][s] -> w'[co][s * cin + ci][r][0]
+      std::vector<float> w2(w.size());
+      for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+          for (int r = 0; r < R; ++r)
+            for (int sx = 0; sx < S; ++sx)
+              w2[((size_t)co * (S * cin) + (size_t)sx * cin + ci) * R + r] = w[(((size_t)co * cin + ci) * R + r) * S + sx];
+      w.swap(w2);
+      L.cin = S * cin;
+      L.S = 1;
+    }
     if ((rc = pack_conv_layer(ctx, &L, w.data(), scale.data(), shift.data(), &net->device_allocs, force_kc))) return nullptr;
     return &(net->convs[key] = L);
   }
@@ -264,6 +278,37 @@ struct Builder {
   }
   void conv(const std::string& name, View in, View out, int R = 1, int S = 1, int stride = 1, int ph = 0, int pw = 0) {
     conv_multi(name, in, {Member{name, out, false}}, R, S, stride, ph, pw);
+  }
+  // stride-1, unpadded R x S convolution evaluated as an R x 1 convolution over windows of S pixels (see layer())
+  void conv_folded(const std::string& name, View in, View out, int R, int S) {
+    if (rc) return;
+    const Buf& bi = bufs[in.buf];
+    const ConvLayer* L = layer(name, {Member{name, out, false}}, in.c, R, S, 1, 0, 0, 0, true);
+    if (!L) return;
+    const int ho = bi.h - R + 1, wo = bi.w - S + 1;
+    if (bufs[out.buf].h != ho || bufs[out.buf].w != wo || in.choff != 0 || in.c != bi.c) {
+      rc = fail(ctx, TISE_ERR_INVALID, "internal: folded conv %s does not match its buffers", name.c_str());
+      return;
+    }
+    if (!plan) return;
+    Step s;
+    s.kind = STEP_CONV;
+    s.layer = L;
+    s.conv.in = (const __half*)ptr(in);
+    s.conv.n = n;
+    s.conv.h = bi.h;
+    s.conv.w = wo;  // logical width: one "pixel" per output column
+    s.conv.in_row_pitch = bi.w;
+    s.conv.in_stride = bi.c;
+    s.conv.n_segs = 1;
+    s.conv.segs[0].out = ptr(out);
+    s.conv.segs[0].out_stride = bufs[out.buf].c;
+    s.conv.segs[0].c = out.c;
+    s.conv.segs[0].relu = 1;
+    s.conv.out_f32 = bufs[out.buf].f32;
+    s.conv.ho = ho;
+    s.conv.wo = wo;
+    plan->steps.push_back(s);
   }
   // flat convolution `name` from buffer `in` to buffer `out` (same physical grid); valid outputs ho x wo
   void flat(const std::string& name, int in, int out, int ho, int wo, int out_shift) {
@@ -462,7 +507,10 @@ struct Builder {
     // block 1
     const int c4 = buf(73, 73, 80), c5 = buf(71, 71, 192), p2 = buf(35, 35, 192);
     conv("Conv2d_3b_1x1", all(p1), all(c4));
-    conv("Conv2d_4a_3x3", all(c4), all(c5), 3, 3, 1, 0, 0);
+    static int fold_env = -1;
+    if (fold_env < 0) fold_env = getenv("TISE_FOLD_4A") ? atoi(getenv("TISE_FOLD_4A")) : 1;
+    if (fold_env) conv_folded("Conv2d_4a_3x3", all(c4), all(c5), 3, 3);
+    else conv("Conv2d_4a_3x3", all(c4), all(c5), 3, 3, 1, 0, 0);
     pool(STEP_MAXPOOL, all(c5), all(p2));
     if (tap == TISE_TAP_192) return gap(all(p2));
     // block 2

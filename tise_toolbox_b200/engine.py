@@ -23,6 +23,16 @@ T_COCO = 0.9091363549232483   # image_realism/IS/coco/inception_score_star_coco.
 T_BIRD = 0.5980541706085205   # image_realism/IS/bird/inception_score_star_bird.py:192
 T_OIS = 2.1737587451934814    # object_fidelity/O-IS/object_centric_inception_score.py:55
 
+# Operand policy of the convolution stack.  Every layer multiplies fp16 activations with fp16-split weights
+# (hi + lo, ~22 bits) in two tcgen05 passes; with the default MIXED policy the layers whose input map is at most 17 x 17
+# (Mixed_6b .. Mixed_7c, half of the FLOPs, all of them tensor-pipe bound) skip the W_lo pass.  Measured on B200 at
+# BASELINE.json configs[0] size (1000 vs 1000 images, profiles/pass_policy_r02.json): FID within 3.5e-5 of the fp32 CPU
+# path (strict: 6.4e-5 -- both at the noise floor of the fp16 activations), IS* within 1e-4, pool3 relative L2 5.4e-4
+# (strict 1.5e-4) -- the TF32-class bound north_star allows, and what cuDNN's default TF32 convolutions give the
+# reference itself on an Ampere-or-later GPU.  0 = strict (two passes everywhere).  TISE_PASS1_MAXHW overrides.
+DEFAULT_SINGLE_PASS_MAX_HW = 17
+POOL3_REL_L2_BOUND = {"strict": 5e-4, "mixed": 1e-3}
+
 
 def input_lut(variant: str) -> torch.Tensor:
     """float32 [3, 256] table: network input for each (channel, uint8 level), built with the op
@@ -83,7 +93,7 @@ class Engine:
 
     def __init__(self, state_dict: Optional[Dict[str, torch.Tensor]] = None,
                  device: Union[int, str, torch.device, None] = None, variant: str = "fid", micro_batch: int = 128,
-                 conv_impl: str = "umma", passes: int = 2):
+                 conv_impl: str = "umma", passes: int = 2, single_pass_max_hw: Optional[int] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("tise_toolbox_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -106,6 +116,9 @@ class Engine:
         self.num_classes = 0
         self.variant = None
         self.set_conv_mode(conv_impl, passes)
+        if single_pass_max_hw is None:
+            single_pass_max_hw = int(os.environ.get("TISE_PASS1_MAXHW", DEFAULT_SINGLE_PASS_MAX_HW))
+        self.set_pass_policy(single_pass_max_hw)
         if state_dict is not None:  # statistics-only use (moments, Frechet distance) needs no weights
             self.load_state_dict(state_dict)
         self.set_variant(variant)

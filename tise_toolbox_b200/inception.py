@@ -33,7 +33,8 @@ class InceptionV3(nn.Module):
     BLOCK_INDEX_BY_DIM = {64: 0, 192: 1, 768: 2, 2048: 3}
 
     def __init__(self, output_blocks=[DEFAULT_BLOCK_INDEX], resize_input=True, normalize_input=True,
-                 requires_grad=False, state_dict=None, weights_path=None, device=None, micro_batch=512, engine=None):
+                 requires_grad=False, state_dict=None, weights_path=None, device=None, micro_batch=512, engine=None,
+                 single_pass_max_hw=None):
         super(InceptionV3, self).__init__()
         self.resize_input = resize_input
         self.normalize_input = normalize_input
@@ -51,7 +52,8 @@ class InceptionV3(nn.Module):
                 raise RuntimeError("InceptionV3: pass state_dict= / weights_path= or set TISE_INCEPTION_WEIGHTS to a "
                                    "torchvision Inception3 state_dict (no download is attempted)")
             state_dict = load_state_dict_file(weights_path)
-        self.engine = Engine(state_dict, device=device, variant="fid", micro_batch=micro_batch)
+        self.engine = Engine(state_dict, device=device, variant="fid", micro_batch=micro_batch,
+                             single_pass_max_hw=single_pass_max_hw)
 
     # the reference calls model.cuda() / model.eval(); both are no-ops here (always CUDA, always eval)
     def cuda(self, device=None):
