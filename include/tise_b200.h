@@ -63,6 +63,11 @@ int tise_set_conv_mode(tise_ctx* ctx, int impl, int passes);
 /* mixed operand policy: with passes = 2, convolutions whose INPUT map is at most `single_pass_max_hw`
  * pixels high (0 = none, the default) skip the W_lo pass.  Measured trade-off: DESIGN.md section 2. */
 int tise_set_pass_policy(tise_ctx* ctx, int single_pass_max_hw);
+/* One-off calibration of the single-pass layers (after tise_load_inception and tise_set_input_lut; synchronous): a strict
+ * forward pass over `n_images` synthetic images generated on the device measures the mean activation of every
+ * convolution input, and  shift += scale * (W_lo . mean)  becomes the shift of the layer's single-pass form -- the
+ * image-independent part of the dropped W_lo product.  `d_ws`: tise_inception_workspace_bytes(ctx, n_images) bytes. */
+int tise_calibrate_single_pass(tise_ctx* ctx, int n_images, void* d_ws, size_t ws_bytes, tise_stream stream);
 
 /* ---- weights -------------------------------------------------------------------------- */
 /* One tensor of a torchvision Inception3 state_dict (fp32, host, contiguous), e.g.

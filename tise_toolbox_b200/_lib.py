@@ -46,6 +46,7 @@ _SIGNATURES = {
     "tise_last_error": (C.c_char_p, [c_ctx_p]),
     "tise_set_conv_mode": (C.c_int, [c_ctx_p, C.c_int, C.c_int]),
     "tise_set_pass_policy": (C.c_int, [c_ctx_p, C.c_int]),
+    "tise_calibrate_single_pass": (C.c_int, [c_ctx_p, C.c_int, C.c_void_p, C.c_size_t, c_stream]),
     "tise_load_inception": (C.c_int, [c_ctx_p, C.POINTER(WeightDesc), C.c_int, C.c_int]),
     "tise_resize_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "tise_resize_u8": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,

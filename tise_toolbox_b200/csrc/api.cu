@@ -97,6 +97,13 @@ extern "C" int tise_load_inception(tise_ctx* ctx, const tise_weight_desc* tensor
   return rc;
 }
 
+extern "C" int tise_calibrate_single_pass(tise_ctx* ctx, int n_images, void* d_ws, size_t ws_bytes, tise_stream stream) {
+  if (!ctx) return TISE_ERR_INVALID;
+  if (!d_ws) return fail(ctx, TISE_ERR_INVALID, "tise_calibrate_single_pass: null workspace");
+  TISE_CUDA(ctx, cudaSetDevice(ctx->device));
+  return net_calibrate_lo(ctx, n_images, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
 extern "C" size_t tise_inception_workspace_bytes(const tise_ctx* ctx, int n) {
   if (!ctx || !ctx->net || n <= 0) return 0;
   size_t m = 0;

@@ -107,6 +107,11 @@ struct ConvLayer {
   __half* d_w = nullptr;    // [2 * cout][ktot], see above
   float* d_scale = nullptr;  // [cout]  gamma / sqrt(var + eps) * 2^-e
   float* d_shift = nullptr;  // [cout]  beta - mean * gamma / sqrt(var + eps)
+  // [cout] shift of the SINGLE-PASS form of the layer: d_shift + d_scale * (W_lo . mean input activation).  The dropped
+  // W_lo pass is a systematic (image-independent to first order) offset of the output; its mean-field value is added
+  // back here (net.cu: net_calibrate_lo).  Equal to d_shift until calibrated.
+  float* d_shift1 = nullptr;
+  int fold = 1;              // filter taps folded into the channel axis (cin = fold * physical channels), see net.cu
 };
 int conv_chunk_of(int cin);
 int conv_ntile_of(int cout);

@@ -649,7 +649,7 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   if (!plan.valid) return fail(ctx, TISE_ERR_STATE, "umma conv: plan not built");
   UmmaParams p;
   p.scale = L.d_scale;
-  p.shift = L.d_shift;
+  p.shift = (passes == 1 && L.d_shift1) ? L.d_shift1 : L.d_shift;
   p.M = (long long)a.n * a.ho * a.wo;
   int end = 0;
   for (int i = 0; i < kMaxSegs; ++i) {

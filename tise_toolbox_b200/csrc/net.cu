@@ -113,9 +113,11 @@ int pack_conv_layer(tise_ctx* ctx, ConvLayer* L, const float* w, const float* sc
   if ((rc = dev_alloc(ctx, allocs, (void**)&L->d_w, n * sizeof(__half)))) return rc;
   if ((rc = dev_alloc(ctx, allocs, (void**)&L->d_scale, L->cout * sizeof(float)))) return rc;
   if ((rc = dev_alloc(ctx, allocs, (void**)&L->d_shift, L->cout * sizeof(float)))) return rc;
+  if ((rc = dev_alloc(ctx, allocs, (void**)&L->d_shift1, L->cout * sizeof(float)))) return rc;
   TISE_CUDA(ctx, cudaMemcpy(L->d_w, wp.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
   TISE_CUDA(ctx, cudaMemcpy(L->d_scale, sc.data(), L->cout * sizeof(float), cudaMemcpyHostToDevice));
   TISE_CUDA(ctx, cudaMemcpy(L->d_shift, sh.data(), L->cout * sizeof(float), cudaMemcpyHostToDevice));
+  TISE_CUDA(ctx, cudaMemcpy(L->d_shift1, sh.data(), L->cout * sizeof(float), cudaMemcpyHostToDevice));
   return TISE_OK;
 }
 
@@ -238,6 +240,7 @@ struct Builder {
       w.swap(w2);
       L.cin = S * cin;
       L.S = 1;
+      L.fold = S;
     }
     if ((rc = pack_conv_layer(ctx, &L, w.data(), scale.data(), shift.data(), &net->device_allocs, force_kc))) return nullptr;
     return &(net->convs[key] = L);
@@ -624,6 +627,123 @@ static int get_plan(tise_ctx* ctx, void* ws, int n, int tap, Plan** out) {
   net->plans.push_back(std::move(plan));
   *out = net->plans.back().get();
   return TISE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-pass calibration ("mean-field W_lo").  A layer run with W_hi only is off by  sum_k W_lo[co][k] a_k, whose
+// image-independent part  sum_k W_lo[co][k] mean(a_k)  is what moves the feature MEAN (and with it IS and any FID
+// against statistics computed elsewhere); the rest is zero-mean noise of the size of the fp16 activation rounding.
+// The channel means of every convolution input are measured once, on a fixed set of synthetic images generated here
+// (they are a property of the network's BatchNorm shifts far more than of the images: calibrating on other image
+// distributions, even white noise, gives the same result to ~1e-5 -- tools/bias_correction_probe.py), and folded into
+// the shift of the single-pass form of the layer.  Nothing here depends on the caller's data, so results stay a pure
+// function of (weights, images).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t calib_hash(uint32_t h) {
+  h ^= h >> 15;
+  h *= 0x85EBCA77u;
+  h ^= h >> 13;
+  h *= 0xC2B2AE3Du;
+  h ^= h >> 16;
+  return h;
+}
+// smooth random colour fields (5 x 5 control grid, bilinear) with per-image gain and pixel noise: uint8 [n][299][299][3]
+__global__ void calib_images_kernel(uint8_t* out, int n) {
+  const size_t total = (size_t)n * kOutSize * kOutSize * 3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % 3);
+    size_t p = i / 3;
+    const int x = (int)(p % kOutSize);
+    p /= kOutSize;
+    const int y = (int)(p % kOutSize), img = (int)(p / kOutSize);
+    const int fy = y * 4 * 256 / kOutSize, fx = x * 4 * 256 / kOutSize;  // 8.8 fixed point, 4 cells across
+    const int iy = min(fy >> 8, 3), ix = min(fx >> 8, 3), ay = fy - (iy << 8), ax = fx - (ix << 8);
+    auto g = [&](int gy, int gx) { return (int)(calib_hash((uint32_t)(((img * 5 + gy) * 5 + gx) * 3 + c) + 0x9E3779B1u) & 255u); };
+    const int top = g(iy, ix) * (256 - ax) + g(iy, ix + 1) * ax, bot = g(iy + 1, ix) * (256 - ax) + g(iy + 1, ix + 1) * ax;
+    const int v = (top * (256 - ay) + bot * ay) >> 16;
+    const int gain = 128 + (int)(calib_hash((uint32_t)img * 2654435761u + 77u) & 255u);
+    const int noise = (int)(calib_hash((uint32_t)i + 0x7F4A7C15u) & 63u) - 32;
+    out[i] = (uint8_t)max(0, min(255, ((v * gain) >> 8) + noise));
+  }
+}
+// sum[c] += sum over pixels of in[pixel * stride + c]   (32 channels x 8 pixel lanes per CTA)
+__global__ void __launch_bounds__(256) channel_sum_kernel(const __half* __restrict__ in, long long pixels, int stride, int c_total,
+                                                          double* __restrict__ sum) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (c >= c_total) return;
+  double acc = 0.0;
+  for (long long p = (long long)blockIdx.y * 8 + (threadIdx.x >> 5); p < pixels; p += (long long)gridDim.y * 8)
+    acc += (double)__half2float(in[p * stride + c]);
+  atomicAdd(sum + c, acc);
+}
+// shift1[co] = shift[co] + scale[co] * sum_k W_lo[co][k] * mean[channel of k]      (one warp per output channel)
+__global__ void __launch_bounds__(256) lo_correction_kernel(const __half* __restrict__ w, int ktot, int cin_pad, int cin, int cin_phys,
+                                                            int nt, int cout, const double* __restrict__ sum, double inv_pixels,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            float* __restrict__ shift1) {
+  const int co = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (co >= cout) return;
+  const __half* lo = w + (((size_t)(co / nt) * 2 + 1) * nt + co % nt) * ktot;
+  double acc = 0.0;
+  for (int k = lane; k < ktot; k += 32) {
+    const int cc = k % cin_pad;
+    if (cc < cin) acc += (double)__half2float(lo[k]) * (sum[cc % cin_phys] * inv_pixels);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) shift1[co] = shift[co] + scale[co] * (float)acc;
+}
+
+static int get_plan(tise_ctx* ctx, void* ws, int n, int tap, Plan** out);
+
+int net_calibrate_lo(tise_ctx* ctx, int n, void* d_ws, size_t ws_bytes, cudaStream_t st) {
+  Net* net = ctx->net;
+  if (!net) return fail(ctx, TISE_ERR_STATE, "tise_calibrate_single_pass: weights not loaded");
+  if (!ctx->lut_set) return fail(ctx, TISE_ERR_STATE, "tise_calibrate_single_pass: input LUT not set");
+  if (n < 1 || n > 4096) return fail(ctx, TISE_ERR_INVALID, "tise_calibrate_single_pass: n = %d", n);
+  uint8_t* d_img = nullptr;
+  float* d_feat = nullptr;
+  double* d_sum = nullptr;
+  TISE_CUDA(ctx, cudaMalloc(&d_img, (size_t)n * kOutSize * kOutSize * 3));
+  TISE_CUDA(ctx, cudaMalloc(&d_feat, (size_t)n * 2048 * sizeof(float)));
+  TISE_CUDA(ctx, cudaMalloc(&d_sum, 4096 * sizeof(double)));
+  calib_images_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(d_img, n);
+  // strict forward: every activation tensor of the graph ends up in the workspace (no buffer is reused)
+  const int keep_passes = ctx->passes, keep_hw = ctx->pass1_max_hw, keep_impl = ctx->conv_impl;
+  const bool keep_prof = ctx->profiling;
+  ctx->passes = 2;
+  ctx->pass1_max_hw = 0;
+  ctx->conv_impl = TISE_CONV_UMMA;
+  ctx->profiling = false;
+  int rc = net_forward(ctx, d_img, nullptr, n, TISE_TAP_2048, d_feat, d_ws, ws_bytes, st);
+  Plan* plan = nullptr;
+  if (!rc) rc = get_plan(ctx, d_ws, n, TISE_TAP_2048, &plan);
+  ctx->passes = keep_passes;
+  ctx->pass1_max_hw = keep_hw;
+  ctx->conv_impl = keep_impl;
+  ctx->profiling = keep_prof;
+  if (!rc) {
+    for (Step& s : plan->steps) {
+      if (s.kind != STEP_CONV) continue;
+      const ConvLayer& L = *s.layer;
+      const int cin_phys = L.cin / L.fold;
+      const long long pixels = (long long)s.conv.n * s.conv.h * (s.conv.in_row_pitch ? s.conv.in_row_pitch : s.conv.w);
+      cudaMemsetAsync(d_sum, 0, 4096 * sizeof(double), st);
+      int slices = (int)((pixels + 8 * 64 - 1) / (8 * 64));
+      if (slices > 1024) slices = 1024;
+      if (slices < 1) slices = 1;
+      channel_sum_kernel<<<dim3((cin_phys + 31) / 32, slices), 256, 0, st>>>(s.conv.in, pixels, s.conv.in_stride, cin_phys, d_sum);
+      lo_correction_kernel<<<(L.cout + 7) / 8, 256, 0, st>>>(L.d_w, L.ktot, L.cin_pad, L.cin, cin_phys, L.nt, L.cout, d_sum,
+                                                            1.0 / (double)pixels, L.d_scale, L.d_shift, L.d_shift1);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(ctx, TISE_ERR_CUDA, "tise_calibrate_single_pass: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_img);
+  cudaFree(d_feat);
+  cudaFree(d_sum);
+  return rc;
 }
 
 int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, int tap, float* d_feat, void* d_ws,

@@ -59,6 +59,7 @@ struct Net {
 
 int net_load(tise_ctx* ctx, const tise_weight_desc* tensors, int n_tensors, int num_classes);
 void net_free(tise_ctx* ctx);
+int net_calibrate_lo(tise_ctx* ctx, int n, void* d_ws, size_t ws_bytes, cudaStream_t st);
 int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, int tap, float* d_feat, void* d_ws,
                 size_t ws_bytes, cudaStream_t st);
 int pack_conv_layer(tise_ctx* ctx, ConvLayer* L, const float* w /*[cout][cin][R][S]*/, const float* scale,

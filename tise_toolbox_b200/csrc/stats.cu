@@ -1,6 +1,7 @@
 // Statistics path: fc head, FID moments (A7) and inception-score partial sums (A11-A13).
 // All of it is a few MFLOP per image next to the trunk's 11.4 GFLOP, so these kernels favour
-// precision (fp64 accumulation of exact fp32 products) and simple coalesced access over tensor cores.
+// precision (fp64 accumulation of exact fp32 products): the covariance sums run as an fp64 SYRK on the tensor pipe
+// (DMMA), the fc head and the softmax / KL sums as plain coalesced kernels.
 #include "net.cuh"
 
 namespace tise {
@@ -54,10 +55,24 @@ __global__ void moments_sum_kernel(const float* __restrict__ x, int n, int d, do
   atomicAdd(sum + j, acc);
 }
 
-// sxx[a][b] += sum_i x[i][a] x[i][b] for the 64 x 64 tile (ta >= tb) of the lower triangle.
-// 256 threads, 4 x 4 fp64 accumulators each; images streamed 16 at a time through shared memory.
-constexpr int MT = 64, MK = 16, MCHUNK = 256;
-__global__ void __launch_bounds__(256) moments_sxx_kernel(const float* __restrict__ x, int n, int d,
+// sxx[a][b] += sum_i x[i][a] x[i][b] for the lower triangle: a SYRK on the fp64 TENSOR pipe
+// (mma.sync.m8n8k4.f64 -> DMMA), exact to fp64 rounding like the FMA kernel it replaces (fid_score.py:194-195's
+// np.cov is an fp64 GEMM too).  One CTA owns a 128 x 128 tile (ta >= tb) for a chunk of up to 1024 images: 16 warps,
+// each a 32 x 32 sub-tile = 4 x 4 DMMA tiles (32 fp64 accumulators per thread); the images stream through shared
+// memory 16 at a time as doubles (fp32 -> fp64 is exact), register-prefetched one chunk ahead.  Fragment layout of
+// m8n8k4 (PTX ISA): lane T holds A[T / 4][T % 4], B[T % 4][T / 4] and C[T / 4][2 (T % 4) + {0, 1}]; with A = X^T and
+// B = X both fragments are the same kind of read, xs[k0 + T % 4][col0 + T / 4] -- a row pitch of 132 doubles makes it
+// conflict-free.  One red.add.f64 per accumulator at the end (the K split over CTAs is the only sharing).
+constexpr int ST = 128, SKC = 16, SPITCH = ST + 4, SCHUNK = 1024;
+constexpr int MT = 64;  // d must be a multiple of 64 (a last half tile is masked)
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(512) moments_sxx_kernel(const float* __restrict__ x, int n, int d,
                                                           double* __restrict__ sxx) {
   // blockIdx.x enumerates lower-triangular tile pairs
   int t = blockIdx.x, ta = 0;
@@ -66,42 +81,57 @@ __global__ void __launch_bounds__(256) moments_sxx_kernel(const float* __restric
     ++ta;
   }
   const int tb = t;
-  __shared__ double sa[MK][MT + 1];
-  __shared__ double sb[MK][MT + 1];
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  double acc[4][4];
+  __shared__ double sa[SKC][SPITCH];
+  __shared__ double sb[SKC][SPITCH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wa = (warp >> 2) * 32, wb = (warp & 3) * 32;  // this warp's 32 x 32 sub-tile
+  const int fr = lane >> 2, fk = lane & 3;
+  double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  const int i0 = blockIdx.y * MCHUNK, i1 = min(n, i0 + MCHUNK);
-  for (int k0 = i0; k0 < i1; k0 += MK) {
-    for (int i = threadIdx.x; i < MK * MT; i += 256) {
-      const int k = i / MT, c = i % MT;
-      const bool ok = k0 + k < i1;
-      sa[k][c] = ok ? (double)x[(size_t)(k0 + k) * d + ta * MT + c] : 0.0;
-      sb[k][c] = ok ? (double)x[(size_t)(k0 + k) * d + tb * MT + c] : 0.0;
-    }
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int i0 = blockIdx.y * SCHUNK, i1 = min(n, i0 + SCHUNK);
+  // loader: thread -> (image k = tid / 32, 4 consecutive columns c = 4 (tid % 32)) of both column blocks
+  const int lk = threadIdx.x >> 5, lc = (threadIdx.x & 31) * 4;
+  const int ca = ta * ST + lc, cb = tb * ST + lc;
+  float4 ra, rb;
+  auto fetch = [&](int k0) {
+    const int img = k0 + lk;
+    const bool ok = img < i1;
+    ra = (ok && ca < d) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)img * d + ca)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = (ok && cb < d) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)img * d + cb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  fetch(i0);
+  for (int k0 = i0; k0 < i1; k0 += SKC) {
+    sa[lk][lc] = (double)ra.x; sa[lk][lc + 1] = (double)ra.y; sa[lk][lc + 2] = (double)ra.z; sa[lk][lc + 3] = (double)ra.w;
+    sb[lk][lc] = (double)rb.x; sb[lk][lc + 1] = (double)rb.y; sb[lk][lc + 2] = (double)rb.z; sb[lk][lc + 3] = (double)rb.w;
     __syncthreads();
+    if (k0 + SKC < i1) fetch(k0 + SKC);  // next chunk in flight during the DMMAs
 #pragma unroll
-    for (int k = 0; k < MK; ++k) {
-      double av[4], bv[4];
+    for (int kk = 0; kk < SKC; kk += 4) {
+      double af[4], bf[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = sa[k][ty * 4 + i];
+      for (int i = 0; i < 4; ++i) af[i] = sa[kk + fk][wa + 8 * i + fr];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = sb[k][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) bf[j] = sb[kk + fk][wb + 8 * j + fr];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
     __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      atomicAdd(sxx + (size_t)(ta * MT + ty * 4 + i) * d + tb * MT + tx * 4 + j, acc[i][j]);
+    for (int j = 0; j < 4; ++j) {
+      const int a = ta * ST + wa + 8 * i + fr, b = tb * ST + wb + 8 * j + 2 * fk;
+      if (a < d && b < d) {  // (tiles on the diagonal also fill their upper half: the finalize kernel reads a >= b only)
+        atomicAdd(sxx + (size_t)a * d + b, acc[i][j][0]);
+        atomicAdd(sxx + (size_t)a * d + b + 1, acc[i][j][1]);
+      }
+    }
 }
 
 // mu = sum / count; sigma[a][b] = (sxx[max][min] - count mu_a mu_b) / (count - 1)
@@ -206,8 +236,8 @@ extern "C" int tise_moments_update(tise_ctx* ctx, const float* d_feat, int n, in
   cudaStream_t st = (cudaStream_t)stream;
   moments_sum_kernel<<<dim3((d + 255) / 256, (n + 255) / 256), 256, 0, st>>>(d_feat, n, d, d_sum);
   TISE_LAUNCH_CHECK(ctx);
-  const int tiles = d / MT;
-  moments_sxx_kernel<<<dim3(tiles * (tiles + 1) / 2, (n + MCHUNK - 1) / MCHUNK), 256, 0, st>>>(d_feat, n, d, d_sxx);
+  const int tiles = (d + ST - 1) / ST;
+  moments_sxx_kernel<<<dim3(tiles * (tiles + 1) / 2, (n + SCHUNK - 1) / SCHUNK), 512, 0, st>>>(d_feat, n, d, d_sxx);
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;
 }

@@ -23,15 +23,18 @@ T_COCO = 0.9091363549232483   # image_realism/IS/coco/inception_score_star_coco.
 T_BIRD = 0.5980541706085205   # image_realism/IS/bird/inception_score_star_bird.py:192
 T_OIS = 2.1737587451934814    # object_fidelity/O-IS/object_centric_inception_score.py:55
 
-# Operand policy of the convolution stack.  Every layer multiplies fp16 activations with fp16-split weights
-# (hi + lo, ~22 bits) in two tcgen05 passes; with the default MIXED policy the layers whose input map is at most 17 x 17
-# (Mixed_6b .. Mixed_7c, half of the FLOPs, all of them tensor-pipe bound) skip the W_lo pass.  Measured on B200 at
-# BASELINE.json configs[0] size (1000 vs 1000 images, profiles/pass_policy_r02.json): FID within 3.5e-5 of the fp32 CPU
-# path (strict: 6.4e-5 -- both at the noise floor of the fp16 activations), IS* within 1e-4, pool3 relative L2 5.4e-4
-# (strict 1.5e-4) -- the TF32-class bound north_star allows, and what cuDNN's default TF32 convolutions give the
-# reference itself on an Ampere-or-later GPU.  0 = strict (two passes everywhere).  TISE_PASS1_MAXHW overrides.
-DEFAULT_SINGLE_PASS_MAX_HW = 17
-POOL3_REL_L2_BOUND = {"strict": 5e-4, "mixed": 1e-3}
+# Operand policy of the convolution stack.  Weights are split offline into fp16 hi + lo planes (~22 bits).
+#   strict  (single_pass_max_hw = 0): every layer multiplies its fp16 activations with W_hi AND W_lo, two tcgen05 passes.
+#   default (single_pass_max_hw = SINGLE_PASS_ALL): the tcgen05 implicit-GEMM layers issue the W_hi pass only, and the
+#           image-independent part of the dropped product, W_lo . mean(activation), is folded into the layer's shift
+#           by a one-off calibration at load time (tise_calibrate_single_pass: synthetic images generated on the
+#           device; the correction is a property of the weights, not of the caller's data).  What remains of the W_lo
+#           term is zero-mean noise of the size of the fp16 activation rounding.
+# Measured on B200 at BASELINE.json configs[0] size: see DESIGN.md §2 / profiles/.  TISE_PASS1_MAXHW overrides.
+SINGLE_PASS_ALL = 1 << 20
+DEFAULT_SINGLE_PASS_MAX_HW = SINGLE_PASS_ALL
+CALIBRATION_IMAGES = 32
+POOL3_REL_L2_BOUND = {"strict": 5e-4, "default": 5e-4, "uncorrected": 1e-3}
 
 
 def input_lut(variant: str) -> torch.Tensor:
@@ -119,9 +122,11 @@ class Engine:
         if single_pass_max_hw is None:
             single_pass_max_hw = int(os.environ.get("TISE_PASS1_MAXHW", DEFAULT_SINGLE_PASS_MAX_HW))
         self.set_pass_policy(single_pass_max_hw)
+        self.calibrated = False
+        self._calibrate = os.environ.get("TISE_LO_CALIBRATION", "1") != "0"
+        self.set_variant(variant)
         if state_dict is not None:  # statistics-only use (moments, Frechet distance) needs no weights
             self.load_state_dict(state_dict)
-        self.set_variant(variant)
 
     # ------------------------------------------------------------------ setup
     def close(self):
@@ -143,9 +148,17 @@ class Engine:
         self.conv_impl, self.passes = conv_impl, int(passes)
 
     def set_pass_policy(self, single_pass_max_hw: int = 0):
-        """Convolutions whose input map is at most this many pixels high skip the W_lo pass (0: none)."""
+        """Convolutions whose input map is at most this many pixels high skip the W_lo pass (0: none = strict)."""
         self._check(self.lib.tise_set_pass_policy(self.ctx, int(single_pass_max_hw)))
         self.pass1_max_hw = int(single_pass_max_hw)
+
+    def calibrate_single_pass(self, n_images: int = CALIBRATION_IMAGES):
+        """Mean-field W_lo correction of the single-pass layers (tise_calibrate_single_pass); needs weights and LUT."""
+        need = int(self.lib.tise_inception_workspace_bytes(self.ctx, n_images))
+        ws = self._buf("_ws", need)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.tise_calibrate_single_pass(self.ctx, int(n_images), ws.data_ptr(), ws.numel(), _stream()))
+        self.calibrated = True
 
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor]):
         keep, descs = [], []
@@ -160,6 +173,9 @@ class Engine:
         with torch.cuda.device(self.device):
             self._check(self.lib.tise_load_inception(self.ctx, arr, len(descs), num_classes))
         self.num_classes = num_classes
+        self.calibrated = False
+        if self._calibrate and self.conv_impl == "umma":  # (cheap: one 32-image forward + ~90 tiny kernels)
+            self.calibrate_single_pass()
 
     def set_variant(self, variant: str):
         if variant == self.variant:

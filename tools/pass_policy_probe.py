@@ -32,7 +32,10 @@ def main():
     ref = [harness.oracle_pool3(sd, s, "fid") for s in sets]
     cpu_s = time.perf_counter() - t0
     np.savez_compressed(os.path.join(os.path.dirname(out_path), "oracle_pool3_cfg1.npz"), a=ref[0], b=ref[1])
-    eng = Engine(sd, device="cuda:0", micro_batch=500)
+    eng = Engine(sd, device="cuda:0", micro_batch=500)  # mean-field W_lo correction calibrated at load
+    os.environ["TISE_LO_CALIBRATION"] = "0"
+    eng_raw = Engine(sd, device="cuda:0", micro_batch=500)  # single-pass layers without the correction
+    del os.environ["TISE_LO_CALIBRATION"]
 
     def gpu_fid(fa, fb):
         st = []
@@ -49,17 +52,20 @@ def main():
     res = {"n_per_set": n, "cpu_oracle_s": cpu_s, "cpu_cores": os.cpu_count(), "fid_oracle_scipy": fid_scipy,
            "fid_oracle_feats_gpu_frechet": fid_ref, "scipy_fid_s": scipy_s, "policies": []}
     dsets = [s.cuda() for s in sets]
-    for name, passes, hw in [("2pass_all", 2, 0), ("1pass_hw<=8", 2, 8), ("1pass_hw<=17", 2, 17), ("1pass_hw<=35", 2, 35),
-                             ("1pass_hw<=73", 2, 73), ("1pass_all", 1, 0)]:
-        eng.set_conv_mode("umma", passes)
-        eng.set_pass_policy(hw)
-        feats = [eng.features(d) for d in dsets]  # also warms up the plans of this policy
+    for name, e, passes, hw in [("strict (2 passes)", eng, 2, 0),
+                                ("1pass hw<=17 calibrated", eng, 2, 17), ("1pass hw<=35 calibrated", eng, 2, 35),
+                                ("1pass all umma layers calibrated (default)", eng, 2, 1 << 20),
+                                ("1pass hw<=17 uncorrected", eng_raw, 2, 17), ("1pass all umma layers uncorrected", eng_raw, 2, 1 << 20)]:
+        e.set_conv_mode("umma", passes)
+        e.set_pass_policy(hw)
+        gpu_feats = e.features
+        feats = [gpu_feats(d) for d in dsets]  # also warms up the plans of this policy
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(3):
             for d in dsets:
-                eng.features(d)
+                gpu_feats(d)
         e1.record()
         torch.cuda.synchronize()
         ips = 3 * 2 * n / (e0.elapsed_time(e1) / 1e3)
