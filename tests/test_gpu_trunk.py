@@ -48,7 +48,7 @@ def test_pool3_parity(engine, batch, oracle_blocks, impl, passes):
 def test_pool3_parity_default_policy(engine, batch, oracle_blocks):
     """The default operand policy: the tcgen05 implicit-GEMM layers run the W_hi pass only, with the mean-field W_lo
     correction folded into their shift at load time (tise_calibrate_single_pass).  Same pool3 bound as the strict
-    two-pass policy; the flat stem layers (block 0) are untouched by it."""
+    two-pass policy; the block-0 tap (the flat stem layers, single pass too) stays within its own bound."""
     from tise_toolbox_b200.engine import POOL3_REL_L2_BOUND, SINGLE_PASS_ALL
 
     engine.set_variant("fid")
@@ -65,7 +65,9 @@ def test_pool3_parity_default_policy(engine, batch, oracle_blocks):
     assert not np.array_equal(single, strict)  # the policy is live
     assert _rel_l2(single, ref) <= POOL3_REL_L2_BOUND["default"], "pool3 rel L2 %.3e" % _rel_l2(single, ref)
     assert _rel_l2(strict, ref) <= POOL3_REL_L2_BOUND["strict"]
-    assert np.array_equal(tap64, tap64_single)
+    ref64 = oracle_blocks[1][0].mean(dim=(2, 3)).numpy()
+    assert not np.array_equal(tap64, tap64_single)
+    assert _rel_l2(tap64_single, ref64) <= 1e-3 and _rel_l2(tap64, ref64) <= 1e-3
 
 
 @pytest.mark.parametrize("dims,block", [(64, 0), (192, 1), (768, 2)])

@@ -36,6 +36,15 @@ def test_split_ids_are_independent_of_sharding():
         assert np.array_equal(np.concatenate(parts), full)
 
 
+def test_split_ids_device_form_equals_host_form():
+    for variant in ("ois", "coco", "bird"):
+        for n, splits in [(100, 10), (101, 10), (7, 10), (64, 3), (30000, 10), (5, 1)]:
+            for start, count in [(0, n), (n // 3, n - n // 3), (n - 1, 4)]:
+                host = isc.split_ids(n, splits, variant, start, count)
+                dev = isc.split_ids_device(n, splits, variant, start, count, "cpu")
+                assert dev.dtype == torch.int32 and np.array_equal(host, dev.numpy()), (variant, n, splits, start, count)
+
+
 def test_shard_range_partitions_exactly():
     for n in (0, 1, 7, 30000, 200001):
         for world in (1, 2, 4, 8):

@@ -45,10 +45,39 @@ extern "C" int tise_ctx_create(int device, tise_ctx** out) {
   return TISE_OK;
 }
 
+int tise::stage_upload(tise_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return TISE_OK;
+  tise_ctx::StageSlot& sl = ctx->stage[ctx->stage_next];
+  ctx->stage_next = (ctx->stage_next + 1) % tise_ctx::kStageSlots;
+  if (sl.pending) {  // only blocks when the host is kStageSlots uploads ahead of the GPU
+    TISE_CUDA(ctx, cudaEventSynchronize(sl.done));
+    sl.pending = false;
+  }
+  if (sl.bytes < bytes) {
+    if (sl.host) TISE_CUDA(ctx, cudaFreeHost(sl.host));
+    sl.host = nullptr;
+    sl.bytes = 0;
+    const size_t want = bytes < 65536 ? 65536 : bytes + bytes / 4;
+    TISE_CUDA(ctx, cudaMallocHost(&sl.host, want));
+    sl.bytes = want;
+  }
+  if (!sl.done) TISE_CUDA(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  memcpy(sl.host, h_src, bytes);
+  TISE_CUDA(ctx, cudaMemcpyAsync(d_dst, sl.host, bytes, cudaMemcpyHostToDevice, st));
+  TISE_CUDA(ctx, cudaEventRecord(sl.done, st));
+  sl.pending = true;
+  return TISE_OK;
+}
+
 extern "C" void tise_ctx_destroy(tise_ctx* ctx) {
   if (!ctx) return;
   DeviceRestore restore;
   cudaSetDevice(ctx->device);
+  for (auto& sl : ctx->stage) {
+    if (sl.pending) cudaEventSynchronize(sl.done);
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.host) cudaFreeHost(sl.host);
+  }
   net_free(ctx);
   if (ctx->d_lut) cudaFree(ctx->d_lut);
   delete ctx;

@@ -41,6 +41,18 @@ struct tise_ctx {
     char tag[96];
   };
   std::vector<ProfRec> prof;
+  // Pinned staging ring for the small host -> device uploads of per-call descriptors.  A cudaMemcpyAsync from PAGEABLE
+  // memory synchronises the stream before it copies, i.e. the host stalls behind everything queued so far and can
+  // never run ahead of the GPU (measured: the H2D copy of the next batch then no longer overlaps the trunk).
+  static constexpr int kStageSlots = 16;
+  struct StageSlot {
+    void* host = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t done = nullptr;
+    bool pending = false;
+  };
+  StageSlot stage[kStageSlots];
+  int stage_next = 0;
 };
 
 namespace tise {
@@ -85,6 +97,9 @@ struct DeviceRestore {
     if (prev >= 0) cudaSetDevice(prev);
   }
 };
+
+// host buffer -> device, truly asynchronous on `st` (see tise_ctx::stage): the bytes are copied into a pinned slot first
+int stage_upload(tise_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -168,14 +183,14 @@ struct FlatArgs {
   int out_shift = 0;           // output position = input position + out_shift (e.g. wp + 1 to centre for a pad-1 consumer)
   int relu = 1;
 };
-struct FlatPlan {
-  alignas(64) CUtensorMap tm_a;
-  alignas(64) CUtensorMap tm_w;
+struct FlatPlan {  // index 0: single-pass form (W_hi rows only), 1: two-pass form (hi | lo rows)
+  alignas(64) CUtensorMap tm_a[2];
+  alignas(64) CUtensorMap tm_w[2];
   bool valid = false;
 };
 bool conv_flat_supported(const ConvLayer& L);
 int build_flat_plan(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, FlatPlan* plan);
-int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const FlatPlan& plan, cudaStream_t st);
+int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const FlatPlan& plan, int passes, cudaStream_t st);
 
 // stem.cu : Conv2d_1a_3x3 (3->32, 3x3, stride 2) fused with the uint8 LUT / float input
 int launch_stem(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, const float* d_w /*[27][32]*/,

@@ -45,7 +45,8 @@ struct FlatParams {
   int R, S, ksteps;     // filter taps, K = 16 steps per tap (cin / 16)
   int row_bytes;        // cin * 2: 64 (SWIZZLE_64B) or 128 (SWIZZLE_128B)
   int swz_type, sbo;
-  int nt;               // cout (<= 128); MMA N = 2 * nt
+  int nt;               // cout (<= 128)
+  int passes;           // 2: hi | lo planes side by side, MMA N = 2 * nt; 1: W_hi only (calibrated shift), MMA N = nt
   int tsub;                 // 128-pixel tiles per work item (their accumulators sit side by side in one TMEM stage)
   int n_boxes, box_rows;    // the run of a work item arrives as n_boxes TMA boxes of box_rows pixels
   int wtile_bytes;          // one tap's weights: 2 * nt rows
@@ -132,7 +133,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    const uint32_t idesc = make_instr_desc(2 * p.nt);
+    const uint32_t idesc = make_instr_desc(p.passes * p.nt);
     const uint64_t dhi = smem_desc_hi(p.swz_type, p.sbo);
     const int R = TR ? TR : p.R, S = TS ? TS : p.S, ksteps = TK ? TK : p.ksteps, n_stages = p.stages, tsub = p.tsub;
     const uint32_t stage_bytes = (uint32_t)p.stage_bytes, row_bytes = (uint32_t)p.row_bytes, wtile_bytes = (uint32_t)p.wtile_bytes;
@@ -143,7 +144,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t tile_step = ((uint32_t)kBlockM * row_bytes) >> 4;  // next 128-pixel tile of the item
     const uint32_t frow_step = ((uint32_t)p.wp * row_bytes) >> 4;     // next filter row: Wp pixels further
     const uint32_t pix_step = row_bytes >> 4;                        // next filter column: one pixel further
-    const uint32_t acc_cols = 2u * (uint32_t)p.nt;
+    const uint32_t acc_cols = (uint32_t)(p.passes * p.nt);
     mbar_wait(wfull_bar, 0);
     int stage = 0;
     uint32_t phase = 0;
@@ -215,7 +216,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t wr_swz = (uint32_t)((row >> 1) & 3);
     const int st_chunk = etid & 3, st_row0 = etid >> 2;
     const int nt = p.nt, wp = p.wp, hpwp = p.hpwp, ho = p.ho, wo = p.wo;
-    const bool relu = p.relu != 0;
+    const bool relu = p.relu != 0, two_pass = p.passes == 2;
     const int as = grp;
     uint32_t aphase = 0;
     uint32_t box_it = 0;
@@ -231,17 +232,23 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int rem = (int)(v % hpwp);
         const int y = rem / wp, x = rem - y * wp;
         const bool valid = v < p.total && y < ho && x < wo;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 256 + t * 2 * nt);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 256 + t * p.passes * nt);
         for (int c0 = 0; c0 < nt; c0 += 32, ++box_it) {
           const uint32_t buf = my_epi + (box_it & 1u) * kFlatEpiBuf;
           float f[32];
-          {
+          if (two_pass) {
             uint32_t a[32], b[32];
             tmem_ld32(taddr + (uint32_t)c0, a);
             tmem_ld32(taddr + (uint32_t)(nt + c0), b);  // W_lo products
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
+          } else {
+            uint32_t a[32];
+            tmem_ld32(taddr + (uint32_t)c0, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(a[j]);
           }
           if (c0 + 32 >= nt && t == tsub - 1) {  // all accumulators of the item read: hand the stage back
             tc_fence_before();
@@ -313,15 +320,18 @@ bool conv_flat_supported(const ConvLayer& L) {
 struct FlatGeom {
   int tsub, n_boxes, box_rows, stage_bytes, stages;
 };
-static FlatGeom flat_geometry(const ConvLayer& L, int wp, int smem_limit) {
+static FlatGeom flat_geometry(const ConvLayer& L, int wp, int smem_limit, int passes) {
   const int row_bytes = L.cin * 2;
-  const int fixed = 1024 + (int)align_up((size_t)L.R * L.S * 2 * L.nt * row_bytes, 1024) + 4 * kFlatEpiBuf + 2 * 128 * 4 +
+  const int fixed = 1024 + (int)align_up((size_t)L.R * L.S * passes * L.nt * row_bytes, 1024) + 4 * kFlatEpiBuf + 2 * 128 * 4 +
                     8 * (2 * kFlatMaxStages + 6) + 16;
   static int t_env = -1;
   if (t_env < 0) t_env = getenv("TISE_FLAT_T") ? atoi(getenv("TISE_FLAT_T")) : 0;
-  int tmax = 256 / (2 * L.nt);
+  // Sharing one run among T tiles cuts the TMA rows per output, but these kernels are bound by the shared-memory reads
+  // of the MMA operands (A: 4 KB per M = 128, K = 16 step whatever N is), not by the fills: measured, T > 1 gains 7 % at
+  // N = 64 (two-pass cout = 32) and loses 7 % at N = 128 (larger work items, fewer stages) -- so only narrow tiles share.
+  int tmax = (passes * L.nt <= 64) ? 256 / (passes * L.nt) : 1;
   if (tmax > 4) tmax = 4;
-  if (t_env > 0 && t_env < tmax) tmax = t_env;
+  if (t_env > 0) tmax = t_env < 256 / (passes * L.nt) ? t_env : 256 / (passes * L.nt);
   FlatGeom g{1, 1, 0, 0, 0};
   for (int t = tmax; t >= 1; --t) {
     const int run_rows = t * kBlockM + (L.R - 1) * wp + L.S - 1;
@@ -347,37 +357,40 @@ int build_flat_plan(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, FlatPl
   }
   const CUtensorMapSwizzle swz = L.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const long long total = (long long)a.n * a.hp * a.wp;
-  const FlatGeom g = flat_geometry(L, a.wp, ctx->smem_optin > 0 ? ctx->smem_optin : 232448);
-  if (g.stages < 2) return fail(ctx, TISE_ERR_INVALID, "flat conv: does not fit shared memory");
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)L.cin, (cuuint64_t)total};
-    cuuint64_t strides[1] = {(cuuint64_t)L.cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)L.kc, (cuuint32_t)g.box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_flat_encode(&plan->tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)a.in, dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ctx, TISE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for flat input", (int)r);
-  }
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)L.ktot, (cuuint64_t)2 * L.cout};
-    cuuint64_t strides[1] = {(cuuint64_t)L.ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)L.kc, (cuuint32_t)(2 * L.nt)};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_flat_encode(&plan->tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)L.d_w, dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ctx, TISE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for flat weights", (int)r);
+  for (int passes = 1; passes <= 2; ++passes) {  // one pair of maps per operand policy (the policy can change per call)
+    const FlatGeom g = flat_geometry(L, a.wp, ctx->smem_optin > 0 ? ctx->smem_optin : 232448, passes);
+    if (g.stages < 2) return fail(ctx, TISE_ERR_INVALID, "flat conv: does not fit shared memory");
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)L.cin, (cuuint64_t)total};
+      cuuint64_t strides[1] = {(cuuint64_t)L.cin * 2};
+      cuuint32_t box[2] = {(cuuint32_t)L.kc, (cuuint32_t)g.box_rows};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = g_flat_encode(&plan->tm_a[passes - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)a.in, dims, strides, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(ctx, TISE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for flat input", (int)r);
+    }
+    {  // rows [0, nt) of the packed weights are W_hi, [nt, 2 nt) W_lo (one output tile: nt = cout)
+      cuuint64_t dims[2] = {(cuuint64_t)L.ktot, (cuuint64_t)2 * L.cout};
+      cuuint64_t strides[1] = {(cuuint64_t)L.ktot * 2};
+      cuuint32_t box[2] = {(cuuint32_t)L.kc, (cuuint32_t)(passes * L.nt)};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = g_flat_encode(&plan->tm_w[passes - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)L.d_w, dims, strides, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(ctx, TISE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for flat weights", (int)r);
+    }
   }
   plan->valid = true;
   return TISE_OK;
 }
 
-int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const FlatPlan& plan, cudaStream_t st) {
+int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const FlatPlan& plan, int passes, cudaStream_t st) {
   if (!plan.valid) return fail(ctx, TISE_ERR_STATE, "flat conv: plan not built");
   FlatParams p;
   p.scale = L.d_scale;
-  p.shift = L.d_shift;
+  p.shift = (passes == 1 && L.d_shift1) ? L.d_shift1 : L.d_shift;
+  p.passes = passes;
   p.out = a.out;
   p.total = (long long)a.n * a.hp * a.wp;
   p.out_total = p.total;
@@ -394,7 +407,7 @@ int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const
   p.swz_type = L.kc == 64 ? 2 : 4;
   p.sbo = 8 * p.row_bytes;
   p.nt = L.cout;
-  p.wtile_bytes = 2 * L.nt * p.row_bytes;
+  p.wtile_bytes = passes * L.nt * p.row_bytes;
   p.relu = a.relu;
 
   static PerDeviceFlag configured;
@@ -404,7 +417,7 @@ int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const
     TISE_CUDA(ctx, cudaFuncSetAttribute(conv_flat_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
     configured.set(ctx, smem_limit);
   }
-  const FlatGeom g = flat_geometry(L, a.wp, smem_limit);  // the same geometry the plan's input box was built for
+  const FlatGeom g = flat_geometry(L, a.wp, smem_limit, passes);  // the same geometry the plan's input box was built for
   if (g.stages < 2) return fail(ctx, TISE_ERR_INVALID, "flat conv: does not fit shared memory");
   p.tsub = g.tsub;
   p.n_boxes = g.n_boxes;
@@ -428,9 +441,9 @@ int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const
   }
   cudaError_t le;
   if (L.R == 3 && L.S == 3 && p.ksteps == 2)
-    le = cudaLaunchKernelEx(&cfg, conv_flat_kernel<3, 3, 2>, plan.tm_a, plan.tm_w, p);
+    le = cudaLaunchKernelEx(&cfg, conv_flat_kernel<3, 3, 2>, plan.tm_a[passes - 1], plan.tm_w[passes - 1], p);
   else
-    le = cudaLaunchKernelEx(&cfg, conv_flat_kernel<0, 0, 0>, plan.tm_a, plan.tm_w, p);
+    le = cudaLaunchKernelEx(&cfg, conv_flat_kernel<0, 0, 0>, plan.tm_a[passes - 1], plan.tm_w[passes - 1], p);
   if (le != cudaSuccess) return fail(ctx, TISE_ERR_CUDA, "conv_flat_kernel launch failed: %s", cudaGetErrorString(le));
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;

@@ -204,10 +204,11 @@ extern "C" int tise_jpeg_decode(tise_ctx* ctx, const uint8_t* h_files, const uin
   JpegDesc* d_descs = (JpegDesc*)ws;
   jpg::Scan* d_scans = (jpg::Scan*)(ws + off_scans);
   jpg::HuffDef* d_tables = (jpg::HuffDef*)(ws + off_tables);
-  // (pageable host memory: cudaMemcpyAsync has staged it before returning)
-  TISE_CUDA(ctx, cudaMemcpyAsync(d_descs, descs.data(), sizeof(JpegDesc) * n, cudaMemcpyHostToDevice, st));
-  TISE_CUDA(ctx, cudaMemcpyAsync(d_scans, scans.data(), sizeof(jpg::Scan) * scans.size(), cudaMemcpyHostToDevice, st));
-  TISE_CUDA(ctx, cudaMemcpyAsync(d_tables, tables.data(), sizeof(jpg::HuffDef) * tables.size(), cudaMemcpyHostToDevice, st));
+  // (through the context's pinned staging ring: no stream synchronisation, common.cuh)
+  int urc = stage_upload(ctx, d_descs, descs.data(), sizeof(JpegDesc) * n, st);
+  if (!urc) urc = stage_upload(ctx, d_scans, scans.data(), sizeof(jpg::Scan) * scans.size(), st);
+  if (!urc) urc = stage_upload(ctx, d_tables, tables.data(), sizeof(jpg::HuffDef) * tables.size(), st);
+  if (urc) return urc;
   TISE_CUDA(ctx, cudaMemsetAsync(d_status, 0xff, sizeof(int32_t) * n, st));
   for (int i0 = 0; i0 < n; i0 += 32768) {  // gridDim.y <= 65535
     const int cnt = n - i0 < 32768 ? n - i0 : 32768;

@@ -724,15 +724,19 @@ int net_calibrate_lo(tise_ctx* ctx, int n, void* d_ws, size_t ws_bytes, cudaStre
   ctx->profiling = keep_prof;
   if (!rc) {
     for (Step& s : plan->steps) {
-      if (s.kind != STEP_CONV) continue;
+      if (s.kind != STEP_CONV && s.kind != STEP_FLATCONV) continue;
       const ConvLayer& L = *s.layer;
       const int cin_phys = L.cin / L.fold;
-      const long long pixels = (long long)s.conv.n * s.conv.h * (s.conv.in_row_pitch ? s.conv.in_row_pitch : s.conv.w);
+      const bool flat = s.kind == STEP_FLATCONV;  // flat layers read the whole padded grid (its zero cells dilute the
+      const __half* in = flat ? s.flat.in : s.conv.in;  // mean by (147 / 149)^2: second order, like the border taps)
+      const int stride = flat ? L.cin : s.conv.in_stride;
+      const long long pixels = flat ? (long long)s.flat.n * s.flat.hp * s.flat.wp
+                                    : (long long)s.conv.n * s.conv.h * (s.conv.in_row_pitch ? s.conv.in_row_pitch : s.conv.w);
       cudaMemsetAsync(d_sum, 0, 4096 * sizeof(double), st);
       int slices = (int)((pixels + 8 * 64 - 1) / (8 * 64));
       if (slices > 1024) slices = 1024;
       if (slices < 1) slices = 1;
-      channel_sum_kernel<<<dim3((cin_phys + 31) / 32, slices), 256, 0, st>>>(s.conv.in, pixels, s.conv.in_stride, cin_phys, d_sum);
+      channel_sum_kernel<<<dim3((cin_phys + 31) / 32, slices), 256, 0, st>>>(in, pixels, stride, cin_phys, d_sum);
       lo_correction_kernel<<<(L.cout + 7) / 8, 256, 0, st>>>(L.d_w, L.ktot, L.cin_pad, L.cin, cin_phys, L.nt, L.cout, d_sum,
                                                             1.0 / (double)pixels, L.d_scale, L.d_shift, L.d_shift1);
     }
@@ -806,7 +810,7 @@ int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, i
         break;
       case STEP_FLATCONV:
         if (!s.flatplan.valid && (rc = build_flat_plan(ctx, *s.layer, s.flat, &s.flatplan))) break;
-        rc = launch_conv_flat(ctx, *s.layer, s.flat, s.flatplan, st);
+        rc = launch_conv_flat(ctx, *s.layer, s.flat, s.flatplan, (s.flat.hp <= ctx->pass1_max_hw) ? 1 : 2, st);
         break;
       case STEP_ZERO: {
         cudaError_t e = cudaMemsetAsync(s.out, 0, s.zero_bytes, st);

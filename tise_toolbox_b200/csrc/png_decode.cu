@@ -226,8 +226,9 @@ extern "C" int tise_png_decode(tise_ctx* ctx, const uint8_t* h_files, const uint
   uint8_t* ws = (uint8_t*)d_ws;
   PngDesc* d_descs = (PngDesc*)(ws + L.off_desc);
   PngSeg* d_segs = (PngSeg*)(ws + L.off_seg);
-  TISE_CUDA(ctx, cudaMemcpyAsync(d_descs, descs.data(), sizeof(PngDesc) * n, cudaMemcpyHostToDevice, st));
-  TISE_CUDA(ctx, cudaMemcpyAsync(d_segs, segs.data(), sizeof(PngSeg) * segs.size(), cudaMemcpyHostToDevice, st));
+  int urc = stage_upload(ctx, d_descs, descs.data(), sizeof(PngDesc) * n, st);
+  if (!urc) urc = stage_upload(ctx, d_segs, segs.data(), sizeof(PngSeg) * segs.size(), st);
+  if (urc) return urc;
   TISE_CUDA(ctx, cudaMemsetAsync(d_status, 0xff, sizeof(int32_t) * n, st));  // -1 until the inflate kernel writes it
 
   png_gather_kernel<<<(unsigned)segs.size(), 256, 0, st>>>(d_files, d_segs, ws);

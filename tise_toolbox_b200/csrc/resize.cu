@@ -319,8 +319,9 @@ static int resize_impl(tise_ctx* ctx, const char* who, const uint8_t* d_imgs, co
   int* d_sizes = (int*)(ws + L.off_sizes);
   int* d_tabs = (int*)(ws + L.off_tabs);
   uint8_t* d_tmp = (uint8_t*)(ws + L.off_tmp);
-  TISE_CUDA(ctx, cudaMemcpyAsync(d_descs, descs.data(), sizeof(ImgDesc) * n, cudaMemcpyHostToDevice, st));
-  TISE_CUDA(ctx, cudaMemcpyAsync(d_sizes, sizes.data(), sizeof(int) * sizes.size(), cudaMemcpyHostToDevice, st));
+  int urc = stage_upload(ctx, d_descs, descs.data(), sizeof(ImgDesc) * n, st);
+  if (!urc) urc = stage_upload(ctx, d_sizes, sizes.data(), sizeof(int) * sizes.size(), st);
+  if (urc) return urc;
 
   resize_coeffs_kernel<<<(unsigned)sizes.size(), 320, 0, st>>>(d_sizes, kmax, d_tabs);
   TISE_LAUNCH_CHECK(ctx);

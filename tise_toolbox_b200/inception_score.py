@@ -44,6 +44,24 @@ def split_ids(n_total: int, splits: int, variant: str, start: int = 0, count: Op
     return sid.astype(np.int32)
 
 
+def split_ids_device(n_total: int, splits: int, variant: str, start: int, count: int, device) -> torch.Tensor:
+    """:func:`split_ids` evaluated on ``device`` (integer index bookkeeping only): no host array crosses to the GPU, so
+    the call is asynchronous -- a pageable host-to-device copy would synchronise the stream first and stall the host
+    behind the whole trunk of the batch."""
+    idx = torch.arange(start, start + count, dtype=torch.int64, device=device)
+    if variant == "ois":
+        per = n_total // splits
+        if per <= 0:
+            return torch.full((count,), -1, dtype=torch.int32, device=device)
+        sid = idx // per
+        sid = torch.where(sid < splits, sid, torch.full_like(sid, -1))
+    else:
+        bounds = (torch.arange(1, splits + 1, dtype=torch.int64, device=device) * n_total) // splits
+        sid = torch.searchsorted(bounds, idx, right=True)
+        sid = torch.where(idx < n_total, sid, torch.full_like(sid, -1))
+    return sid.to(torch.int32)
+
+
 def kept_images(n: int, variant: str, batch_size: int = 64) -> int:
     """How many of n images enter the score: bird keeps floor(n / 64) full batches
     (inception_score_star_bird.py:83), the others keep all."""
@@ -53,7 +71,7 @@ def kept_images(n: int, variant: str, batch_size: int = 64) -> int:
 def update_from_logits(engine: Engine, parts: ISPartials, logits: torch.Tensor, variant: str, n_total: int,
                        start: int):
     t, off, _, _ = VARIANTS[variant]
-    sid = torch.from_numpy(split_ids(n_total, parts.s, variant, start, int(logits.shape[0]))).to(engine.device)
+    sid = split_ids_device(n_total, parts.s, variant, start, int(logits.shape[0]), engine.device)
     parts.update(logits, sid, off, t)
 
 
