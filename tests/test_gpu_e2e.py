@@ -226,12 +226,15 @@ def test_ois_folder_path_on_device_matches_reference_pipeline(tmp_path):
     head = np.load(os.path.join(GOLD, "ois_head.npy"))
     sd80["fc.weight"] = torch.from_numpy(head[:, :2048].copy())
     sd80["fc.bias"] = torch.from_numpy(head[:, 2048].copy())
-    sizes = synth.crop_sizes(8, 0, 26, lo=24, hi=320)
+    # 208 crops, 2 splits of 104: the 1e-3 bound is BASELINE.json's bound for sets of thousands of images; a split of a
+    # dozen crops (the round-1 size of this test) turns the per-image fp16 rounding noise of one or two crops into
+    # > 1e-3 of exp(mean KL) (measured on B200: 26 crops -> 1.4e-4 ... 1.3e-3 depending on the file order alone)
+    sizes = synth.crop_sizes(8, 0, 208, lo=24, hi=320)
     for i, (h, w) in enumerate(sizes):
         Image.fromarray(synth.images(5, i % 2, i, 1, h, w)[0].numpy()).save(str(tmp_path / ("crop_%03d.png" % i)))
     eng = Engine(sd80, device="cuda:0", variant="ois", micro_batch=16)
     ds = ois.IgnoreLabelDataset(str(tmp_path), raw_u8=True)
-    dev = ois.inception_score(ds, batch_size=8, splits=2, engine=eng)
+    dev = ois.inception_score(ds, batch_size=32, splits=2, engine=eng)
     # the host pipeline, file by file in the dataset's own order
     names = [os.path.join(str(tmp_path), n) for n in ds.namelist]  # os.listdir order, as the reference walks it
     ims = [np.asarray(Image.open(n).convert("RGB")) for n in names]
@@ -241,5 +244,5 @@ def test_ois_folder_path_on_device_matches_reference_pipeline(tmp_path):
     assert ref[0] > 1.2, ref
     assert abs(dev[0] - ref[0]) <= 1e-3 * ref[0] and abs(dev[1] - ref[1]) <= 2e-2 * ref[1] + 1e-4, (dev, ref)
     # and the float path of the drop-in (host PIL resize + ToTensor + Normalize, trunk on the GPU) agrees with both
-    flt = ois.inception_score(ois.IgnoreLabelDataset(str(tmp_path)), batch_size=8, splits=2, engine=eng)
+    flt = ois.inception_score(ois.IgnoreLabelDataset(str(tmp_path)), batch_size=32, splits=2, engine=eng)
     assert abs(flt[0] - ref[0]) <= 1e-3 * ref[0], (flt, ref)
