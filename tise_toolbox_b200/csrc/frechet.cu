@@ -13,6 +13,7 @@
 //   4. Sturm-sequence bisection, one thread per eigenvalue, then sum sqrt(max(lambda, 0)).
 // Everything is fp64 FMA on the CUDA cores; the two GEMMs are the only O(d^3) dense steps.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "net.cuh"
@@ -496,6 +497,320 @@ __global__ void __launch_bounds__(TRI_THREADS) tri_persistent_kernel(double* M, 
   }
 }
 
+// ---------------------------------------------------------------------------- on-chip tridiagonalisation
+// The persistent kernel above is bound by synchronisation and L2 round trips (~9.7 us per column at d = 2048: grid
+// barrier 1.9 us + ~4 dependent L2 round trips for the pass + the preamble, profiles/frechet_launches_r01.txt), not
+// by bandwidth or arithmetic.  This kernel keeps the WHOLE symmetric matrix on chip for the whole factorisation:
+//   * row i lives in CTA i % G (cyclic, so the shrinking trailing matrix stays balanced), as local row i / G: the
+//     first TR_RS local rows in shared memory, the last TR_RR (the longest-lived ones) in registers; thread t owns the
+//     columns t + 512 c of every local row.  148 CTAs x 14 rows x 2048 columns x 8 B = 32 MB of shared memory + registers;
+//   * v, w and the next reflector are column-distributed the same way (thread t holds entries t + 512 c in registers);
+//     the few row-indexed entries a CTA needs (its own <= 14 rows) are passed through tiny shared arrays;
+//   * per column the CTAs exchange exactly two vectors through L2: y = A v_next and column k + 2 of the updated matrix
+//     (= the next row to finalise, by symmetry), each CTA contributing the entries of its own rows.  There is no grid
+//     barrier and no fence: every 8-byte value travels as two (32-bit half, epoch) pairs in one 16-byte volatile
+//     access ("LL" words), so the data carries its own flag and a reader spins on the values it needs, requesting
+//     only what has not arrived yet.  Two alternating buffers suffice (a CTA can be at most one column ahead of the
+//     slowest reader of its data).
+// Per column: one L2 write -> read latency, two block reductions (p.v and the reflector norm), the fused rank-2 update +
+// matrix-vector pass over on-chip data, and a 14-value transpose reduction.  Measured on B200, d = 2048
+// (TISE_FRECHET_DEBUG=64, cycles per column): exchange ~7 k, reflector 1.9 k, pass 3.3 k (fp64 FMA rate), y reduction 1 k.
+constexpr int TR_THREADS = 512;
+constexpr int TR_CS = 4;                        // column slots per thread: j = t + 512 c
+constexpr int TR_PITCH = TR_THREADS * TR_CS;    // d <= 2048
+constexpr int TR_RS = 10;                       // local rows in shared memory
+constexpr int TR_RR = 4;                        // local rows in registers
+constexpr int TR_ROWS = TR_RS + TR_RR;
+constexpr int TR_MAX_CTAS = 256;                // flag words reserved in the workspace
+
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// "LL" words: an 8-byte value travels as two (32-bit half, epoch) pairs in one 16-byte access, so the data carries its own
+// flag -- no fence, no separate flag round trip; a reader spins on the value itself.
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned epoch) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"(epoch),
+               "r"((unsigned)(b >> 32)), "r"(epoch)
+               : "memory");
+}
+__device__ __forceinline__ bool ll_load(const uint4* p, unsigned epoch, double& v) {
+  unsigned a, fa, b, fb;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(p) : "memory");
+  v = __longlong_as_double((long long)(((unsigned long long)b << 32) | (unsigned long long)a));
+  return fa == epoch && fb == epoch;
+}
+// sum over the 512 threads of the CTA with ONE __syncthreads; every thread gets the same bits
+__device__ __forceinline__ double block_sum512(double v, double* red16) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red16[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = red16[threadIdx.x & 15];
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+template <bool kDbg>
+__global__ void __launch_bounds__(TR_THREADS, 1)
+tri_resident_kernel(const double* __restrict__ M, int d, uint4* xbuf,
+                    double* __restrict__ diag, double* __restrict__ off, unsigned long long* dbg, int abl) {
+  // abl (kDbg only; results are garbage, timing ablations): 1 no pass, 2 no flag waits, 4 no loads of y / row,
+  // 8 relaxed flag stores, 16 no y reduction
+  // kDbg: thread 0 of every CTA accumulates the cycles of the five phases of a column (TISE_FRECHET_DEBUG=64)
+  unsigned long long ph[6] = {0, 0, 0, 0, 0, 0};
+  long long tp = 0;
+#define TR_MARK(idx)                                   \
+  if (kDbg && threadIdx.x == 0) {                      \
+    const long long now = clock64();                   \
+    ph[idx] += (unsigned long long)(now - tp);         \
+    tp = now;                                          \
+  }
+  extern __shared__ double S[];  // [TR_RS][TR_PITCH]
+  __shared__ double red_a[16], red_b[16], red_y[16][17];
+  __shared__ double s_v[2][16], s_w[16], s_bc[4], s_col[16];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int G = gridDim.x, cta = blockIdx.x;
+  int own_l[TR_CS];  // local row whose index equals this thread's column (the row-indexed copy of v / w it must publish)
+#pragma unroll
+  for (int c = 0; c < TR_CS; ++c) {
+    const int j = t + c * TR_THREADS;
+    own_l[c] = (j < d && j % G == cta) ? j / G : -1;
+  }
+  // ---- the matrix goes on chip
+#pragma unroll
+  for (int l = 0; l < TR_RS; ++l) {
+    const int i = l * G + cta;
+#pragma unroll
+    for (int c = 0; c < TR_CS; ++c) {
+      const int j = t + c * TR_THREADS;
+      S[l * TR_PITCH + j] = (i < d && j < d) ? M[(size_t)i * d + j] : 0.0;
+    }
+  }
+  double areg[TR_RR][TR_CS];
+#pragma unroll
+  for (int l = 0; l < TR_RR; ++l) {
+    const int i = (TR_RS + l) * G + cta;
+#pragma unroll
+    for (int c = 0; c < TR_CS; ++c) {
+      const int j = t + c * TR_THREADS;
+      areg[l][c] = (i < d && j < d) ? M[(size_t)i * d + j] : 0.0;
+    }
+  }
+  double vj[TR_CS], wj[TR_CS], vnj[TR_CS];
+#pragma unroll
+  for (int c = 0; c < TR_CS; ++c) vj[c] = wj[c] = vnj[c] = 0.0;
+  double tau = 0.0;
+  if (t < 16) {
+    s_v[0][t] = 0.0;
+    s_v[1][t] = 0.0;
+    s_w[t] = 0.0;
+  }
+  if (t < 4) s_bc[t] = 0.0;
+  __syncthreads();
+  int cur = 0;
+  // step k: finalise row q = k + 1 (its diagonal and sub-diagonal), build the reflector of column q, apply the rank-2
+  // update of column k to rows / columns >= q + 1 and accumulate y = A v_q there.  k = -1 is the start (no update).
+  if (kDbg) tp = clock64();
+  for (int k = -1; k <= d - 3; ++k) {
+    const int q = k + 1, r0 = q + 1;
+    double yj[TR_CS], rj[TR_CS];
+    if (k < 0) {
+#pragma unroll
+      for (int c = 0; c < TR_CS; ++c) {
+        const int j = t + c * TR_THREADS;
+        yj[c] = 0.0;
+        rj[c] = j < d ? M[j] : 0.0;
+      }
+    } else {
+      const unsigned epoch = (unsigned)(k + 1);
+      const uint4* xb = xbuf + (size_t)(k & 1) * 2 * d;  // word 2 j: y_j, word 2 j + 1: A[j][q] (= row q by symmetry)
+      // spin on the values themselves; a word that has arrived is not requested again
+      unsigned need = 0;
+#pragma unroll
+      for (int c = 0; c < TR_CS; ++c) {
+        const int j = t + c * TR_THREADS;
+        yj[c] = rj[c] = 0.0;
+        if (j >= q && j < d && !(kDbg && (abl & 4))) need |= 3u << (2 * c);
+      }
+      while (need) {  // (all outstanding words are requested before the first one is examined)
+        unsigned got = (kDbg && (abl & 2)) ? need : 0u;
+#pragma unroll
+        for (int c = 0; c < TR_CS; ++c) {
+          const int j = t + c * TR_THREADS;
+          if (need & (1u << (2 * c)))
+            if (ll_load(xb + 2 * j, epoch, yj[c])) got |= 1u << (2 * c);
+          if (need & (2u << (2 * c)))
+            if (ll_load(xb + 2 * j + 1, epoch, rj[c])) got |= 2u << (2 * c);
+        }
+        need &= ~got;
+        if (kDbg && (abl & 32) && need) __nanosleep(100);
+      }
+      TR_MARK(0);
+    }
+    // w = p - (tau / 2)(p . v) v with p = tau y      (v is zero outside its support)
+    double dot = 0.0;
+#pragma unroll
+    for (int c = 0; c < TR_CS; ++c) {
+      yj[c] *= tau;
+      dot = fma(vj[c], yj[c], dot);
+    }
+    dot = block_sum512(dot, red_a);
+    TR_MARK(1);
+    const double cc = 0.5 * tau * dot;
+#pragma unroll
+    for (int c = 0; c < TR_CS; ++c) {
+      wj[c] = yj[c] - cc * vj[c];
+      if (own_l[c] >= 0) s_w[own_l[c]] = wj[c];
+      if (t + c * TR_THREADS == q) {
+        s_bc[0] = vj[c];
+        s_bc[1] = wj[c];
+      }
+    }
+    __syncthreads();
+    // row q after the update of column k; its reflector
+    const double v0 = s_bc[0], w0 = s_bc[1];
+    double ss = 0.0;
+#pragma unroll
+    for (int c = 0; c < TR_CS; ++c) {
+      const int j = t + c * TR_THREADS;
+      rj[c] -= v0 * wj[c] + w0 * vj[c];
+      if (j >= q + 2 && j < d) ss = fma(rj[c], rj[c], ss);
+      if (j == q + 1) s_bc[2] = rj[c];
+      if (j == q) s_bc[3] = rj[c];
+    }
+    ss = block_sum512(ss, red_b);
+    const double alpha = s_bc[2];
+    double tau_n, beta, scale;
+    if (ss == 0.0) {
+      tau_n = 0.0;
+      beta = alpha;
+      scale = 0.0;
+    } else {
+      beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+      tau_n = (beta - alpha) / beta;
+      scale = 1.0 / (alpha - beta);
+    }
+    if (cta == 0 && t == 0) {
+      diag[q] = s_bc[3];
+      off[q] = beta;
+    }
+#pragma unroll
+    for (int c = 0; c < TR_CS; ++c) {
+      const int j = t + c * TR_THREADS;
+      vnj[c] = (j == r0) ? 1.0 : ((j > r0 && j < d) ? rj[c] * scale : 0.0);
+      if (own_l[c] >= 0) s_v[cur ^ 1][own_l[c]] = vnj[c];
+    }
+    TR_MARK(2);
+    // ---- y = (A - v w^T - w v^T) v_next = A v_next - v (w . v_next) - w (v . v_next): the matrix-vector product runs on
+    // the matrix as it stands and y is published at once; the rank-2 update itself (two thirds of the arithmetic) is
+    // applied AFTER the publication, while the other CTAs' contributions are in flight (LAPACK dlatrd's delayed update).
+    const bool last = k == d - 3;
+    const unsigned epoch_n = (unsigned)(k + 2);
+    uint4* xb_n = xbuf + (size_t)((k + 1) & 1) * 2 * d;
+    double acc[16];
+#pragma unroll
+    for (int l = 0; l < 14; ++l) acc[l] = 0.0;
+    {
+      double s14 = 0.0, s15 = 0.0;  // the two correction dot products ride along in the unused reduction slots
+#pragma unroll
+      for (int c = 0; c < TR_CS; ++c) {
+        s14 = fma(wj[c], vnj[c], s14);
+        s15 = fma(vj[c], vnj[c], s15);
+      }
+      acc[14] = s14;
+      acc[15] = s15;
+    }
+    // No per-element predicates: columns left of r0 are dead storage (the finished part of a row is never read again)
+    // and v_next is zero there, columns >= d hold zeros; a column slot is skipped once ALL of its columns are dead.
+    const int c_first = r0 / TR_THREADS;  // first column slot with live columns (uniform)
+#pragma unroll
+    for (int l = 0; l < TR_ROWS; ++l) {
+      const int i = l * G + cta;
+      if (i >= r0 && i < d && !(kDbg && (abl & 1))) {  // (uniform across the CTA)
+        double a[TR_CS];
+#pragma unroll
+        for (int c = 0; c < TR_CS; ++c)
+          if (c >= c_first) a[c] = l < TR_RS ? S[l * TR_PITCH + t + c * TR_THREADS] : areg[l < TR_RS ? 0 : l - TR_RS][c];
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < TR_CS; c += 2) {
+          if (c >= c_first) s0 = fma(a[c], vnj[c], s0);
+          if (c + 1 >= c_first) s1 = fma(a[c + 1], vnj[c + 1], s1);
+        }
+        acc[l] = s0 + s1;
+        // column r0 of this row after the update (= entry i of the next row to finalise): travels with y_i
+#pragma unroll
+        for (int c = 0; c < TR_CS; ++c)
+          if (t + c * TR_THREADS == r0) s_col[l] = fma(-s_w[l], vj[c], fma(-s_v[cur][l], wj[c], a[c]));
+      }
+    }
+    TR_MARK(3);
+    // ---- y: transpose reduction of the 16 sums across the warp (31 exchanges instead of 16 x 5), then across warps
+    if (!(kDbg && (abl & 16)))
+#pragma unroll
+    for (int m = 16, n = 8; m >= 2; m >>= 1, n >>= 1) {
+      const bool hi = (lane & m) != 0;
+#pragma unroll
+      for (int r = 0; r < n; ++r) {
+        const double send = hi ? acc[r] : acc[r + n];
+        const double keep = hi ? acc[r + n] : acc[r];
+        acc[r] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+      }
+    }
+    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);  // lanes 2 r and 2 r + 1 now hold the warp's sum of local row r
+    if ((lane & 1) == 0) red_y[lane >> 1][warp] = acc[0];
+    __syncthreads();
+    if (warp == 0 && !last) {
+      const int row = lane & 15, h8 = (lane >> 4) * 8;
+      double s = 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += red_y[row][h8 + u];
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      const double w_vn = __shfl_sync(0xffffffffu, s, 14), v_vn = __shfl_sync(0xffffffffu, s, 15);
+      const int i = row * G + cta;
+      if (lane < TR_ROWS && i >= r0 && i < d) {
+        s = fma(-s_w[lane], v_vn, fma(-s_v[cur][lane], w_vn, s));
+        ll_store(xb_n + 2 * i, s, epoch_n);
+        ll_store(xb_n + 2 * i + 1, s_col[lane], epoch_n);
+      }
+    }
+    if (last && t == 0 && (d - 1) % G == cta) diag[d - 1] = s_col[(d - 1) / G];
+    // ---- the delayed rank-2 update (off the critical path: the next column's values are still in flight)
+#pragma unroll
+    for (int l = 0; l < TR_ROWS; ++l) {
+      const int i = l * G + cta;
+      if (i >= r0 && i < d && !(kDbg && (abl & 1))) {
+        const double vi = -s_v[cur][l], wi = -s_w[l];
+#pragma unroll
+        for (int c = 0; c < TR_CS; ++c)
+          if (c >= c_first) {
+            if (l < TR_RS) {
+              double* ap = S + l * TR_PITCH + t + c * TR_THREADS;
+              *ap = fma(wi, vj[c], fma(vi, wj[c], *ap));
+            } else {
+              double& ar = areg[l < TR_RS ? 0 : l - TR_RS][c];
+              ar = fma(wi, vj[c], fma(vi, wj[c], ar));
+            }
+          }
+      }
+    }
+    TR_MARK(4);
+#pragma unroll
+    for (int c = 0; c < TR_CS; ++c) vj[c] = vnj[c];
+    tau = tau_n;
+    cur ^= 1;
+  }
+  if (kDbg && threadIdx.x == 0)
+    for (int u = 0; u < 5; ++u) dbg[blockIdx.x * 8 + u] = ph[u];
+#undef TR_MARK
+}
+
 __global__ void tri_tail_kernel(const double* M, int d, double* diag, double* off) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (d >= 2) {
@@ -698,7 +1013,36 @@ static int frechet_once(tise_ctx* ctx, const double* mu1, const double* s1, cons
   // 3. tridiagonalise
   static int legacy = -1;
   if (legacy < 0) legacy = getenv("TISE_FRECHET_LEGACY") ? atoi(getenv("TISE_FRECHET_LEGACY")) : 0;
-  if (!legacy && d > 2) {  // one cooperative launch for all columns
+  static int resident = -1;
+  if (resident < 0) resident = getenv("TISE_FRECHET_RESIDENT") ? atoi(getenv("TISE_FRECHET_RESIDENT")) : 1;
+  if (!legacy && resident && d >= (resident > 1 ? 3 : 512) && d <= TR_PITCH && d <= TR_ROWS * ctx->num_sms) {
+    // the whole matrix in shared memory + registers of one cooperative launch (one CTA per SM), see tri_resident_kernel
+    uint4* xbuf = (uint4*)vbuf;    // 2 buffers x d x {y, column} LL words = 64 d bytes (one vector area of the workspace)
+    TISE_CUDA(ctx, cudaMemsetAsync(xbuf, 0, (size_t)4 * d * sizeof(uint4), st));  // epochs restart at 1 in every call
+    int dd = d;
+    static int dbg = -1;
+    if (dbg < 0) dbg = getenv("TISE_FRECHET_DEBUG") ? atoi(getenv("TISE_FRECHET_DEBUG")) : 0;
+    unsigned long long* d_dbg = nullptr;
+    int abl = getenv("TISE_FRECHET_ABL") ? atoi(getenv("TISE_FRECHET_ABL")) : 0;
+    if (dbg & 64) TISE_CUDA(ctx, cudaMalloc(&d_dbg, (size_t)ctx->num_sms * 8 * sizeof(unsigned long long)));
+    void* args[] = {(void*)&M, (void*)&dd, (void*)&xbuf, (void*)&diag, (void*)&off, (void*)&d_dbg, (void*)&abl};
+    const void* fn = (dbg & 64) ? (const void*)tri_resident_kernel<true> : (const void*)tri_resident_kernel<false>;
+    TISE_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(ctx->num_sms), dim3(TR_THREADS), args,
+                                               (size_t)TR_RS * TR_PITCH * sizeof(double), st));
+    if (dbg & 64) {  // cycles per column of the five phases, averaged over the CTAs
+      std::vector<unsigned long long> h((size_t)ctx->num_sms * 8);
+      TISE_CUDA(ctx, cudaStreamSynchronize(st));
+      TISE_CUDA(ctx, cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      cudaFree(d_dbg);
+      double sum[5] = {0, 0, 0, 0, 0};
+      for (int b = 0; b < ctx->num_sms; ++b)
+        for (int u = 0; u < 5; ++u) sum[u] += (double)h[(size_t)b * 8 + u];
+      const double den = (double)ctx->num_sms * (d - 1);
+      fprintf(stderr, "tri_resident d=%d cycles/column: wait flags %.0f | load y,row + p.v %.0f | w, row, reflector %.0f | pass %.0f | "
+                      "y reduce + publish %.0f\n", d, sum[0] / den, sum[1] / den, sum[2] / den, sum[3] / den, sum[4] / den);
+    }
+    ctx->launches++;
+  } else if (!legacy && d > 2) {  // one cooperative launch for all columns, matrix in L2
     unsigned* bar = (unsigned*)(scal + FR_NSLOTS);
     TISE_CUDA(ctx, cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
     const size_t smem = (size_t)d * 32;
@@ -726,7 +1070,7 @@ static int frechet_once(tise_ctx* ctx, const double* mu1, const double* s1, cons
       TISE_LAUNCH_CHECK(ctx);
     }
   }
-  if (legacy || d <= 2) {  // (the persistent kernel publishes the 2 x 2 tail itself)
+  if (legacy || d <= 2) {  // (the persistent kernels publish the 2 x 2 tail themselves)
     tri_tail_kernel<<<1, 32, 0, st>>>(M, d, diag, off);
     TISE_LAUNCH_CHECK(ctx);
   }
@@ -760,6 +1104,10 @@ extern "C" int tise_frechet(tise_ctx* ctx, const double* d_mu1, const double* d_
   if (!configured.is(ctx, 1)) {
     TISE_CUDA(ctx, cudaFuncSetAttribute(tri_rank2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
     TISE_CUDA(ctx, cudaFuncSetAttribute(tri_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 32));
+    TISE_CUDA(ctx, cudaFuncSetAttribute(tri_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        TR_RS * TR_PITCH * (int)sizeof(double)));
+    TISE_CUDA(ctx, cudaFuncSetAttribute(tri_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        TR_RS * TR_PITCH * (int)sizeof(double)));
     TISE_CUDA(ctx, cudaFuncSetAttribute(sturm_sqrt_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
     configured.set(ctx, 1);
   }
