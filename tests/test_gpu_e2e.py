@@ -242,7 +242,8 @@ def test_ois_folder_path_on_device_matches_reference_pipeline(tmp_path):
     logits = trunk.logits(restate.preprocess(ims, "ois"))
     ref = restate.ois_inception_score(restate.ois_preds(logits), 2)
     assert ref[0] > 1.2, ref
-    assert abs(dev[0] - ref[0]) <= 1e-3 * ref[0] and abs(dev[1] - ref[1]) <= 2e-2 * ref[1] + 1e-4, (dev, ref)
+    # (the std over 2 splits is half the difference of two split scores, each within 1e-3 relative: same absolute bound)
+    assert abs(dev[0] - ref[0]) <= 1e-3 * ref[0] and abs(dev[1] - ref[1]) <= 1e-3 * ref[0], (dev, ref)
     # and the float path of the drop-in (host PIL resize + ToTensor + Normalize, trunk on the GPU) agrees with both
     flt = ois.inception_score(ois.IgnoreLabelDataset(str(tmp_path)), batch_size=32, splits=2, engine=eng)
     assert abs(flt[0] - ref[0]) <= 1e-3 * ref[0], (flt, ref)

@@ -116,6 +116,7 @@ class Engine:
         self._fr_ws: Optional[torch.Tensor] = None
         self._png_ws: Optional[torch.Tensor] = None
         self._jpg_ws: Optional[torch.Tensor] = None
+        self._d_files: Optional[torch.Tensor] = None
         self.num_classes = 0
         self.variant = None
         self.set_conv_mode(conv_impl, passes)
@@ -364,7 +365,18 @@ class Engine:
         total = int(out_off[-1] + nbytes[-1]) if n else 0
         out = torch.empty(max(total, 16), dtype=torch.uint8, device=self.device)
         if len(on_png) or len(on_jpg):
-            d_files = staged["pinned"][:staged["total"]].to(self.device, non_blocking=True)
+            # file bytes -> HBM on a private upload stream into a persistent buffer: the copy does not queue behind the
+            # trunk kernels of the previous group on the compute stream (the buffer is free: the previous decode was
+            # awaited below before this call)
+            total = int(staged["total"])
+            d_files = self._buf("_d_files", total)[:total]
+            if not hasattr(self, "_upload_stream"):
+                self._upload_stream = torch.cuda.Stream(device=self.device)
+            with torch.cuda.stream(self._upload_stream):
+                d_files.copy_(staged["pinned"][:total], non_blocking=True)
+                uploaded = torch.cuda.Event()
+                uploaded.record(self._upload_stream)
+            torch.cuda.current_stream(self.device).wait_event(uploaded)
             runs = [(idx, self.decode_staged_png(staged, d_files, idx, out, out_off[idx], jpeg=j), "JPEG" if j else "PNG")
                     for idx, j in ((on_png, False), (on_jpg, True)) if len(idx)]
             for idx, status, what in runs:

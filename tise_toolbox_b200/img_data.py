@@ -66,12 +66,12 @@ class DeviceImageLoader:
     reference's 50 / 64 would leave 97 % of the SMs idle) and handed out as ``batch_size`` slices of that pack.
     File reads of the next group run on ``io_threads`` host threads while the GPU works on the current one."""
 
-    def __init__(self, file_names, engine, batch_size, drop_last=True, io_threads=8, decode_batch=4096):
+    def __init__(self, file_names, engine, batch_size, drop_last=True, io_threads=None, decode_batch=4096):
         self.file_names = list(file_names)
         self.engine = engine
         self.batch_size = int(batch_size)
         self.drop_last = bool(drop_last)
-        self.io_threads = int(io_threads)
+        self.io_threads = int(io_threads) if io_threads else max(4, min(16, os.cpu_count() or 8))
         per = max(1, int(decode_batch) // self.batch_size)
         self.group = per * self.batch_size  # files per decode call: a whole number of consumer batches
 
@@ -95,9 +95,11 @@ class DeviceImageLoader:
             nxt = stager.submit(self.engine.stage_files, groups[0], readers)
             for gi, g in enumerate(groups):
                 staged = nxt.result()
-                pack = self.engine.decode_staged(staged)  # returns after the H2D + decode of this group completed
+                # the next group goes into the engine's OTHER pinned buffer (last used by group gi - 1, whose upload was
+                # awaited inside its decode_staged), so its file reads overlap this group's upload, decode and trunk
                 if gi + 1 < len(groups):
                     nxt = stager.submit(self.engine.stage_files, groups[gi + 1], readers)
+                pack = self.engine.decode_staged(staged)  # returns after the H2D + decode of this group completed
                 yield pack
 
     def __iter__(self):

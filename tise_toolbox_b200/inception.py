@@ -33,7 +33,7 @@ class InceptionV3(nn.Module):
     BLOCK_INDEX_BY_DIM = {64: 0, 192: 1, 768: 2, 2048: 3}
 
     def __init__(self, output_blocks=[DEFAULT_BLOCK_INDEX], resize_input=True, normalize_input=True,
-                 requires_grad=False, state_dict=None, weights_path=None, device=None, micro_batch=512, engine=None,
+                 requires_grad=False, state_dict=None, weights_path=None, device=None, micro_batch=1024, engine=None,
                  single_pass_max_hw=None):
         super(InceptionV3, self).__init__()
         self.resize_input = resize_input

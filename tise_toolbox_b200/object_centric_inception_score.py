@@ -30,7 +30,7 @@ def inception_score(imgs, cuda=True, batch_size=32, resize=False, splits=1, stat
     if engine is None:
         if state_dict is None:
             state_dict = load_state_dict_file(os.environ.get("TISE_OIS_WEIGHTS", WEIGHTS))
-        engine = Engine(state_dict, variant="ois", micro_batch=512)
+        engine = Engine(state_dict, variant="ois", micro_batch=1024)
     engine.set_variant("ois")
     raw = bool(getattr(imgs, "raw_u8", False))
     on_device = raw and hasattr(imgs, "imgspath") and os.environ.get("TISE_GPU_DECODE", "1") != "0"

@@ -38,7 +38,7 @@ try:
     sd = synth.inception_state_dict(0, num_classes=1000)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    model = InceptionV3([3], state_dict=sd, micro_batch=512)
+    model = InceptionV3([3], state_dict=sd)  # default micro-batch, as the command line runs it
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     print("engine: weights folded / split / uploaded in %.3f s" % (t1 - t0))
