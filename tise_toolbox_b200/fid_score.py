@@ -113,9 +113,13 @@ def _prefetched(images, device):
         cur = nxt
 
 
-def _accumulate_moments(images, model, batch_size, dims):
+def _accumulate_moments(images, model, batch_size, dims, next_loader=None):
     model.eval()
     mom = Moments(model.engine, dims)
+    if hasattr(images, "groups") and next_loader is not None:
+        for pack in images.groups(next_loader=next_loader):
+            mom.update(_batch_features(pack, model, dims))
+        return mom
     if hasattr(images, "groups"):
         # DeviceImageLoader: the sums do not depend on how the set is cut into batches, so whole decode groups (a whole
         # number of drop_last batches each) go through the trunk at once instead of batch_size images per call
@@ -147,7 +151,27 @@ def _world():
     return 0, 1
 
 
-def _compute_statistics_of_path(path, model, batch_size, dims, cuda):
+def _folder_loader(path, model, batch_size):
+    """DeviceImageLoader over this rank's share of a folder (None for .npz / .shard paths or TISE_GPU_DECODE=0)."""
+    if path.endswith(".npz") or (path.endswith(".shard") and os.path.isfile(path)) or \
+            os.environ.get("TISE_GPU_DECODE", "1") == "0":
+        return None
+    dataset = img_data.Dataset(path, raw_u8=True)
+    rank, world = _world()
+    if world > 1:
+        # launched under torchrun: every rank takes a contiguous run of whole batches of the folder and the packed
+        # moments are summed with ONE all-reduce (SURVEY.md §8e); each rank ends up with the same (mu, sigma)
+        from .pipeline import shard_batches
+
+        lo, hi = shard_batches(len(dataset.file_names), batch_size, rank, world)
+        dataset.file_names = dataset.file_names[lo:hi]
+    return img_data.DeviceImageLoader(dataset.file_names, model.engine, batch_size, drop_last=True)
+
+
+def _compute_statistics_of_path(path, model, batch_size, dims, cuda, loader=None, next_loader=None):
+    """fid_score.py:199-220.  ``loader`` / ``next_loader`` (optional, folders only): this path's DeviceImageLoader built
+    by the caller, and the loader of the path that follows -- its first group is read while this path's last group is
+    still on the GPU (calculate_fid_given_paths)."""
     if path.endswith(".npz"):
         f = np.load(path, allow_pickle=True)  # fid_score.py:200-203
         m, s = f["mu"][:], f["sigma"][:]
@@ -166,21 +190,19 @@ def _compute_statistics_of_path(path, model, batch_size, dims, cuda):
     else:
         # fid_score.py:206-217 with decode, Resize and ToTensor moved onto the GPU: host threads only read bytes.
         # TISE_GPU_DECODE=0 keeps PIL decode on DataLoader workers (resize / ToTensor still on the GPU).
-        dataset = img_data.Dataset(path, raw_u8=True)
         rank, world = _world()
-        if world > 1:
-            # launched under torchrun: every rank takes a contiguous run of whole batches of the folder and the packed
-            # moments are summed with ONE all-reduce; each rank ends up with the same (mu, sigma)
-            from .pipeline import shard_batches
+        dataloader = loader if loader is not None else _folder_loader(path, model, batch_size)
+        if dataloader is None:  # TISE_GPU_DECODE=0
+            dataset = img_data.Dataset(path, raw_u8=True)
+            if world > 1:
+                from .pipeline import shard_batches
 
-            lo, hi = shard_batches(len(dataset.file_names), batch_size, rank, world)
-            dataset.file_names = dataset.file_names[lo:hi]
-        if os.environ.get("TISE_GPU_DECODE", "1") != "0":
-            dataloader = img_data.DeviceImageLoader(dataset.file_names, model.engine, batch_size, drop_last=True)
-        else:
+                lo, hi = shard_batches(len(dataset.file_names), batch_size, rank, world)
+                dataset.file_names = dataset.file_names[lo:hi]
             dataloader = torch.utils.data.DataLoader(dataset=dataset, batch_size=batch_size, shuffle=False,
                                                      drop_last=True, num_workers=8, collate_fn=img_data.collate_u8)
-        mom = _accumulate_moments(dataloader, model, batch_size, dims)
+            next_loader = None
+        mom = _accumulate_moments(dataloader, model, batch_size, dims, next_loader=next_loader)
         if world > 1:
             mom.allreduce()
         print(" done")
@@ -196,8 +218,11 @@ def calculate_fid_given_paths(paths, batch_size, cuda, dims, model=None):
     block_idx = InceptionV3.BLOCK_INDEX_BY_DIM[dims]
     if model is None:
         model = InceptionV3([block_idx])
-    m1, s1 = _compute_statistics_of_path(paths[0], model, batch_size, dims, cuda)
-    m2, s2 = _compute_statistics_of_path(paths[1], model, batch_size, dims, cuda)
+    # both folders are one stream of decode groups: the second set's first files are read while the first set's last
+    # group is on the GPU
+    loaders = [_folder_loader(p, model, batch_size) for p in paths]
+    m1, s1 = _compute_statistics_of_path(paths[0], model, batch_size, dims, cuda, loader=loaders[0], next_loader=loaders[1])
+    m2, s2 = _compute_statistics_of_path(paths[1], model, batch_size, dims, cuda, loader=loaders[1])
     return calculate_frechet_distance(m1, s1, m2, s2)
 
 

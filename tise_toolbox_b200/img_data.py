@@ -79,28 +79,52 @@ class DeviceImageLoader:
         n, b = len(self.file_names), self.batch_size
         return n // b if self.drop_last else (n + b - 1) // b
 
-    def groups(self):
-        """The decoded packs themselves, ``decode_batch`` files at a time (a whole number of consumer batches each).
-        Consumers whose result does not depend on how the set is cut into batches (the FID moments, the IS partial
-        sums) take these instead of the ``batch_size`` slices: 50 images per trunk call would leave the GPU idle."""
+    def _group_lists(self):
         b = self.batch_size
         n_used = len(self) * b if self.drop_last else len(self.file_names)
         names = self.file_names[:n_used]
-        groups = [names[i:i + self.group] for i in range(0, len(names), self.group)]
-        if not groups:
-            return
-        # one staging thread reads group k + 1 into the engine's other pinned buffer (itself fanning the reads out over
-        # `io_threads`) while this thread uploads / decodes group k and the consumer runs the trunk on it
-        with ThreadPoolExecutor(max_workers=self.io_threads) as readers, ThreadPoolExecutor(max_workers=1) as stager:
-            nxt = stager.submit(self.engine.stage_files, groups[0], readers)
+        # ramp-up: a short first group (~1024 files) lets the GPU start after ~30 ms of file reads instead of ~110 ms;
+        # every later group is read while its predecessor is on the GPU
+        first = min(self.group, max(b, 1024 // b * b))
+        if len(names) <= 2 * first:
+            first = self.group
+        cuts = [0] + list(range(first, len(names), self.group)) if len(names) > first else [0]
+        return [names[lo:hi] for lo, hi in zip(cuts, cuts[1:] + [len(names)]) if hi > lo]
+
+    def prestage(self):
+        """Starts reading this loader's first group in the background (idempotent).  A consumer that walks several
+        loaders back to back (fid_score: generated set, then real set) calls it while the previous loader's last group
+        is on the GPU, so the second set does not pay the pipeline fill again."""
+        if getattr(self, "_pre", None) is None:
+            self._lists = self._group_lists()
+            self._readers = ThreadPoolExecutor(max_workers=self.io_threads)
+            self._stager = ThreadPoolExecutor(max_workers=1)
+            self._pre = self._stager.submit(self.engine.stage_files, self._lists[0], self._readers) if self._lists else None
+
+    def groups(self, next_loader=None):
+        """The decoded packs themselves, ``decode_batch`` files at a time (a whole number of consumer batches each).
+        Consumers whose result does not depend on how the set is cut into batches (the FID moments, the IS partial
+        sums) take these instead of the ``batch_size`` slices: 50 images per trunk call would leave the GPU idle.
+        ``next_loader``: a loader whose first group is pre-staged while this one's last group is being processed."""
+        self.prestage()
+        groups, nxt = self._lists, self._pre
+        self._pre = None
+        try:
+            # one staging thread reads group k + 1 into the engine's other pinned buffer (itself fanning the reads out
+            # over `io_threads`) while this thread uploads / decodes group k and the consumer runs the trunk on it
             for gi, g in enumerate(groups):
                 staged = nxt.result()
                 # the next group goes into the engine's OTHER pinned buffer (last used by group gi - 1, whose upload was
                 # awaited inside its decode_staged), so its file reads overlap this group's upload, decode and trunk
                 if gi + 1 < len(groups):
-                    nxt = stager.submit(self.engine.stage_files, groups[gi + 1], readers)
+                    nxt = self._stager.submit(self.engine.stage_files, groups[gi + 1], self._readers)
+                elif next_loader is not None:
+                    next_loader.prestage()
                 pack = self.engine.decode_staged(staged)  # returns after the H2D + decode of this group completed
                 yield pack
+        finally:
+            self._stager.shutdown(wait=True)
+            self._readers.shutdown(wait=True)
 
     def __iter__(self):
         from .engine import PackedImages
