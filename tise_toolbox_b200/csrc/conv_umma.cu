@@ -697,6 +697,14 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   // pairs: two M tiles per CTA (512 output pixels per work item) where a K block would otherwise hold < 300 tensor
   // cycles against ~600 cycles of producer / MMA-issue instructions (nt <= 64: the 5x5 convolutions)
   if (cs == 2 && passes == 2 && 4 * p.nt <= kAccumCols && cdiv(m_tiles, 4) * p.n_ntiles >= ctx->num_sms / 2) msub = 2;
+  // single pass: the accumulator of an M tile takes nt columns, so two M tiles fit for nt <= 128.  Measured per layer at
+  // 1024 images (profiles/layers_r02_msub_sweep.txt): conv 3b 0.47 -> 0.38 ms, the 5x5 convolutions 0.42 -> 0.36, the
+  // 35 x 35 3x3 convolutions 0.20 -> 0.17 / 0.33 -> 0.27, 17 x 17 128-channel 1x7 0.085 -> 0.074; nt > 128 unchanged.
+  // (TISE_UMMA_MSUB1P=<largest nt> overrides; 0 disables.)  Each M tile still accumulates its K blocks in the same
+  // order, so the output bits do not depend on msub.
+  static int msub1p = -1;
+  if (msub1p < 0) msub1p = getenv("TISE_UMMA_MSUB1P") ? atoi(getenv("TISE_UMMA_MSUB1P")) : 128;
+  if (cs == 2 && passes == 1 && p.nt <= msub1p && 2 * p.nt <= kAccumCols && cdiv(m_tiles, 4) * p.n_ntiles >= ctx->num_sms / 2) msub = 2;
   if (msub_env == 1) msub = 1;
   p.msub = msub;
   p.onebox = (passes == 2 && 2 * p.nt <= 256) ? 1 : 0;
