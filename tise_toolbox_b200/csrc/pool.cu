@@ -81,71 +81,82 @@ __global__ void avgpool3s1p1_kernel(const __half* __restrict__ in, int n, int h,
 // RAW (pre-BN) fp16 output of that convolution (pf = 32..192 channels instead of the block's 192..2048), so
 // avg_pool2d(3,1,1)(count_include_pad) + BN scale/shift + ReLU is applied here.  Exact: conv1x1 and the
 // zero-padded average are both linear and the convolution has no bias.
-// One thread produces a run of kXs horizontally adjacent output pixels of one row for 8 channels from the 3 x (kXs + 2)
-// input window: 3 (kXs + 2) / kXs loads per output instead of 9.  The window loop is fully unrolled with predicated
-// loads, so all loads of a thread are in flight together (the looped version ran at ~2 TB/s, latency-bound).
+// One thread owns kXs horizontally adjacent output columns x 8 channels of one image and walks DOWN the rows with a
+// three-row window of the kXs + 2 input columns in registers: every input value is loaded once per column strip
+// ((kXs + 2) / kXs = 1.5 loads per output instead of the 4.5 of the per-row version, which ran at 7 TB/s of L2 -> SM
+// traffic, i.e. L2-bound, for 2.1-2.7 TB/s of HBM traffic -- profiles/launches_r02_summary.txt).  The loads of row y + 2
+// are issued before row y is evaluated, so a thread never waits for the row it needs next.
 // 32-bit index arithmetic (the host checks the range); consecutive threads take consecutive channel groups (coalesced).
 template <bool kF32, int kXs>
-__global__ void __launch_bounds__(256) avgpool_bn_kernel(const __half* __restrict__ in, int n, int h, int w, int c8, int segs,
+__global__ void __launch_bounds__(128) avgpool_bn_kernel(const __half* __restrict__ in, int n, int h, int w, int c8, int segs,
                                                          const float* __restrict__ scale, const float* __restrict__ shift,
                                                          void* __restrict__ out, int out_stride) {
-  const unsigned total = (unsigned)n * h * segs * c8;
+  const unsigned total = (unsigned)n * segs * c8;
   const int c = c8 * 8;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g = (int)(i % (unsigned)c8);
     unsigned p = i / (unsigned)c8;
     const int sg = (int)(p % (unsigned)segs);
-    p /= (unsigned)segs;
-    const int oy = (int)(p % (unsigned)h);
-    const int img = (int)(p / (unsigned)h);
+    const int img = (int)(p / (unsigned)segs);
     const int x0 = sg * kXs;
-    const __half* row = in + ((size_t)img * h + oy) * w * c + g * 8;
-    const bool up = oy > 0, down = oy + 1 < h;
-    // column sums (the <= 3 valid rows) of columns x0 - 1 ... x0 + kXs
-    float cs[kXs + 2][8];
-#pragma unroll
-    for (int t = 0; t < kXs + 2; ++t) {
-      const int x = x0 - 1 + t;
-      const bool okx = x >= 0 && x < w;
-      uint4 v[3];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const bool ok = okx && (r == 1 || (r == 0 ? up : down));
-        v[r] = ok ? __ldg(reinterpret_cast<const uint4*>(row + (ptrdiff_t)(r - 1) * w * c + (ptrdiff_t)x * c)) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 a = __half22float2(reinterpret_cast<const __half2*>(&v[0])[j]);
-        const float2 b = __half22float2(reinterpret_cast<const __half2*>(&v[1])[j]);
-        const float2 d = __half22float2(reinterpret_cast<const __half2*>(&v[2])[j]);
-        cs[t][2 * j] = a.x + b.x + d.x;
-        cs[t][2 * j + 1] = a.y + b.y + d.y;
-      }
-    }
+    const __half* base = in + (size_t)img * h * w * c + g * 8;
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sc[j] = __ldg(scale + g * 8 + j) * (1.0f / 9.0f);
       sh[j] = __ldg(shift + g * 8 + j);
     }
+    auto load_row = [&](int y, uint4 (&r)[kXs + 2]) {
 #pragma unroll
-    for (int t = 0; t < kXs; ++t) {
-      const int x = x0 + t;
-      if (x < w) {
-        float y8[8];
+      for (int t = 0; t < kXs + 2; ++t) {
+        const int x = x0 - 1 + t;
+        const bool ok = y >= 0 && y < h && x >= 0 && x < w;
+        r[t] = ok ? __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y * w + x) * c)) : make_uint4(0, 0, 0, 0);
+      }
+    };
+    uint4 r0[kXs + 2], r1[kXs + 2], r2[kXs + 2], r3[kXs + 2];  // rows y - 1, y, y + 1 and the prefetched y + 2
+    load_row(-1, r0);
+    load_row(0, r1);
+    load_row(1, r2);
+    for (int y = 0; y < h; ++y) {
+      load_row(y + 2, r3);
+      // column sums of the three rows
+      float cs[kXs + 2][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y8[j] = fmaxf(fmaf(cs[t][j] + cs[t + 1][j] + cs[t + 2][j], sc[j], sh[j]), 0.f);
-        const size_t o = (((size_t)img * h + oy) * w + x) * out_stride + g * 8;
-        if (kF32) {
-          float4* dst = reinterpret_cast<float4*>((float*)out + o);
-          dst[0] = make_float4(y8[0], y8[1], y8[2], y8[3]);
-          dst[1] = make_float4(y8[4], y8[5], y8[6], y8[7]);
-        } else {
-          __half2 hh[4];
+      for (int t = 0; t < kXs + 2; ++t)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) hh[j] = __floats2half2_rn(fminf(y8[2 * j], 65504.f), fminf(y8[2 * j + 1], 65504.f));
-          *reinterpret_cast<uint4*>((__half*)out + o) = *reinterpret_cast<uint4*>(hh);
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = __half22float2(reinterpret_cast<const __half2*>(&r0[t])[j]);
+          const float2 b = __half22float2(reinterpret_cast<const __half2*>(&r1[t])[j]);
+          const float2 d = __half22float2(reinterpret_cast<const __half2*>(&r2[t])[j]);
+          cs[t][2 * j] = a.x + b.x + d.x;
+          cs[t][2 * j + 1] = a.y + b.y + d.y;
         }
+#pragma unroll
+      for (int t = 0; t < kXs; ++t) {
+        const int x = x0 + t;
+        if (x < w) {
+          float y8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y8[j] = fmaxf(fmaf(cs[t][j] + cs[t + 1][j] + cs[t + 2][j], sc[j], sh[j]), 0.f);
+          const size_t o = (((size_t)img * h + y) * w + x) * out_stride + g * 8;
+          if (kF32) {
+            float4* dst = reinterpret_cast<float4*>((float*)out + o);
+            dst[0] = make_float4(y8[0], y8[1], y8[2], y8[3]);
+            dst[1] = make_float4(y8[4], y8[5], y8[6], y8[7]);
+          } else {
+            __half2 hh[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hh[j] = __floats2half2_rn(fminf(y8[2 * j], 65504.f), fminf(y8[2 * j + 1], 65504.f));
+            *reinterpret_cast<uint4*>((__half*)out + o) = *reinterpret_cast<uint4*>(hh);
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < kXs + 2; ++t) {
+        r0[t] = r1[t];
+        r1[t] = r2[t];
+        r2[t] = r3[t];
       }
     }
   }
@@ -191,15 +202,16 @@ int launch_avgpool3s1p1(tise_ctx* ctx, const __half* in, int n, int h, int w, in
 
 int launch_avgpool_bn(tise_ctx* ctx, const __half* in, int n, int h, int w, int c, const float* scale,
                       const float* shift, void* out, int out_stride, int out_f32, cudaStream_t st) {
-  constexpr int kXs = 4;  // pixels per thread
+  constexpr int kXs = 4;  // output columns per thread
   const int segs = (w + kXs - 1) / kXs;
-  const long long total = (long long)n * h * segs * (c / 8);
-  if (total >= (1ll << 31)) return fail(ctx, TISE_ERR_INVALID, "avgpool_bn: batch too large (%lld work items)", total);
-  const int grid = grid_for(total, 256, ctx->num_sms);
+  const long long total = (long long)n * segs * (c / 8);
+  if ((long long)n * h * w * c >= (1ll << 31) * 8 || total >= (1ll << 31))
+    return fail(ctx, TISE_ERR_INVALID, "avgpool_bn: batch too large (%lld work items)", total);
+  const int grid = grid_for(total, 128, ctx->num_sms);
   if (out_f32)
-    avgpool_bn_kernel<true, kXs><<<grid, 256, 0, st>>>(in, n, h, w, c / 8, segs, scale, shift, out, out_stride);
+    avgpool_bn_kernel<true, kXs><<<grid, 128, 0, st>>>(in, n, h, w, c / 8, segs, scale, shift, out, out_stride);
   else
-    avgpool_bn_kernel<false, kXs><<<grid, 256, 0, st>>>(in, n, h, w, c / 8, segs, scale, shift, out, out_stride);
+    avgpool_bn_kernel<false, kXs><<<grid, 128, 0, st>>>(in, n, h, w, c / 8, segs, scale, shift, out, out_stride);
   TISE_LAUNCH_CHECK(ctx);
   return TISE_OK;
 }
