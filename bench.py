@@ -319,7 +319,7 @@ def _emit(text: str) -> None:
     os.write(_RESULT_FD, (text + "\n").encode())
 
 
-def fixed_size_run(eng, host, n_fixed, rank, world, real_stats, barrier, batch=1000):
+def fixed_size_run(eng, host, n_fixed, rank, world, real_stats, barrier, batch=2048):
     """north_star's target: `n_fixed` images (this rank's contiguous shard of them) from pinned host memory through
     H2D -> resize -> trunk -> moments + IS* sums -> ONE packed all-reduce -> (rank 0) Frechet distance against the
     real-set statistics -> FID and IS* scalars on the host.  Returns wall seconds (max over ranks is taken by the
@@ -545,7 +545,7 @@ def main():
                  "finish_ms": runs[1]["finish_ms"], "frechet_ms": runs[1]["frechet_ms"], "fid": runs[1]["fid"],
                  "is_mean": runs[1]["is_mean"], "count": runs[1]["count"],
                  "what": "wall clock (max over ranks) from the first H2D copy to the FID and IS* scalars on rank 0: "
-                         "per-rank shard from pinned host memory in batches of 1000, one packed all-reduce "
+                         "per-rank shard from pinned host memory in batches of 2048, one packed all-reduce "
                          "(finish_ms, every rank finalises mu / sigma / IS*), Frechet distance on rank 0 against "
                          "precomputed real-set statistics (frechet_ms)"}
 

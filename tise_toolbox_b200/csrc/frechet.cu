@@ -556,6 +556,55 @@ __device__ __forceinline__ double block_sum512(double v, double* red16) {
   return s;
 }
 
+// The two passes over a CTA's rows, specialised on the first live column slot CF (= r0 / 512, uniform): no per-slot
+// predicates inside, ~12 instructions per row -- the passes were bound by instruction issue, not by the fp64 pipe.
+template <int CF>
+__device__ __forceinline__ void tr_matvec(const double* __restrict__ S, const double (&areg)[TR_RR][TR_CS],
+                                          const double (&vj)[TR_CS], const double (&wj)[TR_CS], const double (&vnj)[TR_CS],
+                                          double (&acc)[16], const double* s_v, const double* s_w, double* s_col, int t, int G,
+                                          int cta, int r0, int d) {
+  const bool own = t == r0 - CF * TR_THREADS;  // this thread holds column r0 (slot CF)
+#pragma unroll
+  for (int l = 0; l < TR_ROWS; ++l) {
+    const int i = l * G + cta;
+    if (i >= r0 && i < d) {  // (uniform across the CTA)
+      double s0 = 0.0, s1 = 0.0, a_cf = 0.0;
+#pragma unroll
+      for (int c = CF; c < TR_CS; ++c) {
+        const double a = l < TR_RS ? S[l * TR_PITCH + t + c * TR_THREADS] : areg[l < TR_RS ? 0 : l - TR_RS][c];
+        if (c == CF) a_cf = a;
+        if ((c - CF) & 1) s1 = fma(a, vnj[c], s1);
+        else s0 = fma(a, vnj[c], s0);
+      }
+      acc[l] = s0 + s1;
+      // column r0 of this row after the update (= entry i of the next row to finalise): travels with y_i
+      if (own) s_col[l] = fma(-s_w[l], vj[CF], fma(-s_v[l], wj[CF], a_cf));
+    }
+  }
+}
+template <int CF>
+__device__ __forceinline__ void tr_update(double* __restrict__ S, double (&areg)[TR_RR][TR_CS], const double (&vj)[TR_CS],
+                                          const double (&wj)[TR_CS], const double* s_v, const double* s_w, int t, int G, int cta,
+                                          int r0, int d) {
+#pragma unroll
+  for (int l = 0; l < TR_ROWS; ++l) {
+    const int i = l * G + cta;
+    if (i >= r0 && i < d) {
+      const double vi = -s_v[l], wi = -s_w[l];
+#pragma unroll
+      for (int c = CF; c < TR_CS; ++c) {
+        if (l < TR_RS) {
+          double* ap = S + l * TR_PITCH + t + c * TR_THREADS;
+          *ap = fma(wi, vj[c], fma(vi, wj[c], *ap));
+        } else {
+          double& ar = areg[l < TR_RS ? 0 : l - TR_RS][c];
+          ar = fma(wi, vj[c], fma(vi, wj[c], ar));
+        }
+      }
+    }
+  }
+}
+
 template <bool kDbg>
 __global__ void __launch_bounds__(TR_THREADS, 1)
 tri_resident_kernel(const double* __restrict__ M, int d, uint4* xbuf,
@@ -729,25 +778,12 @@ tri_resident_kernel(const double* __restrict__ M, int d, uint4* xbuf,
     // No per-element predicates: columns left of r0 are dead storage (the finished part of a row is never read again)
     // and v_next is zero there, columns >= d hold zeros; a column slot is skipped once ALL of its columns are dead.
     const int c_first = r0 / TR_THREADS;  // first column slot with live columns (uniform)
-#pragma unroll
-    for (int l = 0; l < TR_ROWS; ++l) {
-      const int i = l * G + cta;
-      if (i >= r0 && i < d && !(kDbg && (abl & 1))) {  // (uniform across the CTA)
-        double a[TR_CS];
-#pragma unroll
-        for (int c = 0; c < TR_CS; ++c)
-          if (c >= c_first) a[c] = l < TR_RS ? S[l * TR_PITCH + t + c * TR_THREADS] : areg[l < TR_RS ? 0 : l - TR_RS][c];
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int c = 0; c < TR_CS; c += 2) {
-          if (c >= c_first) s0 = fma(a[c], vnj[c], s0);
-          if (c + 1 >= c_first) s1 = fma(a[c + 1], vnj[c + 1], s1);
-        }
-        acc[l] = s0 + s1;
-        // column r0 of this row after the update (= entry i of the next row to finalise): travels with y_i
-#pragma unroll
-        for (int c = 0; c < TR_CS; ++c)
-          if (t + c * TR_THREADS == r0) s_col[l] = fma(-s_w[l], vj[c], fma(-s_v[cur][l], wj[c], a[c]));
+    if (!(kDbg && (abl & 1))) {
+      switch (c_first) {
+        case 0: tr_matvec<0>(S, areg, vj, wj, vnj, acc, s_v[cur], s_w, s_col, t, G, cta, r0, d); break;
+        case 1: tr_matvec<1>(S, areg, vj, wj, vnj, acc, s_v[cur], s_w, s_col, t, G, cta, r0, d); break;
+        case 2: tr_matvec<2>(S, areg, vj, wj, vnj, acc, s_v[cur], s_w, s_col, t, G, cta, r0, d); break;
+        default: tr_matvec<3>(S, areg, vj, wj, vnj, acc, s_v[cur], s_w, s_col, t, G, cta, r0, d); break;
       }
     }
     TR_MARK(3);
@@ -782,22 +818,12 @@ tri_resident_kernel(const double* __restrict__ M, int d, uint4* xbuf,
     }
     if (last && t == 0 && (d - 1) % G == cta) diag[d - 1] = s_col[(d - 1) / G];
     // ---- the delayed rank-2 update (off the critical path: the next column's values are still in flight)
-#pragma unroll
-    for (int l = 0; l < TR_ROWS; ++l) {
-      const int i = l * G + cta;
-      if (i >= r0 && i < d && !(kDbg && (abl & 1))) {
-        const double vi = -s_v[cur][l], wi = -s_w[l];
-#pragma unroll
-        for (int c = 0; c < TR_CS; ++c)
-          if (c >= c_first) {
-            if (l < TR_RS) {
-              double* ap = S + l * TR_PITCH + t + c * TR_THREADS;
-              *ap = fma(wi, vj[c], fma(vi, wj[c], *ap));
-            } else {
-              double& ar = areg[l < TR_RS ? 0 : l - TR_RS][c];
-              ar = fma(wi, vj[c], fma(vi, wj[c], ar));
-            }
-          }
+    if (!(kDbg && (abl & 1))) {
+      switch (c_first) {
+        case 0: tr_update<0>(S, areg, vj, wj, s_v[cur], s_w, t, G, cta, r0, d); break;
+        case 1: tr_update<1>(S, areg, vj, wj, s_v[cur], s_w, t, G, cta, r0, d); break;
+        case 2: tr_update<2>(S, areg, vj, wj, s_v[cur], s_w, t, G, cta, r0, d); break;
+        default: tr_update<3>(S, areg, vj, wj, s_v[cur], s_w, t, G, cta, r0, d); break;
       }
     }
     TR_MARK(4);
