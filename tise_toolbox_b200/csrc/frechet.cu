@@ -180,54 +180,107 @@ __global__ void zero_upper_kernel(double* A, int d) {
 }
 
 // ---------------------------------------------------------------------------- fp64 GEMM  C = op(A) * B, row-major d x d
+// On the fp64 TENSOR pipe (mma.sync.m8n8k4.f64 -> DMMA; the CUDA-core fp64 rate of this part is a quarter of it: the
+// FMA version of this kernel ran at 7.6 TFLOP/s).  One CTA owns a 128 x 128 tile of C: 16 warps, each a 32 x 32 sub-tile
+// = 4 x 4 DMMA tiles; op(A) and B stream through shared memory 16 k at a time, register-prefetched one chunk ahead.
+// Fragments of m8n8k4: lane T holds A[T / 4][T % 4], B[T % 4][T / 4], C[T / 4][2 (T % 4) + {0, 1}]; both operands are
+// kept k-major in shared memory ([k][m] and [k][n], row pitch 132 doubles: conflict-free fragment reads).
+constexpr int GT = 128, GKC = 16, GPITCH = GT + 4;
+
+__device__ __forceinline__ void fr_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
 template <bool TA>
-__global__ void __launch_bounds__(256) dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B,
+__global__ void __launch_bounds__(512) dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B,
                                                     double* __restrict__ Cm, int d) {
-  constexpr int BM = 64, BN = 64, BK = 16;
-  __shared__ double sa[BK][BM + 1];
-  __shared__ double sb[BK][BN + 1];
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  __shared__ double sa[GKC][GPITCH];
+  __shared__ double sb[GKC][GPITCH];
+  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
   // Both products have a lower-triangular factor (L[k][j] = 0 for k < j, exact zeros from zero_upper_kernel):
   //   TA = false: T = S2 L      -> only k >= n0 contributes to column block n0        (half of the k range on average)
   //   TA = true:  M = L^T T     -> only k >= m0 contributes to row block m0, and M is symmetric: tiles above the
-  //                                diagonal are not computed at all (mirror_lower_kernel fills them)   (a quarter)
+  //                                diagonal are not computed at all (symmetrize_kernel fills them)   (a quarter)
   if (TA && n0 > m0) return;
   const int k_begin = TA ? m0 : n0;
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  double acc[4][4] = {};
-  for (int k0 = k_begin; k0 < d; k0 += BK) {
-    for (int t = threadIdx.x; t < BM * BK; t += 256) {
-      if (TA) {  // op(A)[m][k] = A[k][m]: consecutive threads walk m (contiguous)
-        const int kk = t / BM, mm = t % BM;
-        sa[kk][mm] = (m0 + mm < d && k0 + kk < d) ? A[(size_t)(k0 + kk) * d + m0 + mm] : 0.0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wa = (warp >> 2) * 32, wb = (warp & 3) * 32;
+  const int fr = lane >> 2, fk = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  // loaders.  [k][x] operands (B always, op(A) = A^T when TA): thread -> (k = tid / 32, 4 consecutive x = 4 (tid % 32)).
+  // A not transposed ([m][k] in memory): thread -> (m = tid % 128, 4 consecutive k = 4 (tid / 128)), stored transposed.
+  const int lk = threadIdx.x >> 5, lx = (threadIdx.x & 31) * 4;
+  const int tm = threadIdx.x & 127, tk = (threadIdx.x >> 7) * 4;
+  double ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ra[u] = rb[u] = 0.0;
+    if (k0 + lk < d) {
+      if (n0 + lx + 3 < d) {
+        const double2 v0 = __ldg(reinterpret_cast<const double2*>(B + (size_t)(k0 + lk) * d + n0 + lx));
+        const double2 v1 = __ldg(reinterpret_cast<const double2*>(B + (size_t)(k0 + lk) * d + n0 + lx + 2));
+        rb[0] = v0.x; rb[1] = v0.y; rb[2] = v1.x; rb[3] = v1.y;
       } else {
-        const int mm = t / BK, kk = t % BK;
-        sa[kk][mm] = (m0 + mm < d && k0 + kk < d) ? A[(size_t)(m0 + mm) * d + k0 + kk] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (n0 + lx + u < d) rb[u] = __ldg(B + (size_t)(k0 + lk) * d + n0 + lx + u);
       }
-      const int kb = t / BN, nn = t % BN;
-      sb[kb][nn] = (n0 + nn < d && k0 + kb < d) ? B[(size_t)(k0 + kb) * d + n0 + nn] : 0.0;
     }
-    __syncthreads();
+    if (TA) {
+      if (k0 + lk < d) {
+        if (m0 + lx + 3 < d) {
+          const double2 v0 = __ldg(reinterpret_cast<const double2*>(A + (size_t)(k0 + lk) * d + m0 + lx));
+          const double2 v1 = __ldg(reinterpret_cast<const double2*>(A + (size_t)(k0 + lk) * d + m0 + lx + 2));
+          ra[0] = v0.x; ra[1] = v0.y; ra[2] = v1.x; ra[3] = v1.y;
+        } else {
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      double a[4], b[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = sa[kk][ty * 4 + u];
-#pragma unroll
-      for (int v = 0; v < 4; ++v) b[v] = sb[kk][tx * 4 + v];
+          for (int u = 0; u < 4; ++u)
+            if (m0 + lx + u < d) ra[u] = __ldg(A + (size_t)(k0 + lk) * d + m0 + lx + u);
+        }
+      }
+    } else if (m0 + tm < d) {
 #pragma unroll
       for (int u = 0; u < 4; ++u)
+        if (k0 + tk + u < d) ra[u] = __ldg(A + (size_t)(m0 + tm) * d + k0 + tk + u);
+    }
+  };
+  fetch(k_begin);
+  for (int k0 = k_begin; k0 < d; k0 += GKC) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    for (int u = 0; u < 4; ++u) {
+      sb[lk][lx + u] = rb[u];
+      if (TA) sa[lk][lx + u] = ra[u];
+      else sa[tk + u][tm] = ra[u];
+    }
+    __syncthreads();
+    if (k0 + GKC < d) fetch(k0 + GKC);
+#pragma unroll
+    for (int kk = 0; kk < GKC; kk += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = sa[kk + fk][wa + 8 * i + fr];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = sb[kk + fk][wb + 8 * j + fr];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fr_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const int i = m0 + ty * 4 + u, j = n0 + tx * 4 + v;
-      if (i < d && j < d) Cm[(size_t)i * d + j] = acc[u][v];
+    for (int j = 0; j < 4; ++j) {
+      const int r = m0 + wa + 8 * i + fr, c = n0 + wb + 8 * j + 2 * fk;
+      if (r < d && c < d) Cm[(size_t)r * d + c] = acc[i][j][0];
+      if (r < d && c + 1 < d) Cm[(size_t)r * d + c + 1] = acc[i][j][1];
     }
 }
 
@@ -1028,10 +1081,10 @@ static int frechet_once(tise_ctx* ctx, const double* mu1, const double* s1, cons
   TISE_LAUNCH_CHECK(ctx);
 
   // 2. M = L^T (S2 L)
-  const dim3 gg((d + 63) / 64, (d + 63) / 64);
-  dgemm_kernel<false><<<gg, 256, 0, st>>>(S2, L, T, d);
+  const dim3 gg((d + GT - 1) / GT, (d + GT - 1) / GT);
+  dgemm_kernel<false><<<gg, 512, 0, st>>>(S2, L, T, d);
   TISE_LAUNCH_CHECK(ctx);
-  dgemm_kernel<true><<<gg, 256, 0, st>>>(L, T, M, d);
+  dgemm_kernel<true><<<gg, 512, 0, st>>>(L, T, M, d);
   TISE_LAUNCH_CHECK(ctx);
   symmetrize_kernel<<<nel_blocks, 256, 0, st>>>(M, d);
   TISE_LAUNCH_CHECK(ctx);
