@@ -518,7 +518,7 @@ def main():
         pass
 
     model = InceptionV3([3], engine=eng)
-    kd = max(2, K // 4)
+    kd = max(2, K // 2)
     hb = HostBatches([host_batch(s) for s in range(kd)])
     fid_score.calculate_activation_statistics(HostBatches(hb[:2]), model, batch_size=B, verbose=False)  # warm-up
     barrier()
@@ -582,15 +582,15 @@ def main():
                 "algorithmic_gflop_per_image": conv_flops / (2 * B) / 1e9,
                 "share_of_trunk_time": conv_ms / trunk_ms if trunk_ms else None,
                 "other_kernels_ms_per_step": {k: v[0] / 2 for k, v in prof.items() if k != "conv"},
-                "note": "algorithmic FLOPs; default operand policy: one MMA pass per FLOP in conv_umma_kernel, two in "
+                "note": "algorithmic FLOPs; default operand policy: one MMA pass per FLOP in conv_umma_kernel and "
                         "conv_flat_kernel (strict policy: two everywhere)",
                 "how": "cudaEvent pairs on the launch stream around each launch, summed over 2 steps after the timed region"}
 
     line = {"metric": "FID/IS* images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": (("f16 x (f16 hi + f16 lo) operands, f32 accumulate" if eng.pass1_max_hw == 0 else
-                       "f16 x f16 (W_hi) operands + calibrated mean-field W_lo term, f32 accumulate (stem layers: "
-                       "f16 x (f16 hi + f16 lo))") if args.passes == 2 else "f16, f32 accumulate"),
+                       "f16 x f16 (W_hi) operands + calibrated mean-field W_lo term, f32 accumulate (Conv2d_1a: "
+                       "f16 (hi + lo) input x f16 (hi + lo) weights)") if args.passes == 2 else "f16, f32 accumulate"),
             "data": "synthetic",
             "config": {"workload": ("cfg2: IS* (bird head, T=0.598, 10 splits) + FID moments" if world == 1 else
                                     "cfg3: FID + IS* sharded over %d GPUs, one all-reduce at the end" % world),

@@ -259,3 +259,45 @@ def test_device_image_loader_grouping_with_a_stub_engine(tmp_path):
     sizes = [len(b) for b in loader]
     assert sizes == [10] * 10 + [3] and len(loader) == 11
     assert sum(len(g) for g in img_data.DeviceImageLoader(names[:7], StubEngine(), 10, drop_last=True).groups()) == 0
+    # ramp-up and chaining: a short first group (the GPU starts after ~1000 files), and the NEXT loader's first group is
+    # staged before this loader's last group is decoded (fid_score.calculate_fid_given_paths walks two folders like this)
+    events = []
+
+    class Recorder(StubEngine):
+        def stage_files(self, paths, pool=None):
+            events.append(("stage", os.path.basename(paths[0])[0], len(paths)))
+            return super().stage_files(paths, pool)
+
+        def decode_staged(self, staged):
+            import time
+
+            time.sleep(0.2)  # (the GPU work of a group; the next group's file reads must have started by its end)
+            events.append(("decoded", os.path.basename(staged["paths"][0])[0], len(staged["paths"])))
+            return super().decode_staged(staged)
+
+    eng = Recorder()
+    a = img_data.DeviceImageLoader([str(tmp_path / ("a%04d.png" % i)) for i in range(5020)], eng, 50, drop_last=True)
+    b = img_data.DeviceImageLoader([str(tmp_path / ("b%04d.png" % i)) for i in range(1200)], eng, 50, drop_last=True)
+    assert [len(g) for g in a._group_lists()] == [1000, 4000] and [len(g) for g in b._group_lists()] == [1200]
+    n_a = sum(len(p) for p in a.groups(next_loader=b))
+    n_b = sum(len(p) for p in b.groups())
+    assert (n_a, n_b) == (5000, 1200)
+    assert events.index(("stage", "b", 1200)) < events.index(("decoded", "a", 4000))
+    assert events.index(("stage", "a", 4000)) < events.index(("decoded", "a", 1000))
+
+
+def test_build_is_serialised_across_processes(tmp_path):
+    """torchrun starts one process per GPU and every one of them calls build_library(): with a fresh library none of
+    them rebuilds, and the lock file / atomic rename keep concurrent callers from corrupting the .so."""
+    import subprocess
+    import sys
+
+    from tise_toolbox_b200 import build
+
+    before = os.path.getmtime(build.build_library())
+    code = "from tise_toolbox_b200 import build; print(build.build_library())"
+    procs = [subprocess.Popen([sys.executable, "-c", code], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                              stdout=subprocess.PIPE, text=True) for _ in range(4)]
+    outs = [p.communicate(timeout=600)[0].strip() for p in procs]
+    assert all(p.returncode == 0 for p in procs) and all(o.endswith("libtise_b200.so") for o in outs), outs
+    assert os.path.getmtime(build.LIB) == before  # nobody rebuilt a fresh library

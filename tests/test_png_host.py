@@ -236,6 +236,12 @@ def test_c_abi_probe_reports_what_the_device_handles():
     jpg = io.BytesIO()
     Image.fromarray(smooth_image(rng, 32, 32, 3)).save(jpg, "JPEG")
     assert lib.tise_png_probe(jpg.getvalue(), len(jpg.getvalue()), C.byref(info)) < 0 and info.supported == 0
+    # a scanline that does not fit the unfilter kernel's shared memory (two rows) is reported at probe time, so that one
+    # such file in a folder takes the host decoder instead of failing the whole tise_png_decode call
+    for width, want in ((38000, 1), (40000, 0)):
+        blob = png_bytes(np.zeros((1, width, 3), dtype=np.uint8))
+        assert lib.tise_png_probe(blob, len(blob), C.byref(info)) == 0 and info.width == width
+        assert info.supported == want, (width, info.supported)
 
 
 def _filter_rows(rows, bpp, filters):

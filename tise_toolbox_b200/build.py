@@ -44,10 +44,27 @@ def _stale() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compiles csrc/*.cu and links libtise_b200.so if it is missing or older than its sources.  Several processes may
+    call this at once (torchrun: one per GPU): the build is serialised with a file lock, whoever gets it second finds
+    the library fresh; the link goes to a temporary name and is renamed into place, so a reader never maps a
+    half-written file."""
     if not force and not _stale():
         return LIB
-    nvcc = _nvcc()
+    import fcntl
+
     os.makedirs(OBJ_DIR, exist_ok=True)
+    with open(os.path.join(OBJ_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():  # another process built it while this one waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
+    nvcc = _nvcc()
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
@@ -63,10 +80,12 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.replace(tmp, LIB)
     return LIB
 
 

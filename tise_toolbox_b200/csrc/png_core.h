@@ -403,7 +403,8 @@ TISE_HD int filter_bpp_of(int color_type, int bit_depth) {
 }
 // What convert("RGB") of Pillow's decoder is reproduced for: 8-bit everything; 16-bit RGB / RGBA / grey+alpha (Pillow
 // keeps the high byte); 1/2/4-bit grey (scaled to 0..255) and palette.  16-bit grey opens as "I;16", whose conversion
-// to RGB saturates instead of scaling -- left to the host together with Adam7 interlacing.
+// to RGB saturates instead of scaling -- left to the host.  (Adam7-interlaced files of the supported depths are decoded
+// on the device: seven filtered sub-images scattered into place.)
 TISE_HD bool depth_supported(int color_type, int bit_depth) {
   if (bit_depth == 8) return samples_of(color_type) > 0;
   if (bit_depth == 16) return color_type == 2 || color_type == 4 || color_type == 6;

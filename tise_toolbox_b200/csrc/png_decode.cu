@@ -117,6 +117,8 @@ static PngWs png_ws_layout(long long n, long long n_seg, long long stream_bytes,
 static inline long long pad_stream(long long b) { return (long long)align_up((size_t)b + 16, 16); }
 static inline long long pad_raw(long long b) { return (long long)align_up((size_t)b, 16); }
 
+constexpr long long kPngRowSmemBudget = 232448 - 1024;  // two scanlines next to the kernel's static shared memory
+
 static void fill_info(const png::Header& h, tise_png_info* info) {
   info->width = h.width;
   info->height = h.height;
@@ -142,6 +144,10 @@ extern "C" int tise_png_probe(const uint8_t* h_file, int64_t file_bytes, tise_pn
     info->supported = 0;
     return TISE_ERR_INVALID;
   }
+  // the unfilter kernel keeps two scanlines in shared memory: a file whose scanline does not fit in the smallest opt-in
+  // limit this library runs with (227 KB) is reported as unsupported HERE, so callers route it to their host decoder
+  // instead of having a whole tise_png_decode call rejected later
+  if (2 * (long long)png::stride_of(h.width, h.color_type, h.bit_depth) > kPngRowSmemBudget) info->supported = 0;
   return TISE_OK;
 }
 
@@ -185,8 +191,8 @@ extern "C" int tise_png_decode(tise_ctx* ctx, const uint8_t* h_files, const uint
     });
     if (rc || !h.supported)
       return fail(ctx, TISE_ERR_INVALID,
-                  "tise_png_decode: file %d is %s (tise_png_probe reports what the device decoder handles: 8-bit, "
-                  "non-interlaced PNG)",
+                  "tise_png_decode: file %d is %s (tise_png_probe reports what the device decoder handles: every "
+                  "colour type at 8 bits, 16-bit RGB / RGBA / grey+alpha, 1/2/4-bit grey / palette, plain or Adam7)",
                   i, rc ? "not a well-formed PNG" : "a PNG variant the device decoder does not handle");
     (void)seg0;
     PngDesc& d = descs[i];

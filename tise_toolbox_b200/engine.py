@@ -306,7 +306,9 @@ class Engine:
             list(pool.map(lambda lo: read_range(lo, min(m, lo + step)), range(0, m, step)))
         else:
             read_range(0, m)
-        return self._probe_staged(pinned, f_off, sizes)
+        staged = self._probe_staged(pinned, f_off, sizes)
+        staged["names"] = list(paths)  # for error messages
+        return staged
 
     def decode_staged_png(self, staged: dict, d_files: torch.Tensor, index: np.ndarray, out: torch.Tensor,
                           out_off: np.ndarray, jpeg: bool = False) -> torch.Tensor:
@@ -383,7 +385,9 @@ class Engine:
                 st = status.cpu().numpy()  # synchronises: the pinned staging buffer may be reused afterwards
                 if st.any():
                     k = int(np.nonzero(st)[0][0])
-                    raise ImageDecodeError("corrupt %s stream in file %d (decoder status %d)" % (what, int(idx[k]), int(st[k])))
+                    names = staged.get("names")
+                    where = "%r (file %d of the group)" % (names[int(idx[k])], int(idx[k])) if names else "file %d" % int(idx[k])
+                    raise ImageDecodeError("corrupt %s stream in %s (decoder status %d)" % (what, where, int(st[k])))
         for i, a in host_imgs.items():
             o = int(out_off[i])
             out[o:o + a.size].copy_(torch.from_numpy(a.reshape(-1)))
