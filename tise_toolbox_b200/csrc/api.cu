@@ -106,6 +106,7 @@ extern "C" int tise_set_pass_policy(tise_ctx* ctx, int single_pass_max_hw) {
 extern "C" int tise_set_input_lut(tise_ctx* ctx, const float* h_lut768) {
   if (!ctx) return TISE_ERR_INVALID;
   if (!h_lut768) return fail(ctx, TISE_ERR_INVALID, "tise_set_input_lut: null table");
+  DeviceRestore restore;  // the caller's current device is left as it was
   TISE_CUDA(ctx, cudaSetDevice(ctx->device));
   TISE_CUDA(ctx, cudaMemcpy(ctx->d_lut, h_lut768, 768 * sizeof(float), cudaMemcpyHostToDevice));
   ctx->lut_set = true;
@@ -116,6 +117,7 @@ extern "C" int tise_load_inception(tise_ctx* ctx, const tise_weight_desc* tensor
   if (!ctx) return TISE_ERR_INVALID;
   if (!tensors || n_tensors <= 0 || num_classes < 0)
     return fail(ctx, TISE_ERR_INVALID, "tise_load_inception: no tensors");
+  DeviceRestore restore;  // the caller's current device is left as it was
   TISE_CUDA(ctx, cudaSetDevice(ctx->device));
   int rc = net_load(ctx, tensors, n_tensors, num_classes);
   if (rc) {
@@ -129,6 +131,7 @@ extern "C" int tise_load_inception(tise_ctx* ctx, const tise_weight_desc* tensor
 extern "C" int tise_calibrate_single_pass(tise_ctx* ctx, int n_images, void* d_ws, size_t ws_bytes, tise_stream stream) {
   if (!ctx) return TISE_ERR_INVALID;
   if (!d_ws) return fail(ctx, TISE_ERR_INVALID, "tise_calibrate_single_pass: null workspace");
+  DeviceRestore restore;  // the caller's current device is left as it was
   TISE_CUDA(ctx, cudaSetDevice(ctx->device));
   return net_calibrate_lo(ctx, n_images, d_ws, ws_bytes, (cudaStream_t)stream);
 }
@@ -152,6 +155,7 @@ extern "C" int tise_debug_conv(tise_ctx* ctx, int impl, int passes, const void* 
   if (!ctx) return TISE_ERR_INVALID;
   if (!d_x || !h_w || !h_scale || !h_shift || !d_y) return fail(ctx, TISE_ERR_INVALID, "tise_debug_conv: null argument");
   if (passes != 1 && passes != 2) return fail(ctx, TISE_ERR_INVALID, "tise_debug_conv: passes %d", passes);
+  DeviceRestore restore;  // the caller's current device is left as it was
   TISE_CUDA(ctx, cudaSetDevice(ctx->device));
   ConvLayer L;
   L.cin = cin;
