@@ -676,18 +676,24 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const __half* __restri
     acc += (double)__half2float(in[p * stride + c]);
   atomicAdd(sum + c, acc);
 }
-// shift1[co] = shift[co] + scale[co] * sum_k W_lo[co][k] * mean[channel of k]      (one warp per output channel)
+// shift1[co] = shift[co] + scale[co] * sum_k W_lo[co][k] * mean[channel of k] * valid[tap of k]   (one warp per output channel)
+// valid[tap]: fraction of the layer's output positions for which that filter tap reads a real pixel rather than zero
+// padding (17 x 17 maps with 1x7 filters: 14/17 for the outermost taps, 8 x 8 maps with 3x3: 7/8 per padded direction).
+// Without it the constant over-corrects every border position, which left ~10 % of the uncorrected mean shift in place.
+struct TapValid {
+  float v[64];
+};
 __global__ void __launch_bounds__(256) lo_correction_kernel(const __half* __restrict__ w, int ktot, int cin_pad, int cin, int cin_phys,
                                                             int nt, int cout, const double* __restrict__ sum, double inv_pixels,
                                                             const float* __restrict__ scale, const float* __restrict__ shift,
-                                                            float* __restrict__ shift1) {
+                                                            float* __restrict__ shift1, const TapValid valid) {
   const int co = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (co >= cout) return;
   const __half* lo = w + (((size_t)(co / nt) * 2 + 1) * nt + co % nt) * ktot;
   double acc = 0.0;
   for (int k = lane; k < ktot; k += 32) {
-    const int cc = k % cin_pad;
-    if (cc < cin) acc += (double)__half2float(lo[k]) * (sum[cc % cin_phys] * inv_pixels);
+    const int cc = k % cin_pad, tap = k / cin_pad;
+    if (cc < cin) acc += (double)__half2float(lo[k]) * (sum[cc % cin_phys] * inv_pixels) * (double)valid.v[tap < 64 ? tap : 63];
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -737,8 +743,26 @@ int net_calibrate_lo(tise_ctx* ctx, int n, void* d_ws, size_t ws_bytes, cudaStre
       if (slices > 1024) slices = 1024;
       if (slices < 1) slices = 1;
       channel_sum_kernel<<<dim3((cin_phys + 31) / 32, slices), 256, 0, st>>>(in, pixels, stride, cin_phys, d_sum);
+      TapValid tv;
+      for (int t = 0; t < 64; ++t) tv.v[t] = 1.0f;
+      static int tv_env = -1;
+      if (tv_env < 0) tv_env = getenv("TISE_LO_TAPVALID") ? atoi(getenv("TISE_LO_TAPVALID")) : 1;
+      if (!flat && tv_env && L.R * L.S <= 64) {  // (flat layers: their padding is part of the grid the mean was taken over)
+        auto frac = [](int n_in, int n_out, int str, int pad, int tap) {  // output positions whose tap lands inside [0, n_in)
+          int ok = 0;
+          for (int o = 0; o < n_out; ++o) {
+            const int i = o * str - pad + tap;
+            ok += i >= 0 && i < n_in;
+          }
+          return n_out > 0 ? (float)ok / (float)n_out : 1.0f;
+        };
+        for (int r = 0; r < L.R; ++r)
+          for (int sx = 0; sx < L.S; ++sx)
+            tv.v[r * L.S + sx] = frac(s.conv.h, s.conv.ho, L.stride, L.pad_h, r) *
+                                 (L.fold > 1 ? 1.0f : frac(s.conv.w, s.conv.wo, L.stride, L.pad_w, sx));
+      }
       lo_correction_kernel<<<(L.cout + 7) / 8, 256, 0, st>>>(L.d_w, L.ktot, L.cin_pad, L.cin, cin_phys, L.nt, L.cout, d_sum,
-                                                            1.0 / (double)pixels, L.d_scale, L.d_shift, L.d_shift1);
+                                                            1.0 / (double)pixels, L.d_scale, L.d_shift, L.d_shift1, tv);
     }
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
