@@ -28,7 +28,12 @@
 
 namespace tise {
 
-constexpr int kFlatThreads = 320;  // producer warp, MMA warp, 2 epilogue groups of 4 warps (one per accumulator stage)
+// The epilogue of these layers is a latency chain per warp (~250 dependent instructions per 128 x 32 box: TMEM load, scale /
+// shift, pack, staging, stores) and with two groups it set the pace (ablation: a third of the MMAs and no global stores still
+// left 70 % of the time).  Four groups of 4 warps, one per accumulator stage of 128 TMEM columns, double its throughput.
+constexpr int kFlatGroups = 4;
+constexpr int kFlatAccCols = 512 / kFlatGroups;  // TMEM columns per accumulator stage
+constexpr int kFlatThreads = 64 + 128 * kFlatGroups;  // producer warp, MMA warp, kFlatGroups epilogue groups of 4 warps
 constexpr int kFlatMaxStages = 8;
 constexpr int kFlatEpiBuf = 128 * 64;
 
@@ -52,6 +57,7 @@ struct FlatParams {
   int wtile_bytes;          // one tap's weights: 2 * nt rows
   int stages, stage_bytes, num_tiles, relu;
   int pdl;  // launched with programmatic stream serialization
+  int debug;  // timing ablations (TISE_FLAT_DEBUG; results are garbage): 1 only the first filter row's MMAs, 2 no global stores
 };
 
 // TR, TS, TK: compile-time filter size and K steps (0: taken from the parameters at run time).  The MMA warp is a single
@@ -67,13 +73,13 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t w_base = smem_base;
   const uint32_t st_base = (w_base + (uint32_t)(taps * p.wtile_bytes) + 1023u) & ~1023u;
   const uint32_t epi_base = st_base + (uint32_t)p.stages * (uint32_t)p.stage_bytes;
-  const uint32_t ss_base = epi_base + 4u * kFlatEpiBuf;
+  const uint32_t ss_base = epi_base + 2u * kFlatGroups * kFlatEpiBuf;
   const uint32_t bar_base = ss_base + 2u * 128u * 4u;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(kFlatMaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kFlatMaxStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kFlatMaxStages + 2 + s); };
-  const uint32_t wfull_bar = bar_base + 8u * (2 * kFlatMaxStages + 4);
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kFlatMaxStages + kFlatGroups + s); };
+  const uint32_t wfull_bar = bar_base + 8u * (2 * kFlatMaxStages + 2 * kFlatGroups);
   const uint32_t tmem_slot = wfull_bar + 8u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -83,7 +89,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kFlatGroups; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4);
     }
@@ -157,11 +163,11 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const uint64_t adesc0 = make_smem_desc(st_base + (uint32_t)stage * stage_bytes, dhi);
       if (elect_one()) {
         for (int t = 0; t < tsub; ++t) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256) + (uint32_t)t * acc_cols;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * kFlatAccCols) + (uint32_t)t * acc_cols;
           const uint64_t at = adesc0 + (uint64_t)((uint32_t)t * tile_step);
           if (TR && TS && TK) {
 #pragma unroll
-            for (int r = 0; r < TR; ++r)
+            for (int r = 0; r < ((p.debug & 1) ? 1 : TR); ++r)
 #pragma unroll
               for (int s2 = 0; s2 < TS; ++s2)
 #pragma unroll
@@ -192,14 +198,14 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         stage = 0;
         phase ^= 1u;
       }
-      if (++as == 2) {
+      if (++as == kFlatGroups) {
         as = 0;
         aphase ^= 1u;
       }
     }
   } else {
     // ===================================================================== epilogue (warps 2..5 and 6..9)
-    // two groups, one per accumulator stage: group g drains this CTA's tiles number g, g + 2, ... (see conv_umma.cu)
+    // kFlatGroups groups, one per accumulator stage: group g drains this CTA's items number g, g + kFlatGroups, ...
     const int grp = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
@@ -222,17 +228,19 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint32_t box_it = 0;
     const int tsub = p.tsub;
     const long long item_pos = (long long)tsub * kBlockM;
-    for (int item = blockIdx.x + grp * gridDim.x; item < p.num_tiles; item += 2 * gridDim.x) {
+    for (int item = blockIdx.x + grp * gridDim.x; item < p.num_tiles; item += kFlatGroups * gridDim.x) {
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       for (int t = 0; t < tsub; ++t) {
         const long long v0 = (long long)item * item_pos + (long long)t * kBlockM;
         // is this thread's output position a real output or a wrap-around cell of the padded grid (written as 0)?
-        const long long v = v0 + row;
-        const int rem = (int)(v % hpwp);
-        const int y = rem / wp, x = rem - y * wp;
-        const bool valid = v < p.total && y < ho && x < wo;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 256 + t * p.passes * nt);
+        // (32-bit arithmetic: a 64-bit modulo is a ~100-instruction dependent chain in front of every tile's epilogue;
+        // the host guarantees total < 2^31)
+        const unsigned v = (unsigned)v0 + (unsigned)row;
+        const unsigned rem = v % (unsigned)hpwp;
+        const int y = (int)(rem / (unsigned)wp), x = (int)(rem - (unsigned)y * (unsigned)wp);
+        const bool valid = (long long)v < p.total && y < ho && x < wo;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kFlatAccCols + t * p.passes * nt);
         for (int c0 = 0; c0 < nt; c0 += 32, ++box_it) {
           const uint32_t buf = my_epi + (box_it & 1u) * kFlatEpiBuf;
           float f[32];
@@ -285,7 +293,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int i = 0; i < 4; ++i) {
               const int r = st_row0 + 32 * i;
               const long long mo = v0 + r + p.out_shift;
-              if (mo < p.out_total && v0 + r < p.total) {
+              if (mo < p.out_total && v0 + r < p.total && !(p.debug & 2)) {
                 const uint4 val = ld_shared_v4(buf + (uint32_t)r * 64u + (((uint32_t)st_chunk ^ (uint32_t)((r >> 1) & 3)) << 4));
                 *reinterpret_cast<uint4*>(obase + (size_t)mo * pitch) = val;
               }
@@ -308,8 +316,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 // ----------------------------------------------------------------------------- host side
 static PFN_cuTensorMapEncodeTiled_v12000 g_flat_encode = nullptr;
 
-bool conv_flat_supported(const ConvLayer& L) {
-  return L.stride == 1 && (L.cin == 32 || L.cin == 64) && L.cout <= 128 && L.cout % 32 == 0 && L.kc == L.cin &&
+bool conv_flat_supported(const ConvLayer& L) {  // (two passes of nt columns must fit one accumulator stage)
+  return L.stride == 1 && (L.cin == 32 || L.cin == 64) && 2 * L.cout <= kFlatAccCols && L.cout % 32 == 0 && L.kc == L.cin &&
          L.nt == L.cout && L.S <= 7 && L.R <= 7;
 }
 
@@ -322,16 +330,17 @@ struct FlatGeom {
 };
 static FlatGeom flat_geometry(const ConvLayer& L, int wp, int smem_limit, int passes) {
   const int row_bytes = L.cin * 2;
-  const int fixed = 1024 + (int)align_up((size_t)L.R * L.S * passes * L.nt * row_bytes, 1024) + 4 * kFlatEpiBuf + 2 * 128 * 4 +
-                    8 * (2 * kFlatMaxStages + 6) + 16;
+  const int fixed = 1024 + (int)align_up((size_t)L.R * L.S * passes * L.nt * row_bytes, 1024) + 2 * kFlatGroups * kFlatEpiBuf + 2 * 128 * 4 +
+                    8 * (2 * kFlatMaxStages + 2 * kFlatGroups + 2) + 16;
   static int t_env = -1;
   if (t_env < 0) t_env = getenv("TISE_FLAT_T") ? atoi(getenv("TISE_FLAT_T")) : 0;
   // Sharing one run among T tiles cuts the TMA rows per output, but these kernels are bound by the shared-memory reads
   // of the MMA operands (A: 4 KB per M = 128, K = 16 step whatever N is), not by the fills: measured, T > 1 gains 7 % at
   // N = 64 (two-pass cout = 32) and loses 7 % at N = 128 (larger work items, fewer stages) -- so only narrow tiles share.
-  int tmax = (passes * L.nt <= 64) ? 256 / (passes * L.nt) : 1;
+  int tmax = (passes * L.nt <= 64) ? kFlatAccCols / (passes * L.nt) : 1;
   if (tmax > 4) tmax = 4;
-  if (t_env > 0) tmax = t_env < 256 / (passes * L.nt) ? t_env : 256 / (passes * L.nt);
+  if (t_env > 0) tmax = t_env < kFlatAccCols / (passes * L.nt) ? t_env : kFlatAccCols / (passes * L.nt);
+  if (tmax < 1) tmax = 1;
   FlatGeom g{1, 1, 0, 0, 0};
   for (int t = tmax; t >= 1; --t) {
     const int run_rows = t * kBlockM + (L.R - 1) * wp + L.S - 1;
@@ -393,6 +402,7 @@ int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const
   p.passes = passes;
   p.out = a.out;
   p.total = (long long)a.n * a.hp * a.wp;
+  if (p.total + 4 * kBlockM >= (1ll << 31)) return fail(ctx, TISE_ERR_INVALID, "flat conv: batch too large (%lld positions)", p.total);
   p.out_total = p.total;
   p.out_stride = L.cout;
   p.wp = a.wp;
@@ -409,6 +419,9 @@ int launch_conv_flat(tise_ctx* ctx, const ConvLayer& L, const FlatArgs& a, const
   p.nt = L.cout;
   p.wtile_bytes = passes * L.nt * p.row_bytes;
   p.relu = a.relu;
+  static int dbg_env = -1;
+  if (dbg_env < 0) dbg_env = getenv("TISE_FLAT_DEBUG") ? atoi(getenv("TISE_FLAT_DEBUG")) : 0;
+  p.debug = dbg_env;
 
   static PerDeviceFlag configured;
   const int smem_limit = ctx->smem_optin > 0 ? ctx->smem_optin : 232448;

@@ -282,9 +282,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       int img[2], wc[2], hc[2];  // base pixel (tap 0,0) of each M tile
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
-        const long long m0 = (long long)(m_tile + sub) * kBlockM;
-        img[sub] = (int)(m0 / p.ho_wo);
-        const int rem = (int)(m0 - (long long)img[sub] * p.ho_wo);
+        // 32-bit arithmetic (the host guarantees M + 512 < 2^31): a 64-bit division is a ~100-instruction dependent
+        // chain, and this warp's instruction stream is what bounds most layers
+        const unsigned m0 = (unsigned)(m_tile + sub) * (unsigned)kBlockM;
+        img[sub] = (int)(m0 / (unsigned)p.ho_wo);
+        const int rem = (int)(m0 - (unsigned)img[sub] * (unsigned)p.ho_wo);
         const int oy = rem / p.wo, ox = rem - oy * p.wo;
         wc[sub] = ox * p.stride - p.pad_w;
         hc[sub] = oy * p.stride - p.pad_h;
@@ -651,6 +653,7 @@ int launch_conv_umma(tise_ctx* ctx, const ConvLayer& L, const ConvArgs& a, const
   p.scale = L.d_scale;
   p.shift = (passes == 1 && L.d_shift1) ? L.d_shift1 : L.d_shift;
   p.M = (long long)a.n * a.ho * a.wo;
+  if (p.M + 4 * kBlockM >= (1ll << 31)) return fail(ctx, TISE_ERR_INVALID, "umma conv: batch too large (%lld output pixels)", p.M);
   int end = 0;
   for (int i = 0; i < kMaxSegs; ++i) {
     const ConvSeg& sg = a.segs[i < a.n_segs ? i : a.n_segs - 1];

@@ -106,35 +106,61 @@ __global__ void __launch_bounds__(kSuThreads, 1) stem_umma_kernel(const StemUmma
     const int row = (warp & 3) * 32 + lane;
     uint32_t phase = 0;  // parity of this group's stages (each is reused every kSuStages / 2 of its tiles)
     int it = 0;
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, ++it) {
-      const int stage = grp + 2 * (it % (kSuStages / 2));
-      if (it > 0 && it % (kSuStages / 2) == 0) phase ^= 1u;
-      const long long m = (long long)tile * kBlockM + row;
-      uint32_t v[27];
-      if (m < p.total) {
-        const int img = (int)(m / (kSuOut * kSuOut));
-        const int rem = (int)(m - (long long)img * (kSuOut * kSuOut));
+    // The 9 aligned words of a pixel's 3 x 9-byte window are requested ONE TILE AHEAD: the global-load latency (~1000
+    // cycles with every SM streaming) was the longest link of this group's per-tile chain (load -> 27 table look-ups ->
+    // pack -> 8 stores); (32 table copies instead of 8 -- no bank conflicts at all -- made the kernel 6 % slower.)
+    uint32_t wn[9], offn[3];
+    auto fetch = [&](int tile_f) {
+      const long long m = (long long)tile_f * kBlockM + row;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) wn[k] = 0u;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) offn[r] = 0u;
+      if (tile_f < p.num_tiles && m < p.total) {
+        const unsigned mu = (unsigned)m;  // (n * 149 * 149 < 2^31: checked on the host)
+        const int img = (int)(mu / (unsigned)(kSuOut * kSuOut));
+        const int rem = (int)(mu - (unsigned)img * (unsigned)(kSuOut * kSuOut));
         const int oy = rem / kSuOut, ox = rem - oy * kSuOut;
         const uint8_t* base = p.u8 + ((size_t)img * kOutSize + 2 * oy) * (kOutSize * 3) + 6 * ox;
-        // 9 contiguous bytes per input row at any alignment (rows are 897 bytes): three aligned 32-bit loads + byte
-        // permutes.  (Deeper prefetching -- L2 prefetch, a cp.async ring -- did not help: the kernel is bound by
-        // shared-memory wavefronts, profiles/README.md.)
+        // 9 contiguous bytes per input row at any alignment (rows are 897 bytes): three aligned 32-bit loads + byte permutes
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const uint8_t* rp = base + (size_t)r * (kOutSize * 3);
           const uint32_t off = (uint32_t)((uintptr_t)rp & 3u);
           const uint32_t* wp = reinterpret_cast<const uint32_t*>(rp - off);
-          const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
-          uint32_t w2 = 0;
+          offn[r] = off;
+          wn[3 * r] = __ldg(wp);
+          wn[3 * r + 1] = __ldg(wp + 1);
           if (reinterpret_cast<const uint8_t*>(wp + 3) <= p.u8_end) {
-            w2 = __ldg(wp + 2);
+            wn[3 * r + 2] = __ldg(wp + 2);
           } else {  // the very last pixels of the batch: never read past the end of the caller's buffer
             const uint8_t* bp = reinterpret_cast<const uint8_t*>(wp + 2);
+            uint32_t w2 = 0;
             for (int b = 0; b < 4; ++b)
               if (bp + b < p.u8_end) w2 |= (uint32_t)__ldg(bp + b) << (8 * b);
+            wn[3 * r + 2] = w2;
           }
-          const uint32_t sel = 0x3210u + 0x1111u * off;  // bytes off .. off + 3 of a register pair
-          const uint32_t b0 = __byte_perm(w0, w1, sel), b1 = __byte_perm(w1, w2, sel), b2 = __byte_perm(w2, 0u, sel);
+        }
+      }
+    };
+    fetch(blockIdx.x + grp * gridDim.x);
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, ++it) {
+      const int stage = grp + 2 * (it % (kSuStages / 2));
+      if (it > 0 && it % (kSuStages / 2) == 0) phase ^= 1u;
+      const long long m = (long long)tile * kBlockM + row;
+      uint32_t wc[9], offc[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) wc[k] = wn[k];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) offc[r] = offn[r];
+      fetch(tile + 2 * gridDim.x);  // next tile of this group: in flight during the look-ups below
+      uint32_t v[27];
+      if (m < p.total) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const uint32_t sel = 0x3210u + 0x1111u * offc[r];  // bytes off .. off + 3 of a register pair
+          const uint32_t b0 = __byte_perm(wc[3 * r], wc[3 * r + 1], sel), b1 = __byte_perm(wc[3 * r + 1], wc[3 * r + 2], sel),
+                         b2 = __byte_perm(wc[3 * r + 2], 0u, sel);
 #pragma unroll
           for (int b = 0; b < 9; ++b) {
             const uint32_t word = b < 4 ? b0 : (b < 8 ? b1 : b2);
@@ -298,6 +324,7 @@ int launch_stem_umma(tise_ctx* ctx, const uint8_t* d_u8, int n, const __half* d_
   p.shift = d_shift;
   p.out = d_out;
   p.total = (long long)n * kSuOut * kSuOut;
+  if (p.total + 4 * kBlockM >= (1ll << 31)) return fail(ctx, TISE_ERR_INVALID, "stem: batch too large (%d images)", n);
   p.num_tiles = (int)((p.total + kBlockM - 1) / kBlockM);
   const int grid = p.num_tiles < ctx->num_sms ? p.num_tiles : ctx->num_sms;
   stem_umma_kernel<<<grid, kSuThreads, kSuSmem, st>>>(p);

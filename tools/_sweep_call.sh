@@ -1,7 +1,3 @@
-mkdir -p gpurun_out
-for cfg in "base" "TISE_UMMA_MSUB1P=128" "TISE_UMMA_MSUB1P=96" "TISE_UMMA_GROUP=1" "TISE_UMMA_GROUP=3" "TISE_UMMA_GROUP=4"; do
-  f=gpurun_out/layers_sweep_$(echo $cfg | tr '=' '_').txt
-  if [ "$cfg" = "base" ]; then TISE_PROFILE_DUMP=$f timeout 200 python tools/profile_trunk.py 1024 > /dev/null 2>&1
-  else env $cfg TISE_PROFILE_DUMP=$f timeout 200 python tools/profile_trunk.py 1024 > /dev/null 2>&1; fi
-  echo "$cfg: $(awk '{s+=$1} END {print s}' $f) ms"
-done
+TISE_PROFILE_DUMP=gpurun_out/layers_stempf.txt timeout 200 python tools/profile_trunk.py 1024 > /dev/null 2>&1
+head -1 gpurun_out/layers_stempf.txt; echo "total $(awk '{s+=$1} END {print s}' gpurun_out/layers_stempf.txt)"
+timeout 400 python -m pytest tests/test_gpu_trunk.py tests/test_gpu_kernels.py -q -m gpu 2>&1 | tail -2
