@@ -36,13 +36,14 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
-    p.add_argument("--batch", type=int, default=4096, help="images per rank per step (20 steps cover >= 2 s)")
+    p.add_argument("--batch", type=int, default=6144, help="images per rank per step (20 steps cover >= 2 s)")
     p.add_argument("--micro-batch", type=int, default=1024)
-    p.add_argument("--pool", type=int, default=4096, help="distinct synthetic images resident per rank")
+    p.add_argument("--pool", type=int, default=6144, help="distinct synthetic images resident per rank")
     p.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
     p.add_argument("--fixed", type=int, default=30000, help="images of the fixed-size end-to-end run (0: skip)")
     p.add_argument("--crops", type=int, default=100000, help="cfg4: number of ragged crops")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--child", default="", help=argparse.SUPPRESS)  # internal: isolated CPU legs (see run_isolated)
     p.add_argument("--passes", type=int, default=2)
     p.add_argument("--strict", action="store_true", help="two MMA passes in every layer (default: mixed operand policy)")
     p.add_argument("--cpu-sample", type=int, default=500, help="images of the CPU reference leg (two sets of half)")
@@ -259,10 +260,71 @@ def gpu_parity(eng, cpu):
                     "reference's TF graphs cannot run (split / KL lines restated)"}
 
 
+def run_isolated(child_args, timeout_s, tries=2):
+    """The CPU legs fork DataLoader workers (the reference's own code: DataLoader(num_workers=8)) out of a process that
+    has already run multi-threaded torch CPU code -- and, in the GPU arm, holds a CUDA context and helper threads.  A
+    fork in that state can leave a worker waiting on a lock some other thread held at the moment of the fork (seen once
+    in ~10 runs: the whole bench line was lost to a 15-minute hang).  So every CPU leg runs in a FRESH interpreter with a
+    timeout and one retry; a leg that still fails is reported as unavailable instead of taking the GPU numbers with it."""
+    cmd = [sys.executable, os.path.abspath(__file__)] + list(child_args)
+    last = "not run"
+    for attempt in range(tries):
+        try:
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout_s,
+                               env=dict(os.environ, TISE_BENCH_CHILD="1"))
+            if r.returncode == 0:
+                sys.stderr.write(r.stderr[-2000:])
+                return r.stdout, None
+            last = "exit code %d: %s" % (r.returncode, r.stderr[-300:].replace("\n", " | "))
+        except subprocess.TimeoutExpired:
+            last = "timed out after %d s (attempt %d)" % (timeout_s, attempt + 1)
+        print("bench: isolated CPU leg failed (%s)%s" % (last, ", retrying" if attempt + 1 < tries else ""), file=sys.stderr)
+    return None, last
+
+
+def child_cpu_leg(spec_path):
+    """--child cpu_leg:<spec.pt>: cpu_leg() in a fresh process; the spec holds the calibrated head, the sample size and the
+    output path."""
+    from tise_toolbox_b200 import synth
+
+    spec = torch.load(spec_path)
+    sd = synth.inception_state_dict(0, num_classes=int(spec["fc.weight"].shape[0]))
+    sd["fc.weight"], sd["fc.bias"] = spec["fc.weight"], spec["fc.bias"]
+    rec, cpu = cpu_leg(sd, int(spec["n_images"]), spec["tmp_root"])
+    np.savez(spec["out"], rec=json.dumps(rec), order0=np.array(cpu["order"][0]), order1=np.array(cpu["order"][1]),
+             feats=cpu["feats"], fid=cpu["fid"], is_mean=cpu["is_mean"], is_std=cpu["is_std"], sqrtm_s=cpu["sqrtm_s"])
+
+
+def cpu_leg_isolated(state_dict, n_images, tmp_root):
+    """cpu_leg() in a fresh interpreter (run_isolated); returns (record, parity inputs) or (unavailable record, None)."""
+    from tise_toolbox_b200 import synth
+
+    spec = os.path.join(tmp_root, "cpu_leg_spec.pt")
+    out = os.path.join(tmp_root, "cpu_leg_out.npz")
+    torch.save({"fc.weight": state_dict["fc.weight"].cpu(), "fc.bias": state_dict["fc.bias"].cpu(), "n_images": n_images,
+                "tmp_root": tmp_root, "out": out}, spec)
+    _, err = run_isolated(["--child", "cpu_leg:" + spec], timeout_s=240)
+    if err is not None or not os.path.exists(out):
+        return {"unavailable": "CPU leg failed twice: %s" % err}, None
+    z = np.load(out, allow_pickle=False)
+    half = max(50, n_images // 2 // 50 * 50)
+    cpu = {"sets": [synth.images(1, 0, 0, half), synth.images(2, 1, 0, half)],
+           "order": [z["order0"].tolist(), z["order1"].tolist()], "feats": z["feats"], "fid": float(z["fid"]),
+           "is_mean": float(z["is_mean"]), "is_std": float(z["is_std"]), "sqrtm_s": float(z["sqrtm_s"])}
+    return json.loads(str(z["rec"])), cpu
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path on the host cores (rank 0 only); each step is
     a bounded sample: `--ref-step` PNG files through _compute_statistics_of_path + the IS* lines."""
     if rank != 0:
+        return
+    if not os.environ.get("TISE_BENCH_CHILD"):  # fresh interpreter + timeout + one retry (run_isolated)
+        out, err = run_isolated([a for a in sys.argv[1:]], timeout_s=600)
+        if out is None:
+            _emit(json.dumps({"impl": "reference", "unavailable": "reference arm failed twice: %s" % err}))
+        else:
+            _emit(out.strip().splitlines()[-1])
         return
     import shutil
     import tempfile
@@ -371,6 +433,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.child.startswith("cpu_leg:"):
+        child_cpu_leg(args.child[len("cpu_leg:"):])
+        return
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -639,12 +704,15 @@ def main():
             eng.load_state_dict(sd_par)
             tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
             try:
-                rec, cpu = cpu_leg(sd_par, args.cpu_sample, tmp)
+                rec, cpu = cpu_leg_isolated(sd_par, args.cpu_sample, tmp)
             finally:
                 shutil.rmtree(tmp, ignore_errors=True)
             line["cpu_baseline"] = rec
-            line["parity"] = gpu_parity(eng, cpu)
-            line["parity"]["operand_policy"] = "strict" if eng.pass1_max_hw == 0 else "default (calibrated single pass)"
+            if cpu is not None:
+                line["parity"] = gpu_parity(eng, cpu)
+                line["parity"]["operand_policy"] = "strict" if eng.pass1_max_hw == 0 else "default (calibrated single pass)"
+            else:
+                line["parity"] = None
             eng.load_state_dict(sd)
             eng.set_variant("bird")
         if not args.no_frechet:

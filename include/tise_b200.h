@@ -173,6 +173,13 @@ int tise_crop_resize_u8(tise_ctx* ctx, const uint8_t* d_imgs, const int64_t* h_o
 int tise_upsample_bilinear_f32(tise_ctx* ctx, const float* d_in, int n, int c, int h, int w, int align_corners,
                                float* d_out, tise_stream stream);
 
+/* Per-channel affine of a float NCHW tensor (c <= 4, hw = H * W), y = x * scale[c] + bias[c] as a rounded multiply and a
+ * rounded add: the normalize_input pre-amble of image_realism/FID/inception.py:119-124 for callers that hand
+ * InceptionV3.forward float tensors (the uint8 path carries it in the lookup table of tise_set_input_lut).
+ * h_scale / h_bias: host arrays of c floats.  d_out may alias d_in. */
+int tise_channel_affine_f32(tise_ctx* ctx, const float* d_in, int n, int c, int hw, const float* h_scale, const float* h_bias,
+                            float* d_out, tise_stream stream);
+
 /* ---- A3/A4: uint8 level -> network input ------------------------------------------------ */
 /* lut[c*256 + v] = float fed to Conv2d_1a_3x3 for channel c and uint8 level v; covers ToTensor
  * (fid_score.py:211) + the affine at image_realism/FID/inception.py:120-124, or

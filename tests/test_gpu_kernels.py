@@ -195,3 +195,17 @@ def test_upsample_float_matches_aten(engine, align):
         got = engine.upsample_float(x, align_corners=align).cpu()
         assert float((got - ref).abs().max()) <= (5e-7 if align else 1e-5), (h, w, align)
     assert tuple(engine.upsample_float(torch.empty(0, 3, 8, 8), align_corners=align).shape) == (0, 3, 299, 299)
+
+
+def test_channel_affine_is_bit_identical_to_the_eager_ops(engine):
+    """InceptionV3.forward's normalize_input pre-amble (image_realism/FID/inception.py:119-124) as ONE libtise kernel:
+    same bits as the reference's three eager `x[:, c] = x[:, c] * s + b` statements (multiply and add rounded apart)."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(5, 3, 37, 41, generator=g)
+    ref = x.clone()
+    ref[:, 0] = ref[:, 0] * (0.229 / 0.5) + (0.485 - 0.5) / 0.5
+    ref[:, 1] = ref[:, 1] * (0.224 / 0.5) + (0.456 - 0.5) / 0.5
+    ref[:, 2] = ref[:, 2] * (0.225 / 0.5) + (0.406 - 0.5) / 0.5
+    got = engine.channel_affine(x.cuda(), (0.229 / 0.5, 0.224 / 0.5, 0.225 / 0.5),
+                                ((0.485 - 0.5) / 0.5, (0.456 - 0.5) / 0.5, (0.406 - 0.5) / 0.5))
+    assert torch.equal(got.cpu(), ref)

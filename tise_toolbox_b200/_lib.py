@@ -63,6 +63,8 @@ _SIGNATURES = {
                                    C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
     "tise_upsample_bilinear_f32": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                              c_stream]),
+    "tise_channel_affine_f32": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          c_stream]),
     "tise_set_input_lut": (C.c_int, [c_ctx_p, C.c_void_p]),
     "tise_inception_workspace_bytes": (C.c_size_t, [c_ctx_p, C.c_int]),
     "tise_inception_features": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

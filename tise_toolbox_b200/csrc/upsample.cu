@@ -41,9 +41,40 @@ __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const float* __r
   out[idx] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
 }
 
+// y[n][c][i] = x[n][c][i] * scale[c] + bias[c] with a rounded multiply followed by a rounded add (what the eager
+// `x[:, c] = x[:, c] * s + b` of image_realism/FID/inception.py:120-124 computes -- no FMA contraction)
+struct Affine4 {
+  float scale[4], bias[4];
+};
+__global__ void channel_affine_kernel(const float* __restrict__ in, long long total, int c, int hw, Affine4 a, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)((i / hw) % c);
+    out[i] = __fadd_rn(__fmul_rn(in[i], a.scale[ch]), a.bias[ch]);
+  }
+}
+
 }  // namespace tise
 
 using namespace tise;
+
+extern "C" int tise_channel_affine_f32(tise_ctx* ctx, const float* d_in, int n, int c, int hw, const float* h_scale,
+                                       const float* h_bias, float* d_out, tise_stream stream) {
+  if (!ctx) return TISE_ERR_INVALID;
+  if (n == 0) return TISE_OK;
+  if (!d_in || !d_out || !h_scale || !h_bias || n < 0 || c <= 0 || c > 4 || hw <= 0)
+    return fail(ctx, TISE_ERR_INVALID, "tise_channel_affine_f32: bad argument");
+  Affine4 a;
+  for (int k = 0; k < 4; ++k) {
+    a.scale[k] = k < c ? h_scale[k] : 1.f;
+    a.bias[k] = k < c ? h_bias[k] : 0.f;
+  }
+  const long long total = (long long)n * c * hw;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)ctx->num_sms * 32) blocks = (long long)ctx->num_sms * 32;
+  channel_affine_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_in, total, c, hw, a, d_out);
+  TISE_LAUNCH_CHECK(ctx);
+  return TISE_OK;
+}
 
 extern "C" int tise_upsample_bilinear_f32(tise_ctx* ctx, const float* d_in, int n, int c, int h, int w, int align_corners,
                                           float* d_out, tise_stream stream) {

@@ -490,6 +490,19 @@ class Engine:
                                                             out.data_ptr(), _stream()))
         return out
 
+    def channel_affine(self, x: torch.Tensor, scale: Sequence[float], bias: Sequence[float]) -> torch.Tensor:
+        """float32 [n, c, h, w] -> x * scale[c] + bias[c] (rounded multiply, then rounded add: inception.py:120-124)."""
+        assert x.dtype == torch.float32 and x.dim() == 4 and len(scale) == len(bias) == int(x.shape[1])
+        x = x.to(self.device).contiguous()
+        n, c, h, w = (int(v) for v in x.shape)
+        out = torch.empty_like(x)
+        sc = np.asarray(scale, dtype=np.float32)
+        bs = np.asarray(bias, dtype=np.float32)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.tise_channel_affine_f32(self.ctx, x.data_ptr(), n, c, h * w, sc.ctypes.data, bs.ctypes.data,
+                                                         out.data_ptr(), _stream()))
+        return out
+
     # ------------------------------------------------------------------ A5 trunk
     def _trunk(self, u8: Optional[torch.Tensor], f32: Optional[torch.Tensor], n: int, tap: int, feat: torch.Tensor):
         need = int(self.lib.tise_inception_workspace_bytes(self.ctx, self.micro_batch))

@@ -70,10 +70,10 @@ class InceptionV3(nn.Module):
             # identity at 299x299 (the Dataset already resized with Pillow); live only for odd callers
             x = self.engine.upsample_float(x, align_corners=True)
         if self.normalize_input:
-            x = x.clone()  # inception.py:119-124, torchvision's transform_input applied to [0,1] data
-            x[:, 0] = x[:, 0] * (0.229 / 0.5) + (0.485 - 0.5) / 0.5
-            x[:, 1] = x[:, 1] * (0.224 / 0.5) + (0.456 - 0.5) / 0.5
-            x[:, 2] = x[:, 2] * (0.225 / 0.5) + (0.406 - 0.5) / 0.5
+            # inception.py:119-124, torchvision's transform_input applied to [0,1] data: one libtise kernel with the
+            # reference's rounding (multiply, then add)
+            x = self.engine.channel_affine(x, (0.229 / 0.5, 0.224 / 0.5, 0.225 / 0.5),
+                                           ((0.485 - 0.5) / 0.5, (0.456 - 0.5) / 0.5, (0.406 - 0.5) / 0.5))
         outp = []
         for idx in self.output_blocks:
             f = self.engine.features_from_float(x, dims=_DIMS[idx])
