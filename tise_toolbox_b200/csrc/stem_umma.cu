@@ -11,8 +11,8 @@
 // network input itself carried at ~22 bits.  864 FMAs per output pixel on the CUDA cores (the previous stem, 47 % of
 // the fp32 pipe) become ~130 gather/pack instructions.
 //
-// Warp roles (544 threads): warps 0-7 two gather groups (tiles alternate between them so the load latency of one tile
-// overlaps the packing of the other), warp 8 TMEM allocator + MMA issuer, warps 9-16 two epilogue groups (one per
+// Warp roles (672 threads): warps 0-11 three gather groups (a CTA's tiles go round-robin to them, so the chain of one
+// tile overlaps those of the next two), warp 12 TMEM allocator + MMA issuer, warps 13-20 two epilogue groups (one per
 // TMEM accumulator stage, as in conv_umma.cu).
 #include <stdlib.h>
 
@@ -21,8 +21,14 @@
 
 namespace tise {
 
-constexpr int kSuThreads = 544;
-constexpr int kSuStages = 4;                 // A stages (even: gather group g fills stages g, g + 2)
+// The gather groups set the pace of this kernel (a ~170-instruction dependent chain per 128-pixel tile and warp: 27 table
+// look-ups, packing, 8 swizzled stores), so there are THREE of them (round 1: two) feeding two epilogue groups; 672 threads
+// leave enough registers (80 used).  Measured per 1024 images: 2 groups 0.84 ms, 3 groups 0.76 ms, 4 groups (800 threads, 72
+// registers, spills) 0.85 ms.
+constexpr int kSuGather = 3;                                // gather groups of 4 warps
+constexpr int kSuMmaWarp = 4 * kSuGather;                   // warp index of the TMEM allocator + MMA issuer
+constexpr int kSuThreads = 32 * (kSuMmaWarp + 1) + 256;     // + two epilogue groups of 4 warps
+constexpr int kSuStages = 2 * kSuGather;     // A stages: gather group g fills stages g and g + kSuGather
 constexpr int kSuATile = 128 * 128;          // 128 pixels x 128 bytes
 constexpr int kSuBTile = 64 * 128;           // 64 weight rows x 128 bytes
 constexpr int kSuEpiBuf = 128 * 64;          // staged output box: 128 pixels x 32 fp16 channels
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(kSuThreads, 1) stem_umma_kernel(const StemUmma
     st_shared_v4(b_base + (uint32_t)r * 128u + ((uint32_t)(c ^ (r & 7)) << 4), v.x, v.y, v.z, v.w);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-  if (warp == 8) {
+  if (warp == kSuMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -100,11 +106,11 @@ __global__ void __launch_bounds__(kSuThreads, 1) stem_umma_kernel(const StemUmma
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp < 8) {
+  if (warp < kSuMmaWarp) {
     // ===================================================================== gather: uint8 pixels -> swizzled fp16 A rows
     const int grp = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
-    uint32_t phase = 0;  // parity of this group's stages (each is reused every kSuStages / 2 of its tiles)
+    uint32_t phase = 0;  // parity of this group's stages (each is reused every 2 of its tiles)
     int it = 0;
     // The 9 aligned words of a pixel's 3 x 9-byte window are requested ONE TILE AHEAD: the global-load latency (~1000
     // cycles with every SM streaming) was the longest link of this group's per-tile chain (load -> 27 table look-ups ->
@@ -144,16 +150,16 @@ __global__ void __launch_bounds__(kSuThreads, 1) stem_umma_kernel(const StemUmma
       }
     };
     fetch(blockIdx.x + grp * gridDim.x);
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, ++it) {
-      const int stage = grp + 2 * (it % (kSuStages / 2));
-      if (it > 0 && it % (kSuStages / 2) == 0) phase ^= 1u;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += kSuGather * gridDim.x, ++it) {
+      const int stage = grp + kSuGather * (it & 1);
+      if (it > 0 && (it & 1) == 0) phase ^= 1u;
       const long long m = (long long)tile * kBlockM + row;
       uint32_t wc[9], offc[3];
 #pragma unroll
       for (int k = 0; k < 9; ++k) wc[k] = wn[k];
 #pragma unroll
       for (int r = 0; r < 3; ++r) offc[r] = offn[r];
-      fetch(tile + 2 * gridDim.x);  // next tile of this group: in flight during the look-ups below
+      fetch(tile + kSuGather * gridDim.x);  // next tile of this group: in flight during the look-ups below
       uint32_t v[27];
       if (m < p.total) {
 #pragma unroll
@@ -192,22 +198,21 @@ __global__ void __launch_bounds__(kSuThreads, 1) stem_umma_kernel(const StemUmma
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(stage));
     }
-  } else if (warp == 8) {
+  } else if (warp == kSuMmaWarp) {
     // ===================================================================== MMA issuer
     const uint64_t dhi = smem_desc_hi(2 /*SWIZZLE_128B*/, 1024);
     const uint32_t hi = (uint32_t)(dhi >> 32);
     const uint32_t a_lo0 = (uint32_t)make_smem_desc(a_base, dhi), b_lo = (uint32_t)make_smem_desc(b_base, dhi);
     const uint32_t idesc = make_instr_desc(64);
-    uint32_t phase[2] = {0u, 0u}, aphase[2] = {0u, 0u};
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int grp = it & 1, git = it >> 1;  // this tile was built by gather group grp as its git-th tile
-      const int stage = grp + 2 * (git % (kSuStages / 2));
-      if (git > 0 && git % (kSuStages / 2) == 0) phase[grp] ^= 1u;
-      const int as = grp;  // accumulator stage = epilogue group
-      if (git > 0) aphase[grp] ^= 1u;
-      mbar_wait(tempty_bar(as), aphase[grp] ^ 1u);
-      mbar_wait(full_bar(stage), phase[grp]);
+      const int grp = it % kSuGather, git = it / kSuGather;  // this tile was built by gather group grp as its git-th tile
+      const int stage = grp + kSuGather * (git & 1);
+      const uint32_t fphase = (uint32_t)(git >> 1) & 1u;   // the stage's git / 2-th use
+      const int as = it & 1;                                // accumulator stage = epilogue group
+      const uint32_t aph = (uint32_t)(it >> 1) & 1u;        // the accumulator's it / 2-th use
+      mbar_wait(tempty_bar(as), aph ^ 1u);
+      mbar_wait(full_bar(stage), fphase);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d = tmem_base + (uint32_t)(as * 64);
@@ -220,10 +225,10 @@ __global__ void __launch_bounds__(kSuThreads, 1) stem_umma_kernel(const StemUmma
     }
   } else {
     // ===================================================================== epilogue (two groups, one per accumulator stage)
-    const int grp = (warp - 9) >> 2;
+    const int grp = (warp - (kSuMmaWarp + 1)) >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int etid = threadIdx.x - 9 * 32 - grp * 128;
+    const int etid = threadIdx.x - (kSuMmaWarp + 1) * 32 - grp * 128;
     const uint32_t my_epi = epi_base + (uint32_t)grp * 2u * kSuEpiBuf;
     const uint32_t wr_off = (uint32_t)row * 64u;
     const uint32_t wr_swz = (uint32_t)((row >> 1) & 3);
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(kSuThreads, 1) stem_umma_kernel(const StemUmma
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kSuMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
   }

@@ -1,3 +1,3 @@
-timeout 300 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_crop.py -q -m gpu -k "resize or crop" 2>&1 | tail -2
-python tools/run_step.py --batch 4096 --steps 4 2>&1 | tail -1
-ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -k regex:resize_fused --csv python tools/run_step.py --batch 1024 --steps 1 2>&1 | grep resize_fused | awk -F'","' '{print $NF}'
+TISE_PROFILE_DUMP=gpurun_out/layers_stem4.txt timeout 200 python tools/profile_trunk.py 1024 > /dev/null 2>&1
+head -1 gpurun_out/layers_stem4.txt; echo "total $(awk '{s+=$1} END {print s}' gpurun_out/layers_stem4.txt)"
+timeout 400 python -m pytest tests/test_gpu_trunk.py tests/test_gpu_kernels.py -q -m gpu 2>&1 | tail -2
