@@ -1,6 +1,7 @@
 #!/bin/bash
 # Regenerates the round-2 evidence under profiles/ on a GPU box (outputs land in gpurun_out/; copy the summaries afterwards).
 mkdir -p gpurun_out
+timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -1
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02_n1.json 2> gpurun_out/bench_r02_n1.err; echo "bench rc=$?"
 timeout 600 python bench.py --workload cfg4 --steps 10 --warmup 3 > gpurun_out/bench_r02_cfg4.json 2> gpurun_out/bench_r02_cfg4.err; echo "cfg4 rc=$?"
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r02_reference.json 2> gpurun_out/bench_r02_reference.err; echo "ref rc=$?"
