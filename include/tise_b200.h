@@ -68,6 +68,12 @@ int tise_set_pass_policy(tise_ctx* ctx, int single_pass_max_hw);
  * convolution input, and  shift += scale * (W_lo . mean)  becomes the shift of the layer's single-pass form -- the
  * image-independent part of the dropped W_lo product.  `d_ws`: tise_inception_workspace_bytes(ctx, n_images) bytes. */
 int tise_calibrate_single_pass(tise_ctx* ctx, int n_images, void* d_ws, size_t ws_bytes, tise_stream stream);
+/* Progress marker for callers that overlap host -> device copies with the trunk: every tise_inception_features call
+ * records `cuda_event` (a cudaEvent_t; NULL clears) on its stream when the forward pass reaches the first convolution
+ * whose input map is at most `max_hw` pixels high.  With max_hw = 17 that is the end of the HBM-bound front of the
+ * network (stem ... Mixed_6a): a copy stream that waits for the event moves its traffic into the compute-bound part,
+ * where it does not compete for HBM with the layers that run at the memory limit. */
+int tise_set_progress_event(tise_ctx* ctx, void* cuda_event, int max_hw);
 
 /* ---- weights -------------------------------------------------------------------------- */
 /* One tensor of a torchvision Inception3 state_dict (fp32, host, contiguous), e.g.

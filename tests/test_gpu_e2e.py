@@ -247,3 +247,29 @@ def test_ois_folder_path_on_device_matches_reference_pipeline(tmp_path):
     # and the float path of the drop-in (host PIL resize + ToTensor + Normalize, trunk on the GPU) agrees with both
     flt = ois.inception_score(ois.IgnoreLabelDataset(str(tmp_path)), batch_size=32, splits=2, engine=eng)
     assert abs(flt[0] - ref[0]) <= 1e-3 * ref[0], (flt, ref)
+
+
+@pytest.mark.parametrize("pace", [True, False])
+def test_step_from_host_equals_resident_steps(state_dict, pace):
+    """RealismJob.step_from_host (pinned host batches, double-buffered staging, next batch uploaded in chunks released by
+    the trunk's progress event when ``pace``) accumulates bit-identical statistics to step() on resident images, for
+    batches of different sizes that span several micro-batches."""
+    from tise_toolbox_b200.pipeline import RealismJob
+
+    eng = Engine(state_dict, device="cuda:0", micro_batch=16)
+    sizes = [40, 24, 7, 40]
+    host = [synth.images(3, 0, 100 * k, n).pin_memory() for k, n in enumerate(sizes)]
+    ref = RealismJob(eng, n_total=sum(sizes), is_variant="ois", splits=3, input_variant="fid")
+    for h in host:
+        ref.step(h.cuda())
+    job = RealismJob(eng, n_total=sum(sizes), is_variant="ois", splits=3, input_variant="fid")
+    job.pace_h2d = pace
+    feats = []
+    for k, h in enumerate(host):
+        feats.append(job.step_from_host(h, host[k + 1] if k + 1 < len(host) else None))
+    torch.cuda.synchronize()
+    # (same kernels on the same bytes; the only freedom is the order of fp64 atomic adds between CTAs)
+    assert torch.allclose(job.pack.buf, ref.pack.buf, rtol=1e-12, atol=0.0)
+    assert torch.equal(job.parts.i, ref.parts.i) and job.moments.count == ref.moments.count == sum(sizes)
+    assert feats[2].shape == (7, 2048)
+    eng.set_progress_event(None)

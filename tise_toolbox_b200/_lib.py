@@ -65,6 +65,7 @@ _SIGNATURES = {
                                              c_stream]),
     "tise_channel_affine_f32": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                           c_stream]),
+    "tise_set_progress_event": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int]),
     "tise_set_input_lut": (C.c_int, [c_ctx_p, C.c_void_p]),
     "tise_inception_workspace_bytes": (C.c_size_t, [c_ctx_p, C.c_int]),
     "tise_inception_features": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -103,6 +103,14 @@ extern "C" int tise_set_pass_policy(tise_ctx* ctx, int single_pass_max_hw) {
   return TISE_OK;
 }
 
+extern "C" int tise_set_progress_event(tise_ctx* ctx, void* cuda_event, int max_hw) {
+  if (!ctx) return TISE_ERR_INVALID;
+  if (cuda_event && max_hw <= 0) return fail(ctx, TISE_ERR_INVALID, "tise_set_progress_event: max_hw = %d", max_hw);
+  ctx->progress_event = (cudaEvent_t)cuda_event;
+  ctx->progress_max_hw = cuda_event ? max_hw : 0;
+  return TISE_OK;
+}
+
 extern "C" int tise_set_input_lut(tise_ctx* ctx, const float* h_lut768) {
   if (!ctx) return TISE_ERR_INVALID;
   if (!h_lut768) return fail(ctx, TISE_ERR_INVALID, "tise_set_input_lut: null table");

@@ -29,6 +29,8 @@ struct tise_ctx {
   int conv_impl = TISE_CONV_UMMA;
   int passes = 2;
   int pass1_max_hw = 0;  // layers whose input map is at most this many pixels high run one MMA pass (0: none)
+  cudaEvent_t progress_event = nullptr;  // tise_set_progress_event: recorded once per forward pass ...
+  int progress_max_hw = 0;               // ... in front of the first convolution whose input map is at most this high
   float* d_lut = nullptr;  // 768 floats
   bool lut_set = false;
   tise::Net* net = nullptr;

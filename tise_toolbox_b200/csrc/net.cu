@@ -793,7 +793,12 @@ int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, i
   static int stem_env = -1;
   if (stem_env < 0) stem_env = getenv("TISE_STEM_UMMA") ? atoi(getenv("TISE_STEM_UMMA")) : 1;
   const bool stem_umma = ctx->conv_impl == TISE_CONV_UMMA && ctx->passes == 2 && stem_env != 0;
+  bool progress_pending = ctx->progress_event != nullptr;
   for (Step& s : plan->steps) {
+    if (progress_pending && s.kind == STEP_CONV && s.conv.h <= ctx->progress_max_hw) {  // tise_set_progress_event
+      TISE_CUDA(ctx, cudaEventRecord(ctx->progress_event, st));
+      progress_pending = false;
+    }
     tise_ctx::ProfRec rec{s.kind == STEP_FLATCONV ? (int)STEP_CONV : (int)s.kind, nullptr, nullptr, 0.0, {0}};
     if (ctx->profiling) {
       if (s.kind == STEP_FLATCONV) {
@@ -859,6 +864,7 @@ int net_forward(tise_ctx* ctx, const uint8_t* d_u8, const float* d_f32, int n, i
       ctx->prof.push_back(rec);
     }
   }
+  if (progress_pending) TISE_CUDA(ctx, cudaEventRecord(ctx->progress_event, st));  // (a tap that ends before that layer)
   return TISE_OK;
 }
 

@@ -371,9 +371,14 @@ class Engine:
             # trunk kernels of the previous group on the compute stream (the buffer is free: the previous decode was
             # awaited below before this call)
             total = int(staged["total"])
-            d_files = self._buf("_d_files", total)[:total]
             if not hasattr(self, "_upload_stream"):
                 self._upload_stream = torch.cuda.Stream(device=self.device)
+            before = self._d_files
+            d_files = self._buf("_d_files", total)[:total]
+            if self._d_files is not before:
+                # a grown buffer comes from the compute stream's pool: kernels queued there may still read the block under
+                # its previous identity, so the upload stream waits for them once
+                self._upload_stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self._upload_stream):
                 d_files.copy_(staged["pinned"][:total], non_blocking=True)
                 uploaded = torch.cuda.Event()
@@ -504,16 +509,31 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ A5 trunk
+    def set_progress_event(self, event: Optional[torch.cuda.Event], max_hw: int = 17):
+        """tise_set_progress_event: ``event`` is recorded in every trunk call when the forward pass leaves the HBM-bound
+        front of the network (first convolution on a map of at most ``max_hw`` pixels); None clears it."""
+        handle = None
+        if event is not None:
+            with torch.cuda.device(self.device):
+                event.record()  # (materialises the cudaEvent_t)
+            handle = C.c_void_p(event.cuda_event)
+        self._check(self.lib.tise_set_progress_event(self.ctx, handle, int(max_hw)))
+        self._progress_event = event  # keep it alive while the context refers to it
+
     def _trunk(self, u8: Optional[torch.Tensor], f32: Optional[torch.Tensor], n: int, tap: int, feat: torch.Tensor):
         need = int(self.lib.tise_inception_workspace_bytes(self.ctx, self.micro_batch))
         ws = self._buf("_ws", need)
+        hook = getattr(self, "on_micro_batch", None)  # callable(index, count): host-side, after each micro-batch is enqueued
+        count = (n + self.micro_batch - 1) // self.micro_batch
         with torch.cuda.device(self.device):
-            for i0 in range(0, n, self.micro_batch):
+            for k, i0 in enumerate(range(0, n, self.micro_batch)):
                 m = min(self.micro_batch, n - i0)
                 self._check(self.lib.tise_inception_features(
                     self.ctx, u8[i0:].data_ptr() if u8 is not None else None,
                     f32[i0:].data_ptr() if f32 is not None else None, m, tap, feat[i0:].data_ptr(),
                     ws.data_ptr(), ws.numel(), _stream()))
+                if hook is not None:
+                    hook(k, count)
 
     def features_from_resized(self, u8_299: torch.Tensor, dims: int = 2048) -> torch.Tensor:
         """uint8 [n, 299, 299, 3] (already resized) -> float32 [n, dims] block features."""

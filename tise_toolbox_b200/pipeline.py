@@ -61,6 +61,9 @@ class RealismJob:
             _, off, _, _ = _is.VARIANTS[is_variant]
             cls = engine.num_classes - off
         # every additive statistic of the set lives in ONE packed fp64 buffer: the exchange step is one all-reduce
+        import os
+
+        self.pace_h2d = os.environ.get("TISE_PACE_H2D", "1") != "0"  # step_from_host: see there
         self.pack = StatsPack(engine, 2048, cls, splits if cls else 0, want_moments)
         self.moments, self.parts = self.pack.moments, self.pack.parts
 
@@ -88,29 +91,78 @@ class RealismJob:
             self._slot_done = [None, None]  # event after the last step that read each staging buffer
             self._pending = {}
             self._slot = 0
+            self._progress = None
+
+        def staging(slot, like):
+            """Device buffer of slot `slot` shaped like the host batch `like`: grow-only storage, a view per batch.
+            Growing allocates from the COMPUTE stream's pool, whose free blocks may still be read by kernels queued
+            there under their previous identity -- the copy stream, which writes the buffer, must wait for them
+            (without this a batch of a new size could be overwritten in flight: caught by
+            tests/test_gpu_e2e.py::test_step_from_host_equals_resident_steps)."""
+            need = like.numel()
+            cur = self._staging[slot]
+            if cur is None or cur.numel() < need:
+                cur = self._staging[slot] = torch.empty(need, dtype=torch.uint8, device=dev)
+                self._copy_stream.wait_stream(torch.cuda.current_stream(dev))
+            return cur[:need].view(like.shape)
 
         def start_copy(src, slot):
-            buf = self._staging[slot]
-            if buf is None or buf.shape != src.shape:
-                buf = self._staging[slot] = torch.empty(src.shape, dtype=torch.uint8, device=dev)
+            buf = staging(slot, src)
             if self._slot_done[slot] is not None:  # only the last reader of THIS buffer has to be finished
                 self._copy_stream.wait_event(self._slot_done[slot])
             with torch.cuda.stream(self._copy_stream):
                 buf.copy_(src, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
-            self._pending[src.data_ptr()] = (slot, ev)
+            self._pending[src.data_ptr()] = (slot, ev, buf)
 
         key = pinned.data_ptr()
         if key not in self._pending:
             start_copy(pinned, self._slot)
-        slot, ev = self._pending.pop(key)
+        slot, ev, cur_buf = self._pending.pop(key)
         torch.cuda.current_stream(dev).wait_event(ev)
-        out = self.step(self._staging[slot])
+        self._slot = 1 - slot
+        paced = self.pace_h2d and next_pinned is not None and next_pinned.data_ptr() not in self._pending
+        if paced:
+            # The next batch crosses PCIe in one chunk per micro-batch of THIS step, each released by the trunk's progress
+            # event (tise_set_progress_event: the forward pass has left the HBM-bound front of the network), so the DMA
+            # traffic runs beside the compute-bound layers instead of beside the ones at the memory limit
+            # (tools/e2e_probe.py: an H2D transfer beside the trunk costs 3-5 % wherever it lands by default).
+            nslot = self._slot
+            buf = staging(nslot, next_pinned)
+            if self._slot_done[nslot] is not None:
+                self._copy_stream.wait_event(self._slot_done[nslot])
+            if self._progress is None:
+                self._progress = torch.cuda.Event()
+                self.e.set_progress_event(self._progress, 17)
+            total = int(next_pinned.shape[0])
+            state = {"done": 0}
+
+            def hook(k, count):
+                hi = total if k == count - 1 else (total * (k + 1)) // count
+                lo = state["done"]
+                if hi > lo:
+                    self._copy_stream.wait_event(self._progress)  # the record of micro-batch k has just been issued
+                    with torch.cuda.stream(self._copy_stream):
+                        buf[lo:hi].copy_(next_pinned[lo:hi], non_blocking=True)
+                    state["done"] = hi
+
+            self.e.on_micro_batch = hook
+        try:
+            out = self.step(cur_buf)
+        finally:
+            self.e.on_micro_batch = None
         self._slot_done[slot] = torch.cuda.Event()
         self._slot_done[slot].record(torch.cuda.current_stream(dev))
-        self._slot = 1 - slot
-        if next_pinned is not None and next_pinned.data_ptr() not in self._pending:
+        if paced:
+            if state["done"] < total:  # (a step without micro-batches: nothing was released)
+                with torch.cuda.stream(self._copy_stream):
+                    buf[state["done"]:].copy_(next_pinned[state["done"]:], non_blocking=True)
+            with torch.cuda.stream(self._copy_stream):
+                ev2 = torch.cuda.Event()
+                ev2.record(self._copy_stream)
+            self._pending[next_pinned.data_ptr()] = (nslot, ev2, buf)
+        elif next_pinned is not None and next_pinned.data_ptr() not in self._pending:
             start_copy(next_pinned, self._slot)
         return out
 

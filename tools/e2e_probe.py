@@ -135,3 +135,11 @@ def full_no_wait(s):
 
 
 timed(full_no_wait, "from host + read-back, awaited 3 steps later")
+
+# ---- paced H2D (chunks released by the trunk's progress event) vs one copy per step
+for pace in (False, True, False, True):
+    job = mk()
+    job.pace_h2d = pace
+    timed(full, "from host + read-back, paced H2D = %s" % pace)
+    if not pace:
+        eng.set_progress_event(None)
