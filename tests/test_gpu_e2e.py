@@ -272,4 +272,15 @@ def test_step_from_host_equals_resident_steps(state_dict, pace):
     assert torch.allclose(job.pack.buf, ref.pack.buf, rtol=1e-12, atol=0.0)
     assert torch.equal(job.parts.i, ref.parts.i) and job.moments.count == ref.moments.count == sum(sizes)
     assert feats[2].shape == (7, 2048)
-    eng.set_progress_event(None)
+
+
+def test_dropin_statistics_from_pinned_host_batches(model, state_dict):
+    """fid_score.calculate_activation_statistics on uint8 HOST batches (what DataLoader(collate_u8) yields): the uploads are
+    prefetched one batch ahead in chunks paced by the trunk's progress event; (mu, sigma) equal the resident computation."""
+    batches = [synth.images(4, 1, 64 * k, 64).pin_memory() for k in range(3)]  # 64 images = 2 micro-batches of 32 each
+    mu, sigma = fid_score.calculate_activation_statistics(batches, model, batch_size=64, dims=2048, cuda=True, verbose=False)
+    mom = Moments(model.engine)
+    for b in batches:
+        mom.update(model.features_u8(b.cuda()))
+    mu_r, sigma_r = mom.finalize()
+    assert np.allclose(mu, mu_r, rtol=1e-12, atol=0) and np.allclose(sigma, sigma_r, rtol=1e-9, atol=1e-15)

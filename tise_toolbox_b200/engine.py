@@ -520,6 +520,15 @@ class Engine:
         self._check(self.lib.tise_set_progress_event(self.ctx, handle, int(max_hw)))
         self._progress_event = event  # keep it alive while the context refers to it
 
+    def progress_event(self, max_hw: int = 17) -> torch.cuda.Event:
+        """The engine's shared progress event (created and registered on first use): every pacing caller waits on this
+        one, so jobs that share an engine do not unregister each other's events."""
+        ev = getattr(self, "_progress_event", None)
+        if ev is None:
+            ev = torch.cuda.Event()
+            self.set_progress_event(ev, max_hw)
+        return ev
+
     def _trunk(self, u8: Optional[torch.Tensor], f32: Optional[torch.Tensor], n: int, tap: int, feat: torch.Tensor):
         need = int(self.lib.tise_inception_workspace_bytes(self.ctx, self.micro_batch))
         ws = self._buf("_ws", need)

@@ -79,15 +79,25 @@ def calculate_frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
     return np.float64(value)
 
 
-def _prefetched(images, device):
+def _prefetched(images, device, engine=None):
     """Iterates ``images`` one batch ahead: host tensors (uint8 HWC batches or the reference's float batches) are
     uploaded on a private copy stream while the previous batch is still in the trunk, so the PCIe transfer hides
-    behind the compute instead of serialising with it.  Ragged lists / device-resident packs pass through untouched."""
+    behind the compute instead of serialising with it.  Ragged lists / device-resident packs pass through untouched.
+
+    With ``engine`` (pinned host batches): the next batch is uploaded in one chunk per micro-batch of the batch being
+    consumed, each chunk released by the trunk's progress event (``Engine.set_progress_event``), so the DMA traffic runs
+    beside the compute-bound layers instead of beside the HBM-bound front of the network -- an unpaced transfer costs the
+    trunk 3-5 % (tools/e2e_probe.py)."""
     copy_stream = torch.cuda.Stream(device=device)
     main = torch.cuda.current_stream(device)
+    progress = None
+    bufs, released, n_paced, cur_slot = [None, None], [None, None], 0, None
 
-    def upload(batch):
-        if torch.is_tensor(batch) and not batch.is_cuda:
+    def is_host(batch):
+        return torch.is_tensor(batch) and not batch.is_cuda
+
+    def upload(batch):  # whole batch at once (the first batch; unpinned or engine-less callers)
+        if is_host(batch):
             with torch.cuda.stream(copy_stream):
                 dev = batch.to(device, non_blocking=True)
                 ev = torch.cuda.Event()
@@ -102,15 +112,62 @@ def _prefetched(images, device):
         return
     while cur is not None:
         try:
-            nxt = upload(next(it))
+            nxt_host = next(it)
         except StopIteration:
-            nxt = None
+            nxt_host = None
         batch, ev = cur
         if ev is not None:
             main.wait_event(ev)
-            batch.record_stream(main)  # allocated on the copy stream, consumed on the compute stream
-        yield batch
-        cur = nxt
+            if cur_slot is None:
+                batch.record_stream(main)  # allocated on the copy stream, consumed on the compute stream
+        paced = engine is not None and nxt_host is not None and is_host(nxt_host) and nxt_host.is_pinned() and len(nxt_host) > 0
+        if paced:
+            progress = engine.progress_event()
+            # two persistent device buffers used alternately (a fresh 1 GB allocation per batch cost more than the pacing
+            # gains); a buffer is overwritten only after the consumer's work on the batch it held two steps ago
+            slot = n_paced & 1
+            n_paced += 1
+            nbytes = nxt_host.numel() * nxt_host.element_size()
+            if bufs[slot] is None or bufs[slot].numel() < nbytes:
+                with torch.cuda.stream(copy_stream):
+                    bufs[slot] = torch.empty(nbytes, dtype=torch.uint8, device=device)  # (copy stream's pool)
+            if released[slot] is not None:
+                copy_stream.wait_event(released[slot])
+            nxt_dev = bufs[slot][:nbytes].view(nxt_host.dtype).view(nxt_host.shape)
+            total, state = int(nxt_host.shape[0]), {"done": 0}
+
+            def hook(k, count, nxt_host=nxt_host, nxt_dev=nxt_dev, total=total, state=state):
+                hi = total if k == count - 1 else (total * (k + 1)) // count
+                lo = state["done"]
+                if hi > lo:
+                    copy_stream.wait_event(progress)  # the record of micro-batch k has just been issued
+                    with torch.cuda.stream(copy_stream):
+                        nxt_dev[lo:hi].copy_(nxt_host[lo:hi], non_blocking=True)
+                    state["done"] = hi
+
+            engine.on_micro_batch = hook
+            try:
+                yield batch  # the consumer runs the trunk on `batch`: the hook fires once per micro-batch
+            finally:
+                engine.on_micro_batch = None
+            if cur_slot is not None:  # the consumer's work on the buffer `batch` lives in has been enqueued
+                released[cur_slot] = torch.cuda.Event()
+                released[cur_slot].record(main)
+            cur_slot = slot
+            with torch.cuda.stream(copy_stream):
+                if state["done"] < total:  # (the consumer did not run the trunk, or ran fewer micro-batches)
+                    nxt_dev[state["done"]:].copy_(nxt_host[state["done"]:], non_blocking=True)
+                ev2 = torch.cuda.Event()
+                ev2.record(copy_stream)
+            cur = (nxt_dev, ev2)
+        else:
+            nxt = upload(nxt_host) if nxt_host is not None else None
+            yield batch
+            if cur_slot is not None:
+                released[cur_slot] = torch.cuda.Event()
+                released[cur_slot].record(main)
+                cur_slot = None
+            cur = nxt
 
 
 def _accumulate_moments(images, model, batch_size, dims, next_loader=None):
@@ -126,7 +183,7 @@ def _accumulate_moments(images, model, batch_size, dims, next_loader=None):
         for pack in images.groups():
             mom.update(_batch_features(pack, model, dims))
         return mom
-    for batch in _prefetched(images, model.engine.device):
+    for batch in _prefetched(images, model.engine.device, model.engine):
         if len(batch) != batch_size:
             raise ValueError("calculate_activation_statistics: batch of %d, expected %d (drop_last=True, "
                              "fid_score.py:216)" % (len(batch), batch_size))

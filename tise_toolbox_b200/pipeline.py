@@ -132,9 +132,7 @@ class RealismJob:
             buf = staging(nslot, next_pinned)
             if self._slot_done[nslot] is not None:
                 self._copy_stream.wait_event(self._slot_done[nslot])
-            if self._progress is None:
-                self._progress = torch.cuda.Event()
-                self.e.set_progress_event(self._progress, 17)
+            self._progress = self.e.progress_event()
             total = int(next_pinned.shape[0])
             state = {"done": 0}
 

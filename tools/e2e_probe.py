@@ -141,5 +141,3 @@ for pace in (False, True, False, True):
     job = mk()
     job.pace_h2d = pace
     timed(full, "from host + read-back, paced H2D = %s" % pace)
-    if not pace:
-        eng.set_progress_event(None)
