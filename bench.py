@@ -320,7 +320,9 @@ def run_reference(args, rank):
     if rank != 0:
         return
     if not os.environ.get("TISE_BENCH_CHILD"):  # fresh interpreter + timeout + one retry (run_isolated)
-        out, err = run_isolated([a for a in sys.argv[1:]], timeout_s=600)
+        per_step = max(50, args.ref_step // 50 * 50)
+        budget = int(max(240, (args.steps + max(args.warmup, 0)) * per_step / 30.0 * 1.5 + 90))  # ~30 img/s worst case seen
+        out, err = run_isolated([a for a in sys.argv[1:]], timeout_s=budget)
         if out is None:
             _emit(json.dumps({"impl": "reference", "unavailable": "reference arm failed twice: %s" % err}))
         else:
