@@ -143,6 +143,20 @@ typedef struct {
   int64_t blocks;           /* 8 x 8 blocks of all components (whole MCUs) */
 } tise_jpeg_info;
 int tise_jpeg_probe(const uint8_t* h_file, int64_t file_bytes, tise_jpeg_info* info);
+
+/* ---- host-side ingest helpers (no device code; callable without a GPU) --------------------
+ * What img_data.py:19-35's Dataset + DataLoader workers do per file from Python, done per decode GROUP in one call each,
+ * on `n_threads` host threads, so that a foreign-function caller holds no interpreter lock meanwhile:
+ *   tise_file_sizes  stat() of every path (sizes[i] = -1 and TISE_ERR_INVALID if one is missing / not a regular file);
+ *   tise_read_files  file i -> dst + offsets[i] (sizes[i] bytes, as returned above; dst is typically pinned memory);
+ *                    on failure *failed_index names a file and the call returns TISE_ERR_INVALID;
+ *   tise_probe_many  tise_png_probe, else (use_jpeg) tise_jpeg_probe on every staged file:
+ *                    kind[i] = 1 PNG / 2 JPEG the device decoders handle / 0 anything else, hw[i] = {height, width}. */
+int tise_file_sizes(const char* const* paths, int n, int64_t* sizes, int n_threads);
+int tise_read_files(const char* const* paths, const int64_t* offsets, const int64_t* sizes, int n, uint8_t* dst, int n_threads,
+                    int* failed_index);
+int tise_probe_many(const uint8_t* h_base, const int64_t* offsets, const int64_t* sizes, int n, int use_jpeg,
+                    tise_png_info* png_infos, tise_jpeg_info* jpeg_infos, int8_t* kind, int32_t* hw, int n_threads);
 size_t tise_jpeg_decode_workspace_bytes(const tise_jpeg_info* infos, int n);
 int tise_jpeg_decode(tise_ctx* ctx, const uint8_t* h_files, const uint8_t* d_files, const int64_t* h_file_off,
                      const int64_t* h_file_bytes, int n, uint8_t* d_out, const int64_t* h_out_off,

@@ -366,3 +366,62 @@ def test_png_adam7_interlaced(host):
         st, got = _decode(host, blob)
         assert st == 0, (name, st)
         assert np.array_equal(got, np.asarray(Image.open(io.BytesIO(blob)).convert("RGB"))), name
+
+
+def test_host_ingest_helpers_match_per_file_calls(tmp_path):
+    """tise_file_sizes / tise_read_files / tise_probe_many (one call per decode group, host threads inside the library)
+    against os.path.getsize, plain reads and the per-file probes; a missing file is reported, not skipped."""
+    from tise_toolbox_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    paths, blobs = [], []
+    for i in range(37):
+        kind = i % 3
+        if kind == 0:
+            blob = png_bytes(smooth_image(rng, 20 + i, 30 + 2 * i, 3))
+        elif kind == 1:
+            b = io.BytesIO()
+            Image.fromarray(smooth_image(rng, 24 + i, 40, 3)).save(b, "JPEG", quality=85)
+            blob = b.getvalue()
+        else:
+            blob = bytes(rng.integers(0, 256, 100 + i, dtype=np.uint8))  # neither container
+        p = tmp_path / ("f%02d.bin" % i)
+        p.write_bytes(blob)
+        paths.append(str(p))
+        blobs.append(blob)
+    n = len(paths)
+    arr = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+    sizes = np.zeros(n, dtype=np.int64)
+    assert lib.tise_file_sizes(arr, n, sizes.ctypes.data, 4) == 0
+    assert sizes.tolist() == [len(b) for b in blobs]
+    offs = np.zeros(n, dtype=np.int64)
+    offs[1:] = np.cumsum((sizes + 15) // 16 * 16)[:-1]
+    buf = np.zeros(int(offs[-1] + sizes[-1]) + 16, dtype=np.uint8)
+    failed = C.c_int(-1)
+    assert lib.tise_read_files(arr, offs.ctypes.data, sizes.ctypes.data, n, buf.ctypes.data, 4, C.byref(failed)) == 0
+    for i in range(n):
+        assert bytes(buf[offs[i]:offs[i] + sizes[i]]) == blobs[i]
+    pinfos, jinfos = (_lib.PngInfo * n)(), (_lib.JpegInfo * n)()
+    kind = np.full(n, -1, dtype=np.int8)
+    hw = np.zeros((n, 2), dtype=np.int32)
+    assert lib.tise_probe_many(buf.ctypes.data, offs.ctypes.data, sizes.ctypes.data, n, 1, pinfos, jinfos, kind.ctypes.data,
+                               hw.ctypes.data, 3) == 0
+    for i in range(n):
+        one_p, one_j = _lib.PngInfo(), _lib.JpegInfo()
+        if lib.tise_png_probe(blobs[i], len(blobs[i]), C.byref(one_p)) == 0 and one_p.supported:
+            assert kind[i] == 1 and tuple(hw[i]) == (one_p.height, one_p.width) and pinfos[i].idat_bytes == one_p.idat_bytes
+        elif lib.tise_jpeg_probe(blobs[i], len(blobs[i]), C.byref(one_j)) == 0 and one_j.supported:
+            assert kind[i] == 2 and tuple(hw[i]) == (one_j.height, one_j.width)
+        else:
+            assert kind[i] == 0
+    assert set(kind.tolist()) == {0, 1, 2}
+    assert lib.tise_probe_many(buf.ctypes.data, offs.ctypes.data, sizes.ctypes.data, n, 0, pinfos, jinfos, kind.ctypes.data,
+                               hw.ctypes.data, 1) == 0 and 2 not in kind.tolist()  # JPEG decode switched off
+    # a missing file
+    arr2 = (C.c_char_p * 2)(os.fsencode(paths[0]), os.fsencode(str(tmp_path / "nope.png")))
+    s2 = np.zeros(2, dtype=np.int64)
+    assert lib.tise_file_sizes(arr2, 2, s2.ctypes.data, 2) != 0 and s2[1] == -1 and s2[0] == len(blobs[0])
+    s2[1] = 10
+    assert lib.tise_read_files(arr2, np.array([0, 4096], dtype=np.int64).ctypes.data, s2.ctypes.data, 2,
+                               np.zeros(8192, dtype=np.uint8).ctypes.data, 2, C.byref(failed)) != 0 and failed.value == 1

@@ -61,6 +61,11 @@ _SIGNATURES = {
     "tise_jpeg_decode_workspace_bytes": (C.c_size_t, [C.POINTER(JpegInfo), C.c_int]),
     "tise_jpeg_decode": (C.c_int, [c_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
+    "tise_file_sizes": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_void_p, C.c_int]),
+    "tise_read_files": (C.c_int, [C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                  C.POINTER(C.c_int)]),
+    "tise_probe_many": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(PngInfo), C.POINTER(JpegInfo),
+                                  C.c_void_p, C.c_void_p, C.c_int]),
     "tise_upsample_bilinear_f32": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                              c_stream]),
     "tise_channel_affine_f32": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
