@@ -83,7 +83,9 @@ class RealismJob:
 
     def step_from_host(self, pinned: torch.Tensor, next_pinned: Optional[torch.Tensor] = None) -> torch.Tensor:
         """End-to-end step from pinned host memory.  The H2D copy runs on a private copy stream into one of two
-        staging buffers; passing the following batch as ``next_pinned`` lets its copy overlap this step's compute."""
+        staging buffers; passing the following batch as ``next_pinned`` lets its copy overlap this step's compute (paced:
+        one chunk per micro-batch, released when the trunk leaves its HBM-bound front).  The caller keeps both host
+        batches alive and unmodified until the step that consumes them has been issued."""
         dev = self.e.device
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=dev)
