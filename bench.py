@@ -383,6 +383,19 @@ def _emit(text: str) -> None:
     os.write(_RESULT_FD, (text + "\n").encode())
 
 
+def ramp_sizes(n, batch, ramp=(256, 768)):
+    """Batch sizes of a run over n images: short first batches (while more than twice their size is left), then `batch`."""
+    sizes, left = [], int(n)
+    for want in ramp:
+        if left > 2 * want:
+            sizes.append(want)
+            left -= want
+    while left > 0:
+        sizes.append(min(batch, left))
+        left -= sizes[-1]
+    return sizes
+
+
 def fixed_size_run(eng, host, n_fixed, rank, world, real_stats, barrier, batch=2048):
     """north_star's target: `n_fixed` images (this rank's contiguous shard of them) from pinned host memory through
     H2D -> resize -> trunk -> moments + IS* sums -> ONE packed all-reduce -> (rank 0) Frechet distance against the
@@ -393,14 +406,7 @@ def fixed_size_run(eng, host, n_fixed, rank, world, real_stats, barrier, batch=2
     lo, hi = shard_range(n_fixed, rank, world)
     # ramp-up: the first H2D copy cannot hide behind compute, so the first batches are short (256, 768 images) -- with 8
     # ranks pulling from one host at once a 2048-image first copy alone cost ~20 ms of a 95 ms run
-    sizes, left = [], hi - lo
-    for want in (256, 768):
-        if left > 2 * want:
-            sizes.append(want)
-            left -= want
-    while left > 0:
-        sizes.append(min(batch, left))
-        left -= sizes[-1]
+    sizes = ramp_sizes(hi - lo, batch)
     offs = [0]
     for n in sizes:
         offs.append(offs[-1] + n)

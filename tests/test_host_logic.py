@@ -301,3 +301,26 @@ def test_build_is_serialised_across_processes(tmp_path):
     outs = [p.communicate(timeout=600)[0].strip() for p in procs]
     assert all(p.returncode == 0 for p in procs) and all(o.endswith("libtise_b200.so") for o in outs), outs
     assert os.path.getmtime(build.LIB) == before  # nobody rebuilt a fresh library
+
+
+def test_bench_helpers_ramp_and_isolated_legs():
+    """bench.py host logic: the fixed-size run's batch ramp covers the shard exactly, and a CPU leg that fails in its
+    fresh interpreter is reported (after the retry) instead of raising or hanging the GPU arm."""
+    import importlib.util
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    saved_fd1 = os.dup(1)  # bench.py points fd 1 at fd 2 at import time (its stdout carries exactly one JSON line)
+    try:
+        spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+        bench = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bench)
+    finally:
+        os.dup2(saved_fd1, 1)
+        os.close(saved_fd1)
+    for n in (1, 255, 600, 3750, 30000):
+        sizes = bench.ramp_sizes(n, 2048)
+        assert sum(sizes) == n and all(0 < s <= 2048 for s in sizes)
+    assert bench.ramp_sizes(3750, 2048) == [256, 768, 2048, 678] and bench.ramp_sizes(600, 2048) == [256, 344]
+    out, err = bench.run_isolated(["--child", "cpu_leg:/nonexistent/spec.pt"], timeout_s=120, tries=2)
+    assert out is None and "exit code" in err
