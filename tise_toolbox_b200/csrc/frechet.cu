@@ -573,7 +573,6 @@ constexpr int TR_PITCH = TR_THREADS * TR_CS;    // d <= 2048
 constexpr int TR_RS = 10;                       // local rows in shared memory
 constexpr int TR_RR = 4;                        // local rows in registers
 constexpr int TR_ROWS = TR_RS + TR_RR;
-constexpr int TR_MAX_CTAS = 256;                // flag words reserved in the workspace
 
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -1093,7 +1092,17 @@ static int frechet_once(tise_ctx* ctx, const double* mu1, const double* s1, cons
   if (legacy < 0) legacy = getenv("TISE_FRECHET_LEGACY") ? atoi(getenv("TISE_FRECHET_LEGACY")) : 0;
   static int resident = -1;
   if (resident < 0) resident = getenv("TISE_FRECHET_RESIDENT") ? atoi(getenv("TISE_FRECHET_RESIDENT")) : 1;
-  if (!legacy && resident && d >= (resident > 1 ? 3 : 512) && d <= TR_PITCH && d <= TR_ROWS * ctx->num_sms) {
+  bool use_resident = !legacy && resident && d >= (resident > 1 ? 3 : 512) && d <= TR_PITCH && d <= TR_ROWS * ctx->num_sms;
+  if (use_resident) {  // every CTA of the kernel must be co-resident (it spins on its peers' values): ask the runtime first
+    int per_sm = 0;
+    const void* probe = (const void*)tri_resident_kernel<false>;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe, TR_THREADS, (size_t)TR_RS * TR_PITCH * sizeof(double)) !=
+            cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      use_resident = false;  // (a device with less shared memory per SM: the L2-resident kernel below)
+    }
+  }
+  if (use_resident) {
     // the whole matrix in shared memory + registers of one cooperative launch (one CTA per SM), see tri_resident_kernel
     uint4* xbuf = (uint4*)vbuf;    // 2 buffers x d x {y, column} LL words = 64 d bytes (one vector area of the workspace)
     TISE_CUDA(ctx, cudaMemsetAsync(xbuf, 0, (size_t)4 * d * sizeof(uint4), st));  // epochs restart at 1 in every call
@@ -1105,9 +1114,13 @@ static int frechet_once(tise_ctx* ctx, const double* mu1, const double* s1, cons
     if (dbg & 64) TISE_CUDA(ctx, cudaMalloc(&d_dbg, (size_t)ctx->num_sms * 8 * sizeof(unsigned long long)));
     void* args[] = {(void*)&M, (void*)&dd, (void*)&xbuf, (void*)&diag, (void*)&off, (void*)&d_dbg, (void*)&abl};
     const void* fn = (dbg & 64) ? (const void*)tri_resident_kernel<true> : (const void*)tri_resident_kernel<false>;
-    TISE_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(ctx->num_sms), dim3(TR_THREADS), args,
-                                               (size_t)TR_RS * TR_PITCH * sizeof(double), st));
-    if (dbg & 64) {  // cycles per column of the five phases, averaged over the CTAs
+    const cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(ctx->num_sms), dim3(TR_THREADS), args,
+                                                       (size_t)TR_RS * TR_PITCH * sizeof(double), st);
+    if (le != cudaSuccess) {  // e.g. SMs reserved by another client: cooperative launch too large -> L2-resident kernel
+      cudaGetLastError();
+      if (d_dbg) cudaFree(d_dbg);
+      use_resident = false;
+    } else if (dbg & 64) {  // cycles per column of the five phases, averaged over the CTAs
       std::vector<unsigned long long> h((size_t)ctx->num_sms * 8);
       TISE_CUDA(ctx, cudaStreamSynchronize(st));
       TISE_CUDA(ctx, cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -1119,7 +1132,10 @@ static int frechet_once(tise_ctx* ctx, const double* mu1, const double* s1, cons
       fprintf(stderr, "tri_resident d=%d cycles/column: wait flags %.0f | load y,row + p.v %.0f | w, row, reflector %.0f | pass %.0f | "
                       "y reduce + publish %.0f\n", d, sum[0] / den, sum[1] / den, sum[2] / den, sum[3] / den, sum[4] / den);
     }
-    ctx->launches++;
+    if (use_resident) ctx->launches++;
+  }
+  if (use_resident) {
+    // done
   } else if (!legacy && d > 2) {  // one cooperative launch for all columns, matrix in L2
     unsigned* bar = (unsigned*)(scal + FR_NSLOTS);
     TISE_CUDA(ctx, cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
